@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Headline benchmark: walker*star log-likelihood terms per second of the ensemble lnprob path.
+
+Workload (BASELINE.json configs[4], the one the metric's 1/2/4/8-GPU sweep is quoted on; it fits one
+GPU): synthetic 10^7-star cluster x 1024 walkers, ModelFit (Lynden-Bell rotation + Plummer
+dispersion), fixed centre, float64.  One *step* = one emcee iteration of the red/blue stretch move =
+two half-ensemble lnprob calls of 512 walkers each over every star = 1.024e10 terms.  With N > 1
+GPUs the SAME catalogue is star-sharded over the ranks (strong scaling) and the per-walker partial
+sums are all-reduced over NCCL after every call.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0.  `value` is device-timed (CUDA events, inputs resident in HBM);
+`e2e` goes through the public host-buffer API (H2D of theta and D2H of lnprob inside the timed
+region); `roofline` and `cpu_baseline` are described in DESIGN.md.
+"""
+import argparse
+import json
+import multiprocessing
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'walker*star lnlike terms/s'
+UNIT = 'terms/s'
+SEED = 4
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--stars', type=int, default=10_000_000)
+    ap.add_argument('--walkers', type=int, default=1024)
+    ap.add_argument('--math', default='fast', choices=['fast', 'plain'])
+    ap.add_argument('--free-centre', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-sample-stars', type=int, default=250_000)
+    return ap.parse_args()
+
+
+def workload_config(args):
+    return {
+        'workload': 'C5: synthetic {0:.0e}-star cluster x {1} walkers, ModelFit {2} centre, star-sharded'.format(
+            args.stars, args.walkers, 'free' if args.free_centre else 'fixed'),
+        'n_stars': args.stars, 'n_walkers': args.walkers, 'walkers_per_call': args.walkers // 2,
+        'calls_per_step': 2, 'model': 'ModelFit', 'free_centre': bool(args.free_centre), 'math': args.math,
+        'seed': SEED,
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle (literal NumPy restatement of the reference), one lnprob call per walker,
+# fanned out over a process pool exactly like analysis/runner.py:398-403
+# ----------------------------------------------------------------------------------------------
+_CPU_ORACLE = None
+
+
+def _cpu_init(columns, parameters_table, fixed):
+    global _CPU_ORACLE
+    from oracle import reference_np as ref
+    params = ref.default_params(parameters_table)
+    for p in params:
+        if p.name in fixed:
+            p.fixed = True
+            p.value = fixed[p.name]
+    _CPU_ORACLE = ref.OracleModelFit(columns, parameters=params)
+
+
+def _cpu_one(theta_row):
+    return _CPU_ORACLE.lnprob(theta_row)
+
+
+def usable_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_run(args, steps, warmup):
+    """Times the CPU reference path on a bounded sample of the workload.  Returns a dict with
+    terms/s for the pool (all cores) and for a single process."""
+    from mcmc_dynamics_b200 import synthetic
+    n_sample = min(args.stars, args.cpu_sample_stars)
+    columns, truth = synthetic.mock_cluster(n_sample, seed=SEED, as_reader=False)
+    fixed = {} if args.free_centre else {'ra_center': truth['ra_center'], 'dec_center': truth['dec_center']}
+    names = [n for n in ('v_sys', 'sigma_max', 'a', 'v_maxx', 'ra_center', 'dec_center', 'v_maxy', 'r_peak')
+             if n not in fixed]
+    cores = usable_cores()
+    per_step = 4 * cores
+    theta = synthetic.initial_ball(truth, names, per_step, seed=5)
+    _cpu_init(columns, 'model', fixed)
+    # single process, n_threads = 1 (the reference default)
+    t0 = time.perf_counter()
+    for row in theta[:2]:
+        _cpu_one(row)
+    single = 2 * n_sample / (time.perf_counter() - t0)
+    ctx = multiprocessing.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        for _ in range(warmup):
+            pool.map(_cpu_one, list(theta[:cores]))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_cpu_one, list(theta))
+        elapsed = time.perf_counter() - t0
+    value = steps * per_step * n_sample / elapsed
+    return {
+        'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+        'sample': '{0} lnprob calls (one walker each, process pool of {1}) over a {2}-star catalogue from the workload generator, '
+                  'x{3} steps; NumPy oracle = literal restatement of the reference'.format(per_step, cores, n_sample,
+                                                                                           steps),
+        'single_process_value': single, 'ms_per_step': 1e3 * elapsed / steps,
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([c.strip() for c in out.stdout.strip().splitlines()[0].split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.15)
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=10)
+
+    def summary(self):
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for row in self.rows:
+            try:
+                sm.append(float(row[0]))
+                smax.append(float(row[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, flag in zip(names, row[3:7]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(np.max(smax)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def gpu_run(args):
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # before CUDA is initialised: the pool forks
+        cpu_baseline = cpu_reference_run(args, steps=3, warmup=1)
+
+    import torch
+    import torch.distributed as dist
+    from mcmc_dynamics_b200 import _native, synthetic, sharded
+    from mcmc_dynamics_b200.analysis import ModelFit
+
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the B200 path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+
+    # ---- the workload: same catalogue on every rank, each keeps its contiguous shard ----------
+    columns, truth = synthetic.mock_cluster(args.stars, seed=SEED, as_reader=False)
+    shard = sharded.shard_columns(columns, rank, world)
+    n_shard = len(shard['v'])
+    del columns
+    model = ModelFit(synthetic.reader_from_columns(shard), device=local_rank, math_mode=args.math)
+    if not args.free_centre:
+        model.parameters['ra_center'].set(value=truth['ra_center'], fixed=True)
+        model.parameters['dec_center'].set(value=truth['dec_center'], fixed=True)
+    else:
+        model.parameters['ra_center'].set(value=truth['ra_center'])
+        model.parameters['dec_center'].set(value=truth['dec_center'])
+    packed = model.pack()
+    like = sharded.ShardedLikelihood(model)
+    info = packed.info()
+
+    half = args.walkers // 2
+    theta_host = synthetic.initial_ball(truth, model.fitted_parameters, args.walkers, seed=5)
+    halves_host = [np.ascontiguousarray(theta_host[:half]), np.ascontiguousarray(theta_host[half:])]
+    halves_dev = [torch.as_tensor(h, device=device) for h in halves_host]
+
+    # inputs smaller than ~2x L2 are evicted between timed steps by writing a 512 MiB buffer
+    bytes_resident = n_shard * info['bytes_per_star']
+    flush = bytes_resident < (256 << 20)
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=device) if flush else None
+
+    def one_step():
+        out = None
+        for th in halves_dev:
+            out = like.lnprob_tensor(th)
+        return out
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    sync_all()
+
+    lib = _native.load_library()
+    launches_before = packed.info()['launches']
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        sync_all()
+        wall0 = time.perf_counter()
+        for k in range(args.steps):
+            if flush:
+                flush_buf.fill_(k & 0xff)
+            starts[k].record()
+            result = one_step()
+            stops[k].record()
+        sync_all()
+        wall = time.perf_counter() - wall0
+    launches = packed.info()['launches'] - launches_before
+    device_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+    t = torch.tensor([device_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    device_ms = float(t.item())
+    ms_per_step = device_ms / args.steps
+    terms_per_step = float(args.walkers) * float(args.stars)
+    value = terms_per_step / (ms_per_step * 1e-3)
+    assert torch.isfinite(result).all(), 'benchmark theta must not be prior-rejected'
+
+    # ---- dominant kernel alone: per-launch duration on the launching stream --------------------
+    k_starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k_stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sync_all()
+    for k in range(args.steps):
+        if flush:
+            flush_buf.fill_(k & 0xff)
+        k_starts[k].record()
+        packed.lnprob_partial_tensor(halves_dev[k & 1])
+        k_stops[k].record()
+    torch.cuda.synchronize(device)
+    kernel_ms = float(np.mean([s.elapsed_time(e) for s, e in zip(k_starts, k_stops)]))
+
+    # ---- end to end through the host-buffer API -------------------------------------------------
+    def e2e_step():
+        out = None
+        for th in halves_host:
+            out = model.lnprob(th) if world == 1 else like.lnprob(th)
+        return out
+
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_out = e2e_step()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = terms_per_step * args.steps / e2e_s
+    # the two paths must agree bit for bit at N = 1 (same kernel), closely otherwise
+    assert np.allclose(e2e_out, result.cpu().numpy(), rtol=1e-12, atol=0)
+
+    # ---- roofline denominators, measured in this process ----------------------------------------
+    fp64 = np.zeros(2)
+    rc = lib.mcd_measure_fp64_peak(local_rank, _native.as_double_ptr(fp64[0:1]), _native.as_double_ptr(fp64[1:2]))
+    fp64_peak = float(fp64[0]) if rc == 0 else None
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    hbm_source = 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+
+    terms_per_launch = float(half) * float(n_shard)
+    flops_per_launch = terms_per_launch * info['flops_per_term']
+    achieved_tflops = flops_per_launch / (kernel_ms * 1e-3) / 1e12
+    bytes_per_launch = float(n_shard) * info['bytes_per_star'] + half * (info['n_theta'] + 1) * 8.0
+    achieved_gbs = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    # FP64-pipe instructions issued per term by the kernel (SASS count): utilisation of
+    # the pipe = instructions/s over the measured DFMA issue rate
+    pipe_instr = {'fast': {False: 20, True: 28}, 'plain': {False: None, True: None}}[args.math][bool(args.free_centre)]
+    pipe_frac = None
+    if fp64_peak and pipe_instr:
+        pipe_frac = (terms_per_launch * pipe_instr / (kernel_ms * 1e-3)) / (fp64_peak * 1e12 / 2.0)
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': dict(workload_config(args), stars_per_gpu=n_shard, collective='nccl all_reduce(sum) of %d f64 per call'
+                       % half if world > 1 else 'none',
+                       l2='flushed between steps (512 MiB write)' if flush else 'inputs larger than L2 (%.0f MB per GPU)'
+                       % (bytes_resident / 1e6)),
+        'steps_per_s': 1e3 / ms_per_step,
+        'wall_ms_per_step': 1e3 * wall / args.steps,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(2 * half * info['n_theta'] * 8),
+                'd2h_bytes_per_step': int(2 * half * 8), 'ms_per_step': 1e3 * e2e_s / args.steps,
+                'api': 'ModelFit.lnprob(theta ndarray) -> C ABI mcd_lnprob (host buffers)' if world == 1 else
+                       'ShardedLikelihood.lnprob(theta ndarray): pinned H2D, shard kernel, NCCL all_reduce, D2H'},
+        'gpu_launches': int(launches),
+        'clocks': clocks.summary(),
+        'roofline': {
+            'bound': 'fp64', 'achieved': achieved_tflops, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+            'frac': (achieved_tflops / fp64_peak) if fp64_peak else None, 'traffic': None,
+            'kernel': 'mcd::lnlike_kernel<RADIAL,%s,BG_NONE,%s>' % ('FREE' if args.free_centre else 'FIXED',
+                                                                    args.math.upper()),
+            'kernel_ms': kernel_ms, 'terms_per_launch': terms_per_launch,
+            'nominal_flops_per_term': info['flops_per_term'],
+            'peak_source': 'mcd_measure_fp64_peak: DFMA chains measured in this run (MEASURED_PEAKS.json has no FP64 '
+                           'figure)',
+            'fp64_pipe_instr_per_term': pipe_instr, 'fp64_pipe_frac': pipe_frac,
+            'hbm': {'achieved': achieved_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved_gbs / hbm_peak,
+                    'bytes_per_star': info['bytes_per_star'], 'peak_source': hbm_source},
+            'grid': [info['last_grid_x'], info['last_grid_y']], 'block': info['last_block'],
+            'walkers_per_cta': info['last_walker_tile'],
+        },
+    }
+    if cpu_baseline is not None:
+        line['cpu_baseline'] = cpu_baseline
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def reference_run(args):
+    """`--impl reference`: the reference's CPU implementation of the path (the NumPy oracle port: the
+    reference itself needs astropy/emcee/asteval/lmfit, none of which exist in this image) on all
+    host cores.  Rank 0 only."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    res = cpu_reference_run(args, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': res['value'], 'unit': UNIT,
+        'n_gpus': int(os.environ.get('WORLD_SIZE', str(args.gpus))), 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': res['ms_per_step'], 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args),
+        'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample', 'single_process_value')},
+        'e2e': {'value': res['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        reference_run(args)
+    else:
+        gpu_run(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,172 @@
+/*
+ * mcd_b200.h -- C ABI of the B200-native mcmc-dynamics likelihood path.
+ *
+ * One shared library (libmcd_b200.so, built from mcmc_dynamics_b200/csrc/ by
+ * __graft_entry__.build()) replaces the per-walker Python likelihood of the
+ * reference with one batched CUDA launch per ensemble call.  Plain pointers and
+ * sizes only: no torch, numpy or C++ types cross this boundary.  Every entry
+ * point names the reference interface it stands in for (paths relative to
+ * /root/reference/mcmc_dynamics/).
+ *
+ * Conventions
+ *   - return value 0 = success, negative = error; mcd_last_error() then gives a
+ *     message (thread-local).  No C++ exception crosses the ABI.
+ *   - a handle owns all of its device memory.  Host columns passed to
+ *     mcd_pack_create() are copied; the caller keeps ownership.
+ *   - a handle is thread-compatible: use it from one host thread at a time.
+ *   - *_device entry points are asynchronous on the given CUDA stream
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream); results
+ *     are valid after that stream is synchronised.  Entry points without the
+ *     suffix take HOST buffers and return when the result is in `out`.
+ *   - theta is row-major float64 [n_walkers][n_theta]: exactly the array emcee
+ *     hands to a vectorised log_prob_fn (analysis/runner.py:403, 162-175).
+ */
+#ifndef MCD_B200_H
+#define MCD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCD_ABI_VERSION 1
+
+/* Rotation / dispersion model.
+ *   CONSTANT: analysis/constant.py:52-111  (ConstantFit.rotation_model / dispersion_model)
+ *   RADIAL  : analysis/model.py:93-180     (ModelFit: Lynden-Bell rotation, Plummer dispersion) */
+enum { MCD_ROT_CONSTANT = 0, MCD_ROT_RADIAL = 1 };
+
+/* Background treatment.
+ *   NONE         : analysis/runner.py:264-271
+ *   FIXED_PMEMBER: analysis/runner.py:272-286 (lnlike_background[N], pmember[N] columns)
+ *   FIXED_DENSITY: analysis/model.py:586-623  (ModelFitConstantBackground: lnlike_background[N],
+ *                  m = density/(density+f_back))
+ *   GAUSSIAN     : analysis/constant.py:326-364, analysis/model.py:414-456 (fitted v_back, sigma_back, f_back) */
+enum { MCD_BG_NONE = 0, MCD_BG_FIXED_PMEMBER = 1, MCD_BG_FIXED_DENSITY = 2, MCD_BG_GAUSSIAN = 3 };
+
+/* Model parameter slots: union of MODEL_PARAMETERS of the five classes
+ * (constant.py:19,256; model.py:71,354,526). */
+enum {
+    MCD_P_V_SYS = 0, MCD_P_SIGMA_MAX, MCD_P_V_MAXX, MCD_P_V_MAXY, MCD_P_RA_CENTER, MCD_P_DEC_CENTER,
+    MCD_P_A, MCD_P_R_PEAK, MCD_P_V_BACK, MCD_P_SIGMA_BACK, MCD_P_F_BACK, MCD_NPARAM
+};
+
+#define MCD_MAX_THETA 16       /* free parameters per walker (the largest shipped config has 11) */
+
+/* Arithmetic variant of the kernels.
+ *   FAST : division-free restructuring, MUFU-seeded Newton reciprocals, logs taken of running
+ *          products; FP64 throughout (default).
+ *   PLAIN: the same per-star formulas with the compiler's div / sqrt / log / exp; kept to
+ *          A/B the restructuring on the device. */
+enum { MCD_MATH_FAST = 0, MCD_MATH_PLAIN = 1 };
+
+/* What mcd_pack_create() compiles: a model, its parameter routing and the star columns.
+ * Stands in for the per-call work of Runner.fetch_parameter_values (analysis/runner.py:143-180),
+ * the inspect-based kwargs routing (constant.py:140-147, model.py:208-215) and the astropy unit
+ * conversions of SURVEY.md section 3.3, all hoisted out of the sampling loop. */
+typedef struct mcd_pack_desc {
+    int32_t rotation;                 /* MCD_ROT_*                                              */
+    int32_t background;               /* MCD_BG_*                                               */
+    int32_t n_theta;                  /* P: number of free parameters = columns of theta        */
+    int32_t math_mode;                /* MCD_MATH_*                                             */
+    int64_t n_stars;                  /* N (of this shard)                                      */
+    const double *ra;                 /* [N] degrees  (runner.py:75-81)                         */
+    const double *dec;                /* [N] degrees                                            */
+    const double *v;                  /* [N] km/s                                               */
+    const double *verr;               /* [N] km/s                                               */
+    const double *pmember;            /* [N] or NULL  (runner.py:103)                           */
+    const double *density;            /* [N] or NULL  (constant.py:257, model.py:355,527)       */
+    const double *lnlike_background;  /* [N] or NULL  (runner.py:102, model.py:563)             */
+    int32_t slot[MCD_NPARAM];         /* column of theta that feeds the parameter, or -1: fixed */
+    double fixed_value[MCD_NPARAM];   /* current value (own unit): used when slot < 0; for a    */
+                                      /* sampled ra_center it is the expansion point ra0 of the */
+                                      /* free-centre geometry (any value is valid)              */
+    double unit_scale[MCD_NPARAM];    /* own unit -> km/s | deg | arcmin | 1                    */
+    double lower[MCD_MAX_THETA];      /* box prior of theta column j (parameter.py:691-692)     */
+    double upper[MCD_MAX_THETA];
+    int32_t fixed_prior_ok;           /* 0: a fixed parameter violates its bounds => all -inf   */
+    int32_t device;                   /* CUDA device ordinal                                    */
+    int64_t n_stars_total;            /* N of the whole catalogue when star-sharded, else 0     */
+} mcd_pack_desc;
+
+typedef struct mcd_handle mcd_handle;
+
+typedef struct mcd_info {
+    int64_t n_stars;
+    int32_t n_theta;
+    int32_t n_columns;            /* device columns read per star by the lnlike kernel          */
+    int32_t bytes_per_star;       /* = 8 * n_columns: algorithmic HBM bytes per star per launch */
+    int32_t flops_per_term;       /* nominal FP64 operations per (walker, star) term*/
+    int32_t free_centre;          /* 1 if ra_center or dec_center is sampled                    */
+    int32_t sm_count;
+    int32_t last_grid_x, last_grid_y, last_block;   /* geometry of the most recent launch       */
+    int32_t last_walker_tile;
+    int64_t launches;             /* kernels launched through this handle so far                */
+} mcd_info;
+
+int mcd_abi_version(void);
+const char *mcd_last_error(void);
+
+/* Model construction: Runner.__init__ + ConstantFit/ModelFit.__init__ (analysis/runner.py:40-106,
+ * constant.py:24-50, model.py:76-91) as far as device state is concerned. */
+int mcd_pack_create(const mcd_pack_desc *desc, mcd_handle **out);
+/* Re-route parameters (fixed <-> free, new fixed values, bounds, math mode, background mode) on
+ * the star columns already resident on the device: what `parameters[name].set(...)` between
+ * construction and the run amounts to (bin/run_tests.py:88-93,137-148).  Column pointers and
+ * n_stars of `desc` are ignored / must match. */
+int mcd_pack_reconfigure(mcd_handle *h, const mcd_pack_desc *desc);
+void mcd_destroy(mcd_handle *h);
+int mcd_get_info(const mcd_handle *h, mcd_info *info);
+
+/* lnlike for a whole (half-)ensemble: <Model>.lnlike (constant.py:113-154,293-324;
+ * model.py:182-223,391-456,565-623) called once per walker by emcee in the reference. */
+int mcd_lnlike(mcd_handle *h, const double *theta_host, int32_t n_walkers, double *out_host);
+int mcd_lnlike_device(mcd_handle *h, const double *theta_dev, int32_t n_walkers, double *out_dev, void *stream);
+
+/* lnprob = box prior + lnlike with exact -inf for rejected walkers: Runner.lnprob
+ * (analysis/runner.py:288-306) with Runner.lnprior (runner.py:182-217) fused in. */
+int mcd_lnprob(mcd_handle *h, const double *theta_host, int32_t n_walkers, double *out_host);
+int mcd_lnprob_device(mcd_handle *h, const double *theta_dev, int32_t n_walkers, double *out_dev, void *stream);
+
+/* Star-sharded partial: out = (sum over THIS shard's stars) + (0 | -inf prior mask), so that a
+ * plain sum over shards (NCCL allreduce) yields lnprob.  Replaces walker-parallel
+ * multiprocessing (analysis/runner.py:398-403) at multi-GPU scale. */
+int mcd_lnprob_partial_device(mcd_handle *h, const double *theta_dev, int32_t n_walkers, double *out_dev,
+                              void *stream);
+
+/* Per-star log-likelihood of ONE parameter vector (`no_sum=True`, model.py:565,620-621). */
+int mcd_lnlike_per_star(mcd_handle *h, const double *theta_host, double *out_host /* [N] */);
+int mcd_lnlike_per_star_device(mcd_handle *h, const double *theta_dev, double *out_dev, void *stream);
+
+/* Background precompute: SingleStars.__call__ (background/single_stars.py:42-77) without the
+ * M x N intermediate.  v_bg[M], v[N], verr[N] are HOST arrays; out[N]. */
+int mcd_single_stars_lnlike(int32_t device, const double *v_bg, int64_t m, const double *v, const double *verr,
+                            int64_t n, double sigma_int, double *out_host);
+
+/* Gaussian.__call__ (background/gaussian.py:23-28); v[N], verr[N] HOST arrays, out[N]. */
+int mcd_gaussian_lnlike(int32_t device, const double *v, const double *verr, int64_t n, double mean, double sigma,
+                        double *out_host);
+
+/* Device-resident affine-invariant ensemble sampler (emcee's default red/blue StretchMove(a=2)
+ * as driven by analysis/runner.py:403,416-419).  All state lives on the device. */
+typedef struct mcd_ensemble mcd_ensemble;
+int mcd_ensemble_create(mcd_handle *h, int32_t n_walkers, uint64_t seed, double stretch_a, mcd_ensemble **out);
+void mcd_ensemble_destroy(mcd_ensemble *e);
+/* set positions [n_walkers][n_theta] (host) and compute their lnprob */
+int mcd_ensemble_set_state(mcd_ensemble *e, const double *pos_host);
+/* advance n_steps; if chain_host != NULL store every step: chain [n_steps][n_walkers][n_theta],
+ * lnprob [n_steps][n_walkers]; n_accepted (may be NULL) [n_walkers] cumulative */
+int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_host, double *lnprob_host,
+                     int64_t *n_accepted_host);
+int mcd_ensemble_get_state(mcd_ensemble *e, double *pos_host, double *lnprob_host);
+
+/* Roofline denominators measured on the device the caller is on: dependent-free DFMA chains
+ * (TFLOP/s, FMA = 2) and a streaming read (GB/s). */
+int mcd_measure_fp64_peak(int32_t device, double *tflops_out, double *ms_out);
+int mcd_measure_read_bandwidth(int32_t device, int64_t bytes, double *gbs_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCD_B200_H */

@@ -1,0 +1,5 @@
+from .runner import Runner
+from .constant import ConstantFit, ConstantFitGB
+from .model import ModelFit, ModelFitGB, ModelFitConstantBackground
+
+__all__ = ['Runner', 'ConstantFit', 'ConstantFitGB', 'ModelFit', 'ModelFitGB', 'ModelFitConstantBackground']

@@ -1,0 +1,74 @@
+"""Constant rotation + dispersion fits (``mcmc_dynamics/analysis/constant.py``).
+
+``ConstantFit`` (``constant.py:18-214``): ``v_los = v_sys + v_max sin(theta_i - theta_0)``,
+``sigma_los = sigma_max``.  ``ConstantFitGB`` (``constant.py:250-374``) adds a fitted Gaussian
+background in velocity and the density prior ``m = density / (density + f_back)``.
+The arithmetic lives in ``csrc/mcd_kernels.cu``; these classes only choose the kernel variant.
+"""
+import logging
+import os
+
+import numpy as np
+
+from .. import _native
+from .. import units as u
+from ..parameter import Parameters
+from .runner import Runner
+
+logger = logging.getLogger(__name__)
+_CONFIG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'config')
+
+
+class ConstantFit(Runner):
+    MODEL_PARAMETERS = ['v_sys', 'sigma_max', 'v_maxx', 'v_maxy', 'ra_center', 'dec_center']
+    OBSERVABLES = {'v': u.km_s, 'verr': u.km_s, 'ra': u.deg, 'dec': u.deg}
+
+    parameters_file = os.path.join(_CONFIG, 'constant.json')
+
+    ROTATION = _native.ROT_CONSTANT
+    BACKGROUND = _native.BG_NONE
+
+    def __init__(self, data, parameters=None, **kwargs):
+        self.ra = None
+        self.dec = None
+        if parameters is None:
+            parameters = Parameters().load(self.parameters_file)
+        super(ConstantFit, self).__init__(data=data, parameters=parameters, **kwargs)
+
+    def compute_theta_vmax(self, chain, n_burn, return_samples=False):
+        """(v_max, theta_0) from the (v_maxx, v_maxy) samples (``constant.py:156-214``,
+        ``utils/coordinates/get_amplitude_and_angle.py:10-51``): medians and 16/84 percentiles."""
+        names = self.fitted_parameters
+        samples = np.asarray(chain)[:, n_burn:, :].reshape((-1, len(names)))
+        vx = samples[:, names.index('v_maxx')] if 'v_maxx' in names else np.full(
+            len(samples), self.parameters['v_maxx'].value)
+        vy = samples[:, names.index('v_maxy')] if 'v_maxy' in names else np.full(
+            len(samples), self.parameters['v_maxy'].value)
+        v_max = np.hypot(vx, vy)
+        theta = np.arctan2(vy, vx)
+        # centre the angle distribution on its circular mean before taking percentiles
+        mean = np.arctan2(np.sin(theta).mean(), np.cos(theta).mean())
+        theta = mean + np.angle(np.exp(1j * (theta - mean)))
+        if return_samples:
+            return v_max, theta
+        return {'v_max': np.percentile(v_max, [16, 50, 84]), 'theta_0': np.percentile(theta, [16, 50, 84])}
+
+
+class ConstantFitGB(ConstantFit):
+    """Constant fit plus a Gaussian background population (``constant.py:250-374``)."""
+
+    MODEL_PARAMETERS = ConstantFit.MODEL_PARAMETERS + ['v_back', 'sigma_back', 'f_back']
+    OBSERVABLES = dict(ConstantFit.OBSERVABLES, **{'density': u.dimensionless_unscaled})
+
+    parameters_file = os.path.join(_CONFIG, 'constant_with_background.json')
+
+    BACKGROUND = _native.BG_GAUSSIAN
+
+    def __init__(self, data, parameters=None, **kwargs):
+        self.density = None
+        if parameters is None:
+            parameters = Parameters().load(self.parameters_file)
+        background = kwargs.pop('background', None)
+        if background is not None:
+            logger.error('Class ConstantFitGB does not support additional background components.')
+        super(ConstantFitGB, self).__init__(data=data, parameters=parameters, **kwargs)

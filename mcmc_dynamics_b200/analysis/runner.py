@@ -1,0 +1,377 @@
+"""``Runner``: parent of the kinematic model classes, B200 edition.
+
+Same public protocol as ``mcmc_dynamics/analysis/runner.py:23-443`` -- ``lnprior / lnlike /
+lnprob(values)``, ``get_initials``, ``fetch_parameter_values``, ``fitted_parameters``, ``units``,
+``labels``, ``__call__(n_walkers, n_steps, ...)`` -- but every likelihood evaluation is one CUDA
+launch over all walkers handed in.  ``values`` may be the reference's 1-D vector of the free
+parameters (a float comes back) or an ``[n_walkers, n_free]`` array, which is what emcee passes with
+``vectorize=True`` (an ``[n_walkers]`` float64 array comes back).
+
+There is no CPU implementation of the likelihood in this package.
+"""
+import logging
+import pickle
+
+import numpy as np
+
+from .. import _native
+from .. import pack
+from .. import sampler as _sampler
+from .. import units as u
+from ..background import Gaussian, SingleStars
+from ..data_reader import DataReader
+from ..parameter import Parameters
+
+logger = logging.getLogger(__name__)
+
+
+class Runner(object):
+    """Parent class of the analysis classes (``analysis/runner.py:23-34``).  Subclasses state their
+    ``MODEL_PARAMETERS``, ``OBSERVABLES``, default ``parameters_file`` and which kernel variant
+    (``ROTATION``, ``BACKGROUND``) evaluates their ``lnlike``."""
+
+    MODEL_PARAMETERS = []
+    OBSERVABLES = {'v': u.km_s, 'verr': u.km_s}
+    parameters_file = None
+
+    #: kernel variant (see include/mcd_b200.h)
+    ROTATION = _native.ROT_CONSTANT
+    BACKGROUND = _native.BG_NONE
+
+    def __init__(self, data, parameters, seed=123, background=None, device=0, math_mode='fast', **kwargs):
+        # same checks, in the same order, as analysis/runner.py:55-106
+        assert not kwargs, "Unknown keyword arguments provided: {0}".format(kwargs)
+        np.random.seed(seed)
+
+        self.v = None
+        self.verr = None
+
+        assert isinstance(data, DataReader), "'data' must be instance of {0}".format(DataReader.__module__)
+        self.data = data
+
+        if 'ra' in self.OBSERVABLES or 'dec' in self.OBSERVABLES:
+            if not data.has_coordinates:
+                raise IOError('Missing WCS coordinates of observed data.')
+
+        for required, unit in self.OBSERVABLES.items():
+            assert required in data.data.columns, "Input data missing required column <{0}>".format(required)
+            quantity = u.as_quantity(data.data[required])
+            if quantity.unit.is_unity() and not unit.is_unity():
+                quantity = u.Quantity(quantity.value, unit)
+                logger.warning('Missing units for <{0}> values. Assuming {1}.'.format(required, unit))
+            setattr(self, required, quantity)
+
+        assert isinstance(parameters, Parameters), "'parameters' must be instance of {0}".format(
+            Parameters.__module__)
+        self.parameters = parameters
+
+        missing = set(self.MODEL_PARAMETERS).difference(self.parameters)
+        if missing:
+            raise IOError("Missing required parameter(s): '{0}'".format(missing))
+
+        unused = set(self.parameters).difference(self.MODEL_PARAMETERS)
+        if unused:
+            logger.warning("Superfluous parameter(s) provided: '{0}'".format(unused))
+
+        self.background = background
+        if self.background:
+            assert isinstance(background, (SingleStars, Gaussian)), \
+                "'background' must be an instance of a Background class."
+            if 'pmember' not in self.data.data.columns:
+                logger.error('Inclusion of background population requires prior probabilities for membership.')
+            self.lnlike_background = self.background(self.v, self.verr)
+            self.pmember = data.data['pmember']
+        else:
+            self.lnlike_background = None
+            self.pmember = None
+
+        self.device = int(device)
+        if math_mode not in ('fast', 'plain'):
+            raise ValueError("math_mode must be 'fast' or 'plain'")
+        self.math_mode = math_mode
+        self._packed = None
+        self._packed_signature = None
+
+    # ------------------------------------------------------------------------------------------
+    # introspection (analysis/runner.py:108-141, 662-673)
+    # ------------------------------------------------------------------------------------------
+    @classmethod
+    def default_parameters(cls):
+        if cls.parameters_file is None:
+            raise NotImplementedError
+        return Parameters().load(open(cls.parameters_file))
+
+    @property
+    def n_data(self):
+        return self.data.sample_size
+
+    @property
+    def fitted_parameters(self):
+        return [p for p in self.parameters if not self.parameters[p].fixed]
+
+    @property
+    def n_fitted_parameters(self):
+        return len(self.fitted_parameters)
+
+    @property
+    def units(self):
+        return {p: self.parameters[p].unit for p in self.parameters}
+
+    @property
+    def labels(self):
+        labels = {}
+        for name, parameter in self.parameters.items():
+            labels[name] = parameter.label
+        return labels
+
+    # ------------------------------------------------------------------------------------------
+    # packing
+    # ------------------------------------------------------------------------------------------
+    def _background_mode(self):
+        """Kernel background variant: a plain class switches to the fixed-background mixture when a
+        background object was supplied (analysis/runner.py:272-286)."""
+        if self.BACKGROUND == _native.BG_NONE and self.background is not None:
+            return _native.BG_FIXED_PMEMBER
+        return self.BACKGROUND
+
+    def _star_columns(self):
+        columns = {
+            'ra': u.strip(self.ra, u.deg), 'dec': u.strip(self.dec, u.deg),
+            'v': u.strip(self.v, u.km_s), 'verr': u.strip(self.verr, u.km_s),
+        }
+        mode = self._background_mode()
+        if mode == _native.BG_FIXED_PMEMBER:
+            columns['pmember'] = u.strip(self.pmember, None)
+        if mode in (_native.BG_FIXED_DENSITY, _native.BG_GAUSSIAN):
+            columns['density'] = u.strip(getattr(self, 'density'), None)
+        if mode in (_native.BG_FIXED_PMEMBER, _native.BG_FIXED_DENSITY):
+            columns['lnlike_background'] = u.strip(self.lnlike_background, None)
+        return columns
+
+    def _check_expressions(self):
+        free = set(self.fitted_parameters)
+        for name, par in self.parameters.items():
+            if par.expr is not None and free.intersection(getattr(par, '_expr_deps', [])):
+                raise pack.PackError(
+                    "Parameter '{0}' is constrained by the expression '{1}', which depends on sampled parameters; "
+                    "per-walker constraint expressions are not supported by the device likelihood.".format(
+                        name, par.expr))
+
+    def _descriptor(self):
+        self._check_expressions()
+        return pack.build_descriptor(
+            self.parameters, self.MODEL_PARAMETERS, rotation=self.ROTATION, background=self._background_mode(),
+            columns=self._star_columns() if self._packed is None else {},
+            math_mode=_native.MATH_FAST if self.math_mode == 'fast' else _native.MATH_PLAIN, device=self.device)
+
+    def pack(self):
+        """Upload the star columns (first call) and compile the current parameter routing.  Called
+        lazily by every likelihood entry point; cheap when nothing changed."""
+        signature = (pack.routing_signature(self.parameters, self.MODEL_PARAMETERS), self.math_mode)
+        if self._packed is not None and signature == self._packed_signature:
+            return self._packed
+        desc, keep = self._descriptor()
+        if self._packed is None:
+            self._packed = pack.PackedModel(desc, keep)
+        else:
+            desc.n_stars = self._packed.n_stars
+            self._packed.reconfigure(desc)
+        self._packed_signature = signature
+        return self._packed
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state['_packed'] = None              # device handles do not pickle; re-packed on first use
+        state['_packed_signature'] = None
+        return state
+
+    # ------------------------------------------------------------------------------------------
+    # parameters and priors
+    # ------------------------------------------------------------------------------------------
+    def fetch_parameter_values(self, values):
+        """``analysis/runner.py:143-180``: dictionary name -> quantity for one parameter vector, fixed
+        parameters merged in.  Unlike the reference it does not write the values back into
+        ``self.parameters`` (a side effect no caller relies on, and a hazard for batched calls)."""
+        current_parameters = {}
+        i = 0
+        for name, parameter in self.parameters.items():
+            if parameter.fixed:
+                v = u.Quantity(parameter.value, parameter.unit)
+            else:
+                v = u.Quantity(values[i], parameter.unit)
+                i += 1
+            current_parameters[name] = v
+        assert i == len(values), 'Not all parameters used.'
+        return current_parameters
+
+    def _as_batch(self, values):
+        values = np.asarray(values, dtype=np.float64)
+        scalar = values.ndim == 1
+        theta = np.atleast_2d(values)
+        assert theta.shape[1] == self.n_fitted_parameters, 'Not all parameters used.'
+        return theta, scalar
+
+    def _expression_priors(self):
+        return [(i, self.parameters[name]) for i, name in enumerate(self.fitted_parameters)
+                if self.parameters[name].lnprior is not None]
+
+    def _lnprior_batch(self, theta, parameters_to_ignore=None):
+        """Box prior over every parameter plus optional expression priors (runner.py:206-217,
+        parameter.py:684-705), for all rows of theta at once."""
+        lnp = np.zeros(theta.shape[0], dtype=np.float64)
+        j = 0
+        for name, par in self.parameters.items():
+            if par.fixed:
+                value = par.value
+                if value < par.min or value > par.max:
+                    lnp[:] = -np.inf
+                elif par.lnprior is not None:
+                    lnp += par.evaluate_lnprior(value)
+            else:
+                column = theta[:, j]
+                outside = (column < par.min) | (column > par.max)
+                lnp[outside] = -np.inf
+                if par.lnprior is not None:
+                    for w in np.flatnonzero(~outside & np.isfinite(lnp)):
+                        lnp[w] += par.evaluate_lnprior(column[w])
+                j += 1
+        lnp[~np.isfinite(lnp)] = -np.inf
+        return lnp
+
+    def lnprior(self, values, parameters_to_ignore=None):
+        """``analysis/runner.py:182-217``; accepts one vector or a batch."""
+        theta, scalar = self._as_batch(values)
+        lnp = self._lnprior_batch(theta, parameters_to_ignore)
+        if scalar:
+            return -np.inf if not np.isfinite(lnp[0]) else (0 if lnp[0] == 0 else lnp[0])
+        return lnp
+
+    # ------------------------------------------------------------------------------------------
+    # likelihood: one CUDA launch per call
+    # ------------------------------------------------------------------------------------------
+    def lnlike(self, values):
+        """Log-likelihood without priors (``constant.py:113-154``, ``model.py:182-223`` and the
+        background variants), for one parameter vector or a batch."""
+        theta, scalar = self._as_batch(values)
+        out = self.pack().lnlike(theta)
+        return float(out[0]) if scalar else out
+
+    def lnprob(self, values):
+        """``analysis/runner.py:288-306``: box prior fused into the kernel; walkers outside the prior
+        come back as exactly ``-inf`` without being evaluated."""
+        theta, scalar = self._as_batch(values)
+        out = self.pack().lnprob(theta)
+        if self._has_expression_priors():
+            extra = self._lnprior_batch(theta)
+            with np.errstate(invalid='ignore'):
+                out = np.where(np.isfinite(extra), out + extra, -np.inf)
+        return float(out[0]) if scalar else out
+
+    def _has_expression_priors(self):
+        return any(par.lnprior is not None for par in self.parameters.values())
+
+    def lnprob_tensor(self, theta):
+        """``lnprob`` for an ``[n_walkers, n_free]`` float64 CUDA tensor, asynchronous on the current
+        stream, result stays on the device.  Expression priors are not applied here."""
+        return self.pack().lnprob_tensor(theta)
+
+    # ------------------------------------------------------------------------------------------
+    # sampling
+    # ------------------------------------------------------------------------------------------
+    def get_initials(self, n_walkers):
+        """``analysis/runner.py:308-330``."""
+        initials = np.zeros((n_walkers, self.n_fitted_parameters))
+        i = 0
+        for name, parameter in self.parameters.items():
+            if parameter.fixed:
+                continue
+            else:
+                initials[:, i] = parameter.evaluate_initials(n_walkers)
+            i += 1
+        return initials
+
+    def __call__(self, n_walkers=100, n_steps=500, n_burn=100, n_threads=1, n_out=None, pos=None, lnprob0=None,
+                 plot=False, prefix='sampler', true_values=None, sampler='host', seed=None, **kwargs):
+        """Run the ensemble sampler (``analysis/runner.py:332-443``).
+
+        ``n_threads`` is accepted and ignored: the walker-parallel process pool of the reference is
+        replaced by the batched launch.  ``sampler='host'`` runs an emcee-compatible stretch-move
+        loop on the host that calls ``lnprob`` in vectorised mode (emcee itself is used when it is
+        importable); ``sampler='device'`` keeps the whole chain on the GPU.
+        """
+        if kwargs:
+            if "filename" in kwargs or "plotfilename" in kwargs:
+                logger.warning('Parameters <filename> and <plotfilename> not used anymore. Use <prefix> instead.')
+        if plot:
+            logger.warning('Plotting is outside the scope of this package; plot=True is ignored.')
+
+        if pos is not None:
+            pos = np.asarray(pos, dtype=np.float64)
+            assert pos.shape == (n_walkers, self.n_fitted_parameters), 'Array with starting values has invalid shape.'
+        else:
+            pos = self.get_initials(n_walkers=n_walkers)
+
+        prior = self._lnprior_batch(pos)
+        for i in range(n_walkers):
+            if not np.isfinite(prior[i]):
+                raise ValueError(
+                    "Invalid initial guesses for walker {0}: {1}={2}".format(i, self.fitted_parameters, pos[i]))
+
+        if sampler == 'device':
+            if self._has_expression_priors():
+                raise ValueError("sampler='device' supports box priors only")
+            engine = _sampler.DeviceEnsembleSampler(n_walkers, self.n_fitted_parameters, self.pack(), seed=seed)
+        else:
+            engine = _sampler.make_host_sampler(n_walkers, self.n_fitted_parameters, self.lnprob, seed=seed)
+        logger.info("Running MCMC chain ...")
+
+        if n_out is not None:
+            msg = "Iter. <log like>   "
+            for name, parameter in self.parameters.items():
+                if not parameter.fixed:
+                    msg += " {0:12s}".format('<' + name + '>')
+            logger.info(msg)
+
+        state = None
+        while engine.iteration < n_steps:
+            todo = n_out if n_out is not None else n_steps
+            todo = min(todo, n_steps - engine.iteration)
+            pos, lnp, state = engine.run_mcmc(pos, todo, log_prob0=lnprob0, rstate0=state, progress=False)
+            lnprob0 = None
+            if n_out is not None:
+                output = " {0:4d} {1:12.5e}".format(engine.iteration, np.mean(lnp[:]))
+                for i in range(self.n_fitted_parameters):
+                    output += " {0:12.5e}".format(np.mean(pos[:, i]))
+                if engine.iteration % n_out == 0 and prefix is not None:
+                    self.save_current_status(engine, prefix=prefix)
+                logger.info(output)
+        return engine
+
+    @staticmethod
+    def save_current_status(sampler, prefix="sampler"):
+        """``analysis/runner.py:458-477``: chain and log-probabilities pickled to two files."""
+        with open("{0}_chain.pkl".format(prefix), "wb") as f:
+            pickle.dump(sampler.chain, f)
+        with open("{0}_lnprob.pkl".format(prefix), "wb") as f:
+            pickle.dump(sampler.lnprobability, f)
+
+    @staticmethod
+    def read_chain(filename):
+        """``analysis/runner.py:480-496``."""
+        with open(filename, 'rb') as f:
+            return pickle.load(f)
+
+    @staticmethod
+    def read_final_chain(filename):
+        """Last positions of every walker, for resuming a run (``analysis/runner.py:499-519``)."""
+        chain = Runner.read_chain(filename)
+        return chain[:, -1, :]
+
+    def compute_percentiles(self, chain, n_burn, pct=None):
+        """``analysis/runner.py:566-613``: percentiles [16, 50, 84] of the post-burn-in samples of every
+        fitted parameter; returns {name: array}."""
+        if pct is None:
+            pct = [16, 50, 84]
+        samples = np.asarray(chain)[:, n_burn:, :].reshape((-1, self.n_fitted_parameters))
+        values = np.percentile(samples, pct, axis=0)
+        return {name: values[:, i] for i, name in enumerate(self.fitted_parameters)}

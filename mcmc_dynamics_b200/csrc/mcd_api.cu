@@ -1,0 +1,427 @@
+// C ABI of libmcd_b200.so (declared in include/mcd_b200.h): handle management, packing, launch
+// geometry and the host-buffer convenience entry points.  No torch, no C++ types across the ABI.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "mcd_internal.h"
+
+using namespace mcd;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_error[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define MCD_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t err__ = (call);                                                                 \
+        if (err__ != cudaSuccess)                                                                   \
+            return fail(-2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+    } while (0)
+
+enum { RAW_RA = 0, RAW_DEC, RAW_V, RAW_VERR, RAW_PMEMBER, RAW_DENSITY, RAW_LBG, RAW_COUNT };
+
+struct mcd_handle {
+    int device = 0;
+    Variant var{};
+    mcd_pack_desc desc{};          // routing part of the descriptor (column pointers cleared)
+    long long n = 0, n_alloc = 0;
+    double *raw[RAW_COUNT] = {};
+    double *cols[kMaxCols] = {};
+    int32_t *icol = nullptr;
+    double ra0_deg = 0.0;
+    // launch scratch
+    double *partials = nullptr;
+    size_t partials_cap = 0;
+    unsigned int *counters = nullptr;
+    int counters_cap = 0;
+    // staging for the host-buffer entry points
+    double *theta_dev = nullptr, *out_dev = nullptr, *theta_pin = nullptr, *out_pin = nullptr;
+    size_t theta_cap = 0, out_cap = 0;
+    double *star_dev = nullptr;    // [n] scratch of the per-star entry point
+    cudaStream_t stream = nullptr;
+    int sm_count = 0, blocks_per_sm = 1;
+    mcd_info info{};
+};
+
+extern "C" int mcd_abi_version(void) { return MCD_ABI_VERSION; }
+extern "C" const char *mcd_last_error(void) { return g_error; }
+
+// ------------------------------------------------------------------------------------------
+// packing
+// ------------------------------------------------------------------------------------------
+static int validate_routing(const mcd_pack_desc *d) {
+    if (d->rotation != MCD_ROT_CONSTANT && d->rotation != MCD_ROT_RADIAL) return fail(-1, "unknown rotation model %d", d->rotation);
+    if (d->background < MCD_BG_NONE || d->background > MCD_BG_GAUSSIAN) return fail(-1, "unknown background mode %d", d->background);
+    if (d->math_mode != MCD_MATH_FAST && d->math_mode != MCD_MATH_PLAIN) return fail(-1, "unknown math mode %d", d->math_mode);
+    if (d->n_theta < 0 || d->n_theta > MCD_MAX_THETA) return fail(-1, "n_theta = %d outside [0, %d]", d->n_theta, MCD_MAX_THETA);
+    if (d->n_stars < 0) return fail(-1, "n_stars < 0");
+    for (int k = 0; k < MCD_NPARAM; ++k)
+        if (d->slot[k] >= d->n_theta) return fail(-1, "slot[%d] = %d but theta has %d columns", k, d->slot[k], d->n_theta);
+    return 0;
+}
+
+static int repack(mcd_handle *h) {
+    const mcd_pack_desc &d = h->desc;
+    h->var.rotation = d.rotation;
+    h->var.background = d.background;
+    h->var.math_mode = d.math_mode;
+    h->var.free_centre = (d.slot[MCD_P_RA_CENTER] >= 0 || d.slot[MCD_P_DEC_CENTER] >= 0) ? 1 : 0;
+
+    const int nc = variant_columns(h->var);
+    for (int c = 0; c < kMaxCols; ++c) {
+        if (c < nc && !h->cols[c]) {
+            MCD_CUDA(cudaMalloc(&h->cols[c], sizeof(double) * h->n_alloc));
+            MCD_CUDA(cudaMemsetAsync(h->cols[c], 0, sizeof(double) * h->n_alloc, h->stream));
+        }
+    }
+    if (variant_has_icol(h->var) && !h->icol) {
+        MCD_CUDA(cudaMalloc(&h->icol, sizeof(int32_t) * h->n_alloc));
+        MCD_CUDA(cudaMemsetAsync(h->icol, 0, sizeof(int32_t) * h->n_alloc, h->stream));
+    }
+    if ((d.background == MCD_BG_FIXED_PMEMBER) && !h->raw[RAW_PMEMBER]) return fail(-1, "background mode needs the pmember column");
+    if ((d.background == MCD_BG_FIXED_DENSITY || d.background == MCD_BG_GAUSSIAN) && !h->raw[RAW_DENSITY])
+        return fail(-1, "background mode needs the density column");
+    if ((d.background == MCD_BG_FIXED_PMEMBER || d.background == MCD_BG_FIXED_DENSITY) && !h->raw[RAW_LBG])
+        return fail(-1, "background mode needs the lnlike_background column");
+
+    PackParams p{};
+    p.raw.ra = h->raw[RAW_RA];
+    p.raw.dec = h->raw[RAW_DEC];
+    p.raw.v = h->raw[RAW_V];
+    p.raw.verr = h->raw[RAW_VERR];
+    p.raw.pmember = h->raw[RAW_PMEMBER];
+    p.raw.density = h->raw[RAW_DENSITY];
+    p.raw.lbg = h->raw[RAW_LBG];
+    for (int c = 0; c < kMaxCols; ++c) p.cols[c] = h->cols[c];
+    p.icol = h->icol;
+    p.n_stars = h->n;
+    p.rotation = d.rotation;
+    p.background = d.background;
+    p.free_centre = h->var.free_centre;
+    p.math_mode = d.math_mode;
+    p.ra_c_deg = d.fixed_value[MCD_P_RA_CENTER] * d.unit_scale[MCD_P_RA_CENTER];
+    p.dec_c_deg = d.fixed_value[MCD_P_DEC_CENTER] * d.unit_scale[MCD_P_DEC_CENTER];
+    // reference right ascension of the free-centre expansion: the parameter's current value
+    h->ra0_deg = p.ra_c_deg;
+    p.ra0_deg = h->ra0_deg;
+    MCD_CUDA(launch_pack(p, h->stream));
+    MCD_CUDA(cudaStreamSynchronize(h->stream));
+
+    h->blocks_per_sm = lnlike_blocks_per_sm(h->var);
+    h->info.n_stars = h->n;
+    h->info.n_theta = d.n_theta;
+    h->info.n_columns = nc;
+    h->info.bytes_per_star = 8 * nc + (variant_has_icol(h->var) ? 4 : 0);
+    h->info.flops_per_term = variant_flops_per_term(h->var);
+    h->info.free_centre = h->var.free_centre;
+    h->info.sm_count = h->sm_count;
+    return 0;
+}
+
+extern "C" void mcd_destroy(mcd_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto &p : h->raw) cudaFree(p);
+    for (auto &p : h->cols) cudaFree(p);
+    cudaFree(h->icol);
+    cudaFree(h->partials);
+    cudaFree(h->counters);
+    cudaFree(h->theta_dev);
+    cudaFree(h->out_dev);
+    cudaFree(h->star_dev);
+    cudaFreeHost(h->theta_pin);
+    cudaFreeHost(h->out_pin);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+static int upload_column(mcd_handle *h, int which, const double *host) {
+    if (!host) return 0;
+    MCD_CUDA(cudaMalloc(&h->raw[which], sizeof(double) * std::max<long long>(h->n, 1)));
+    if (h->n > 0)
+        MCD_CUDA(cudaMemcpyAsync(h->raw[which], host, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+extern "C" int mcd_pack_create(const mcd_pack_desc *desc, mcd_handle **out) {
+    if (!desc || !out) return fail(-1, "null argument");
+    *out = nullptr;
+    if (int rc = validate_routing(desc)) return rc;
+    if (desc->n_stars > 0 && (!desc->ra || !desc->dec || !desc->v || !desc->verr))
+        return fail(-1, "ra, dec, v and verr columns are required");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
+        return fail(-3, "no CUDA device is visible: the B200 path has no CPU fallback");
+    if (desc->device < 0 || desc->device >= count) return fail(-1, "device %d not in [0, %d)", desc->device, count);
+    mcd_handle *h = new (std::nothrow) mcd_handle();
+    if (!h) return fail(-4, "out of host memory");
+    h->device = desc->device;
+    int rc = 0;
+    do {
+        if (cudaSetDevice(h->device) != cudaSuccess) { rc = fail(-2, "cudaSetDevice(%d) failed", h->device); break; }
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) { rc = fail(-2, "cudaGetDeviceProperties failed"); break; }
+        h->sm_count = prop.multiProcessorCount;
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(-2, "cudaStreamCreate failed"); break; }
+        h->n = desc->n_stars;
+        h->n_alloc = ((h->n + kMaxTile - 1) / kMaxTile + 1) * kMaxTile;   // full bulk copies at the tail
+        h->desc = *desc;
+        h->desc.ra = h->desc.dec = h->desc.v = h->desc.verr = nullptr;
+        h->desc.pmember = h->desc.density = h->desc.lnlike_background = nullptr;
+        if ((rc = upload_column(h, RAW_RA, desc->ra))) break;
+        if ((rc = upload_column(h, RAW_DEC, desc->dec))) break;
+        if ((rc = upload_column(h, RAW_V, desc->v))) break;
+        if ((rc = upload_column(h, RAW_VERR, desc->verr))) break;
+        if ((rc = upload_column(h, RAW_PMEMBER, desc->pmember))) break;
+        if ((rc = upload_column(h, RAW_DENSITY, desc->density))) break;
+        if ((rc = upload_column(h, RAW_LBG, desc->lnlike_background))) break;
+        if ((rc = repack(h))) break;
+    } while (0);
+    if (rc) {
+        mcd_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int mcd_pack_reconfigure(mcd_handle *h, const mcd_pack_desc *desc) {
+    if (!h || !desc) return fail(-1, "null argument");
+    if (int rc = validate_routing(desc)) return rc;
+    if (desc->n_stars != h->n) return fail(-1, "reconfigure cannot change the catalogue (n_stars %lld != %lld)", (long long)desc->n_stars, h->n);
+    MCD_CUDA(cudaSetDevice(h->device));
+    h->desc = *desc;
+    h->desc.ra = h->desc.dec = h->desc.v = h->desc.verr = nullptr;
+    h->desc.pmember = h->desc.density = h->desc.lnlike_background = nullptr;
+    return repack(h);
+}
+
+extern "C" int mcd_get_info(const mcd_handle *h, mcd_info *info) {
+    if (!h || !info) return fail(-1, "null argument");
+    *info = h->info;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// launch geometry
+// ------------------------------------------------------------------------------------------
+static void choose_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p) {
+    // walkers per CTA: minimise groups / slices (CTA time ~ stars / slices, CTAs ~ groups)
+    int best_g = 1, best_wl = std::max(1, std::min(n_walkers, kBlock)), best_s = 1;
+    double best_cost = 1e300;
+    const int g_min = std::max(1, (n_walkers + kBlock - 1) / kBlock);
+    for (int g = g_min; g <= std::max(g_min, std::min(n_walkers, 4 * g_min + 8)); ++g) {
+        const int wl = (n_walkers + g - 1) / g;
+        const int gg = (n_walkers + wl - 1) / wl;
+        const int s = std::max(1, kBlock / wl);
+        const double cost = (double)gg / (double)s;
+        if (cost < best_cost * (1.0 - 1e-9)) {
+            best_cost = cost;
+            best_g = gg;
+            best_wl = wl;
+            best_s = s;
+        }
+    }
+    p.wl = best_wl;
+    p.slices = best_s;
+    p.n_groups = best_g;
+    // one wave of CTAs: star chunks per walker group
+    const int wave = std::max(1, h->sm_count * h->blocks_per_sm);
+    const int chunks_target = std::max(1, wave / p.n_groups);
+    // stars per stage: large enough that every slice has work, small enough to spread a small
+    // catalogue over the machine
+    long long tile = (h->n + chunks_target - 1) / chunks_target;
+    tile = std::max<long long>(tile, p.slices);
+    tile = ((tile + 15) / 16) * 16;
+    tile = std::min<long long>(std::max<long long>(tile, 16), kMaxTile);
+    p.tile = (int)tile;
+    p.n_tiles = (int)((h->n + tile - 1) / tile);
+    p.tiles_per_chunk = std::max(1, (p.n_tiles + chunks_target - 1) / chunks_target);
+    p.n_chunks = std::max(1, (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk);
+}
+
+static int ensure_scratch(mcd_handle *h, const LaunchParams &p) {
+    const size_t need = (size_t)p.n_chunks * p.n_walkers;
+    if (need > h->partials_cap) {
+        MCD_CUDA(cudaFree(h->partials));
+        h->partials = nullptr;
+        h->partials_cap = 0;
+        MCD_CUDA(cudaMalloc(&h->partials, sizeof(double) * need));
+        h->partials_cap = need;
+    }
+    if (p.n_groups > h->counters_cap) {
+        MCD_CUDA(cudaFree(h->counters));
+        h->counters = nullptr;
+        h->counters_cap = 0;
+        const int cap = std::max(64, p.n_groups);
+        MCD_CUDA(cudaMalloc(&h->counters, sizeof(unsigned int) * cap));
+        MCD_CUDA(cudaMemset(h->counters, 0, sizeof(unsigned int) * cap));
+        h->counters_cap = cap;
+    }
+    return 0;
+}
+
+static void fill_params(const mcd_handle *h, LaunchParams &p) {
+    const mcd_pack_desc &d = h->desc;
+    for (int c = 0; c < kMaxCols; ++c) p.cols[c] = h->cols[c];
+    p.icol = h->icol;
+    p.n_stars = h->n;
+    p.n_theta = d.n_theta;
+    p.fixed_prior_ok = d.fixed_prior_ok;
+    for (int k = 0; k < MCD_NPARAM; ++k) {
+        p.slot[k] = d.slot[k];
+        p.scale[k] = d.unit_scale[k];
+        p.fixed_scaled[k] = d.fixed_value[k] * d.unit_scale[k];
+    }
+    for (int j = 0; j < MCD_MAX_THETA; ++j) {
+        p.lower[j] = d.lower[j];
+        p.upper[j] = d.upper[j];
+    }
+    p.ra0_deg = h->ra0_deg;
+}
+
+static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double *out_dev, int apply_prior,
+                  cudaStream_t stream) {
+    if (!h) return fail(-1, "null handle");
+    if (n_walkers < 0) return fail(-1, "n_walkers < 0");
+    if (n_walkers == 0) return 0;
+    if (!theta_dev && h->desc.n_theta > 0) return fail(-1, "null theta");
+    if (!out_dev) return fail(-1, "null out");
+    MCD_CUDA(cudaSetDevice(h->device));
+    LaunchParams p{};
+    fill_params(h, p);
+    p.n_walkers = n_walkers;
+    p.apply_prior = apply_prior;
+    p.theta = theta_dev;
+    p.out = out_dev;
+    choose_geometry(h, n_walkers, p);
+    if (int rc = ensure_scratch(h, p)) return rc;
+    p.partials = h->partials;
+    p.counters = h->counters;
+    MCD_CUDA(launch_lnlike(h->var, p, stream));
+    h->info.last_grid_x = p.n_chunks;
+    h->info.last_grid_y = p.n_groups;
+    h->info.last_block = kBlock;
+    h->info.last_walker_tile = p.wl;
+    h->info.launches += 1;
+    return 0;
+}
+
+static int ensure_staging(mcd_handle *h, size_t theta_doubles, size_t out_doubles) {
+    if (theta_doubles > h->theta_cap) {
+        cudaFree(h->theta_dev);
+        cudaFreeHost(h->theta_pin);
+        h->theta_dev = h->theta_pin = nullptr;
+        h->theta_cap = 0;
+        const size_t cap = std::max<size_t>(theta_doubles, 4096);
+        MCD_CUDA(cudaMalloc(&h->theta_dev, sizeof(double) * cap));
+        MCD_CUDA(cudaMallocHost(&h->theta_pin, sizeof(double) * cap));
+        h->theta_cap = cap;
+    }
+    if (out_doubles > h->out_cap) {
+        cudaFree(h->out_dev);
+        cudaFreeHost(h->out_pin);
+        h->out_dev = h->out_pin = nullptr;
+        h->out_cap = 0;
+        const size_t cap = std::max<size_t>(out_doubles, 1024);
+        MCD_CUDA(cudaMalloc(&h->out_dev, sizeof(double) * cap));
+        MCD_CUDA(cudaMallocHost(&h->out_pin, sizeof(double) * cap));
+        h->out_cap = cap;
+    }
+    return 0;
+}
+
+static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, double *out_host, int apply_prior) {
+    if (!h) return fail(-1, "null handle");
+    if (n_walkers < 0) return fail(-1, "n_walkers < 0");
+    if (n_walkers == 0) return 0;
+    if (!out_host || (!theta_host && h->desc.n_theta > 0)) return fail(-1, "null buffer");
+    MCD_CUDA(cudaSetDevice(h->device));
+    const size_t nt = (size_t)n_walkers * h->desc.n_theta;
+    if (int rc = ensure_staging(h, nt, (size_t)n_walkers)) return rc;
+    if (nt) {
+        memcpy(h->theta_pin, theta_host, sizeof(double) * nt);
+        MCD_CUDA(cudaMemcpyAsync(h->theta_dev, h->theta_pin, sizeof(double) * nt, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (int rc = launch(h, h->theta_dev, n_walkers, h->out_dev, apply_prior, h->stream)) return rc;
+    MCD_CUDA(cudaMemcpyAsync(h->out_pin, h->out_dev, sizeof(double) * n_walkers, cudaMemcpyDeviceToHost, h->stream));
+    MCD_CUDA(cudaStreamSynchronize(h->stream));
+    memcpy(out_host, h->out_pin, sizeof(double) * n_walkers);
+    return 0;
+}
+
+int mcd::launch_ensemble(mcd_handle *h, const double *theta_dev, int n_walkers, double *out_dev, int apply_prior,
+                         cudaStream_t stream) {
+    return launch(h, theta_dev, n_walkers, out_dev, apply_prior, stream);
+}
+int mcd::handle_device(const mcd_handle *h) { return h->device; }
+
+extern "C" int mcd_lnlike(mcd_handle *h, const double *theta_host, int32_t n_walkers, double *out_host) {
+    return host_call(h, theta_host, n_walkers, out_host, 0);
+}
+extern "C" int mcd_lnprob(mcd_handle *h, const double *theta_host, int32_t n_walkers, double *out_host) {
+    return host_call(h, theta_host, n_walkers, out_host, 1);
+}
+extern "C" int mcd_lnlike_device(mcd_handle *h, const double *theta_dev, int32_t n_walkers, double *out_dev, void *stream) {
+    return launch(h, theta_dev, n_walkers, out_dev, 0, static_cast<cudaStream_t>(stream));
+}
+extern "C" int mcd_lnprob_device(mcd_handle *h, const double *theta_dev, int32_t n_walkers, double *out_dev, void *stream) {
+    return launch(h, theta_dev, n_walkers, out_dev, 1, static_cast<cudaStream_t>(stream));
+}
+extern "C" int mcd_lnprob_partial_device(mcd_handle *h, const double *theta_dev, int32_t n_walkers, double *out_dev,
+                                         void *stream) {
+    // a shard's lnprob kernel already returns (sum over its stars) or -inf: additive across shards
+    return launch(h, theta_dev, n_walkers, out_dev, 1, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------
+// per-star lnlike (no_sum)
+// ------------------------------------------------------------------------------------------
+static int per_star(mcd_handle *h, const double *theta_dev, double *out_dev, cudaStream_t stream) {
+    LaunchParams p{};
+    fill_params(h, p);
+    p.n_walkers = 1;
+    p.theta = theta_dev;
+    // the per-star kernel evaluates the reference's formulas literally and wants lbg itself where
+    // the FAST packing keeps a mantissa
+    const int nb = variant_columns(h->var) - (h->var.background == MCD_BG_NONE ? 0 : (h->var.background == MCD_BG_GAUSSIAN ? 1 : 2));
+    if (h->var.background == MCD_BG_FIXED_PMEMBER || h->var.background == MCD_BG_FIXED_DENSITY) p.cols[nb + 1] = h->raw[RAW_LBG];
+    MCD_CUDA(launch_per_star(h->var, p, out_dev, stream));
+    h->info.launches += 1;
+    return 0;
+}
+
+extern "C" int mcd_lnlike_per_star_device(mcd_handle *h, const double *theta_dev, double *out_dev, void *stream) {
+    if (!h || !out_dev) return fail(-1, "null argument");
+    MCD_CUDA(cudaSetDevice(h->device));
+    return per_star(h, theta_dev, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mcd_lnlike_per_star(mcd_handle *h, const double *theta_host, double *out_host) {
+    if (!h || !out_host) return fail(-1, "null argument");
+    MCD_CUDA(cudaSetDevice(h->device));
+    if (h->n == 0) return 0;
+    if (int rc = ensure_staging(h, (size_t)h->desc.n_theta, 1)) return rc;
+    if (!h->star_dev) MCD_CUDA(cudaMalloc(&h->star_dev, sizeof(double) * h->n));
+    if (h->desc.n_theta) {
+        memcpy(h->theta_pin, theta_host, sizeof(double) * h->desc.n_theta);
+        MCD_CUDA(cudaMemcpyAsync(h->theta_dev, h->theta_pin, sizeof(double) * h->desc.n_theta, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (int rc = per_star(h, h->theta_dev, h->star_dev, h->stream)) return rc;
+    MCD_CUDA(cudaMemcpyAsync(out_host, h->star_dev, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
+    MCD_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}

@@ -1,0 +1,84 @@
+// Internal declarations shared by the translation units of libmcd_b200.so.
+// Nothing in here crosses the C ABI (include/mcd_b200.h does).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mcd_b200.h"
+
+namespace mcd {
+
+constexpr int kBlock = 256;        // threads per CTA of the lnlike kernel
+constexpr int kMaxCols = 8;        // packed float64 columns per star
+constexpr int kMaxTile = 256;      // stars per shared-memory stage
+constexpr int kStages = 2;         // TMA bulk-copy stages in flight per CTA
+constexpr double kDeg2Rad = 0.017453292519943295769236907684886;
+constexpr double kR0Arcmin = 3437.7467707849392526078892888463;   // 10800/pi, calc_xy_offset.py:11
+
+// Raw star columns as uploaded (reference units: deg, km/s) -- kept on the device so that a
+// change of the parameter routing (fixed centre moved, parameter fixed/freed) re-packs without
+// another host transfer.
+struct RawColumns {
+    const double *ra, *dec, *v, *verr, *pmember, *density, *lbg;
+};
+
+// Everything the pack kernel needs to turn raw columns into the per-variant packed columns.
+struct PackParams {
+    RawColumns raw;
+    double *cols[kMaxCols];
+    int32_t *icol;
+    long long n_stars;
+    int rotation, background, free_centre, math_mode;
+    double ra_c_deg, dec_c_deg;     // fixed centre (ignored when free_centre)
+    double ra0_deg;                 // reference right ascension of the free-centre expansion
+};
+
+// Kernel argument block of one lnlike / lnprob launch (passed by value, __grid_constant__).
+struct LaunchParams {
+    const double *cols[kMaxCols];
+    const int32_t *icol;
+    long long n_stars;
+    int tile;                 // stars per stage (multiple of 16, <= kMaxTile)
+    int n_tiles;
+    int tiles_per_chunk;
+    int n_chunks;             // gridDim.x
+    int n_groups;             // gridDim.y
+    int n_walkers;
+    int wl;                   // walkers per CTA
+    int slices;               // star slices per CTA: kBlock / wl
+    int n_theta;
+    int apply_prior;          // 1: lnprob (box prior fused), 0: lnlike
+    int fixed_prior_ok;
+    const double *theta;      // [n_walkers][n_theta]
+    double *partials;         // [n_chunks][n_walkers]
+    unsigned int *counters;   // [n_groups], zero between launches
+    double *out;              // [n_walkers]
+    int slot[MCD_NPARAM];
+    double fixed_scaled[MCD_NPARAM];   // fixed value already multiplied by its unit scale
+    double scale[MCD_NPARAM];
+    double lower[MCD_MAX_THETA], upper[MCD_MAX_THETA];
+    double ra0_deg;
+};
+
+struct Variant {
+    int rotation, free_centre, background, math_mode;
+};
+
+// number of packed float64 columns of a variant / whether it has the int32 exponent column
+int variant_columns(const Variant &v);
+bool variant_has_icol(const Variant &v);
+int variant_flops_per_term(const Variant &v);
+
+cudaError_t launch_pack(const PackParams &p, cudaStream_t stream);
+cudaError_t launch_lnlike(const Variant &v, const LaunchParams &p, cudaStream_t stream);
+// per-star lnlike of walker 0 of p.theta into out[N] (always PLAIN arithmetic)
+cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out, cudaStream_t stream);
+// resident CTAs per SM of the lnlike kernel of this variant (occupancy API)
+int lnlike_blocks_per_sm(const Variant &v);
+
+// one lnlike (apply_prior = 0) / lnprob (1) launch on `stream`, device pointers (mcd_api.cu)
+int launch_ensemble(mcd_handle *h, const double *theta_dev, int n_walkers, double *out_dev, int apply_prior,
+                    cudaStream_t stream);
+int handle_device(const mcd_handle *h);
+
+}  // namespace mcd

@@ -1,0 +1,564 @@
+// Likelihood kernels of the B200-native mcmc-dynamics hot path (sm_100a).
+//
+// One launch evaluates a whole (half-)ensemble: every walker of the call against every star of
+// the catalogue shard held by this GPU, reduced to one float64 per walker.  It replaces the
+// per-walker Python call chain of the reference
+//   Runner.lnprob -> lnprior + <Model>.lnlike -> rotation_model / dispersion_model
+//                 -> calc_xy_offset -> Runner._calculate_lnlike
+//   (analysis/runner.py:182-306, constant.py:52-154,293-364, model.py:93-223,391-456,565-623,
+//    utils/coordinates/calc_xy_offset.py:9-33)
+// and the walker-parallel process pool around it (analysis/runner.py:398-403).
+//
+// Work decomposition
+//   grid  = (star chunks, walker groups); a CTA owns `wl` walkers x `slices` star slices
+//           (wl * slices <= 256 threads) and a contiguous run of star tiles.
+//   tile  = `tile` stars of every packed column, brought into shared memory by TMA bulk copies
+//           (cp.async.bulk, mbarrier completion), double buffered; every thread of the CTA then
+//           reads the stars of its slice as shared-memory broadcasts.
+//   thread= one walker: its derived constants live in registers for the whole launch, its
+//           partial sums are register accumulators (no shuffles in the star loop).
+//   reduce= slices -> shared memory, chunks -> `partials` in global memory; the last CTA of a
+//           walker group to finish (atomic ticket) adds the chunk partials in chunk order, so the
+//           result does not depend on CTA scheduling.
+#include <math.h>
+
+#include "mcd_internal.h"
+#include "mcd_math.cuh"
+
+namespace mcd {
+
+// ------------------------------------------------------------------------------------------
+// packed column layout
+// ------------------------------------------------------------------------------------------
+//   free centre            : p1 = cos(dec) sin(ra-ra0), p2 = cos(dec) cos(ra-ra0), sin(dec), v, verr^2
+//   fixed centre, constant : cos(theta_i), sin(theta_i), v, verr^2
+//   fixed centre, radial   : x, y [arcmin], r^2, v, verr^2
+//   + FIXED_PMEMBER        : pmember, then FAST: mantissa of (1-p) sqrt(2pi) exp(lbg) (+ int32 exponent)
+//                                           PLAIN: lbg
+//   + FIXED_DENSITY        : density, then FAST: mantissa of sqrt(2pi) exp(lbg) (+ int32 exponent)
+//                                           PLAIN: lbg
+//   + GAUSSIAN             : density
+__host__ __device__ constexpr int base_columns(int rot, int free_centre) {
+    return free_centre ? 5 : (rot == MCD_ROT_RADIAL ? 5 : 4);
+}
+__host__ __device__ constexpr int total_columns(int rot, int free_centre, int bg) {
+    return base_columns(rot, free_centre) +
+           (bg == MCD_BG_NONE ? 0 : (bg == MCD_BG_GAUSSIAN ? 1 : 2));
+}
+__host__ __device__ constexpr bool has_icol(int bg, int math) {
+    return math == MCD_MATH_FAST && (bg == MCD_BG_FIXED_PMEMBER || bg == MCD_BG_FIXED_DENSITY);
+}
+
+int variant_columns(const Variant &v) { return total_columns(v.rotation, v.free_centre, v.background); }
+bool variant_has_icol(const Variant &v) { return has_icol(v.background, v.math_mode); }
+
+// Nominal FP64 operations per (walker, star) term: add/sub/mul/compare = 1, fma = 2, every
+// div / sqrt / rsqrt / log / exp = 1 (DESIGN.md "work per term").
+int variant_flops_per_term(const Variant &v) {
+    int f;
+    if (v.rotation == MCD_ROT_CONSTANT) f = v.free_centre ? 29 : 11;
+    else f = v.free_centre ? 35 : 19;
+    if (v.background == MCD_BG_FIXED_PMEMBER || v.background == MCD_BG_FIXED_DENSITY) f += 12;
+    if (v.background == MCD_BG_FIXED_DENSITY) f += 3;
+    if (v.background == MCD_BG_GAUSSIAN) f += 23;
+    return f;
+}
+
+// ------------------------------------------------------------------------------------------
+// pack: raw catalogue columns -> packed columns (one thread per star, once per model object)
+// ------------------------------------------------------------------------------------------
+__global__ void pack_kernel(const PackParams P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_stars) return;
+    const double ra = P.raw.ra[i], dec = P.raw.dec[i];
+    const double v = P.raw.v[i], verr = P.raw.verr[i];
+    const double e2 = verr * verr;
+    int c = 0;
+    if (P.free_centre) {
+        double sa, ca, sd, cd;
+        sincos((ra - P.ra0_deg) * kDeg2Rad, &sa, &ca);
+        sincos(dec * kDeg2Rad, &sd, &cd);
+        P.cols[c++][i] = cd * sa;
+        P.cols[c++][i] = cd * ca;
+        P.cols[c++][i] = sd;
+    } else {
+        // utils/coordinates/calc_xy_offset.py:30-31, arcmin
+        double sda, cda, sd, cd, sdc, cdc;
+        sincos((ra - P.ra_c_deg) * kDeg2Rad, &sda, &cda);
+        sincos(dec * kDeg2Rad, &sd, &cd);
+        sincos(P.dec_c_deg * kDeg2Rad, &sdc, &cdc);
+        const double dx = -kR0Arcmin * cd * sda;
+        const double dy = kR0Arcmin * (sd * cdc - cd * sdc * cda);
+        if (P.rotation == MCD_ROT_CONSTANT) {
+            // theta_i = atan2(dy, dx) (constant.py:107); atan2(0, 0) = 0
+            const double r = sqrt(dx * dx + dy * dy);
+            P.cols[c++][i] = r > 0.0 ? dx / r : 1.0;
+            P.cols[c++][i] = r > 0.0 ? dy / r : 0.0;
+        } else {
+            P.cols[c++][i] = dx;
+            P.cols[c++][i] = dy;
+            P.cols[c++][i] = dx * dx + dy * dy;
+        }
+    }
+    P.cols[c++][i] = v;
+    P.cols[c++][i] = e2;
+    if (P.background == MCD_BG_FIXED_PMEMBER || P.background == MCD_BG_FIXED_DENSITY) {
+        const double w = P.background == MCD_BG_FIXED_PMEMBER ? P.raw.pmember[i] : P.raw.density[i];
+        const double lbg = P.raw.lbg[i];
+        P.cols[c++][i] = w;
+        if (P.math_mode == MCD_MATH_FAST) {
+            double m;
+            int e, invalid = 0;
+            exp_split(lbg, m, e, invalid);
+            const double wb = P.background == MCD_BG_FIXED_PMEMBER ? (1.0 - w) : 1.0;
+            P.cols[c++][i] = invalid ? __longlong_as_double(0x7ff8000000000000LL) : wb * kSqrt2Pi * m;
+            P.icol[i] = e;
+        } else {
+            P.cols[c++][i] = lbg;
+        }
+    } else if (P.background == MCD_BG_GAUSSIAN) {
+        P.cols[c++][i] = P.raw.density[i];
+    }
+}
+
+cudaError_t launch_pack(const PackParams &p, cudaStream_t stream) {
+    if (p.n_stars <= 0) return cudaSuccess;
+    const int block = 256;
+    const long long grid = (p.n_stars + block - 1) / block;
+    pack_kernel<<<(unsigned)grid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// per-walker derived constants
+// ------------------------------------------------------------------------------------------
+struct Walker {
+    double vsys, s2;            // systemic velocity, sigma_max^2
+    double cx, cy;              // rotation: v_rot numerator = x*cx + y*cy
+    double ip2, ia2;            // 1/r_peak^2, 1/a^2 in units of the stored coordinates
+    double sb, cb, sdc, cdc;    // free centre: sin/cos(ra_c - ra0), sin/cos(dec_c)
+    double vb, sb2, fb;         // background: v_back, sigma_back^2, f_back
+    int prior_ok;
+};
+
+template <int ROT, int FREE, int BG>
+__device__ __forceinline__ void load_walker(const LaunchParams &P, int w, Walker &W) {
+    double par[MCD_NPARAM];
+    const double *row = P.theta + (size_t)w * P.n_theta;
+#pragma unroll
+    for (int k = 0; k < MCD_NPARAM; ++k) {
+        const int s = P.slot[k];
+        par[k] = s >= 0 ? row[s] * P.scale[k] : P.fixed_scaled[k];
+    }
+    int ok = P.fixed_prior_ok;
+    // box prior, bounds inclusive (parameter.py:691-692); NaN compares false and passes, as it
+    // does in the reference
+    for (int j = 0; j < P.n_theta; ++j) {
+        const double t = row[j];
+        ok &= !(t < P.lower[j] || t > P.upper[j]);
+    }
+    W.prior_ok = ok;
+    W.vsys = par[MCD_P_V_SYS];
+    W.s2 = par[MCD_P_SIGMA_MAX] * par[MCD_P_SIGMA_MAX];
+    const double vmx = par[MCD_P_V_MAXX], vmy = par[MCD_P_V_MAXY];
+    if constexpr (ROT == MCD_ROT_CONSTANT) {
+        // v_max sin(theta_i - theta_0) = sin(theta_i) v_maxx - cos(theta_i) v_maxy (constant.py:109-111)
+        W.cx = -vmy;
+        W.cy = vmx;
+        W.ip2 = 0.0;
+        W.ia2 = 0.0;
+    } else {
+        // coordinates are stored in arcmin (fixed centre) or in units of r0 = 10800/pi arcmin (free)
+        const double L = FREE ? kR0Arcmin : 1.0;
+        const double rp = par[MCD_P_R_PEAK], a = par[MCD_P_A];
+        W.cx = -2.0 * L * vmy / rp;
+        W.cy = 2.0 * L * vmx / rp;
+        W.ip2 = (L / rp) * (L / rp);
+        W.ia2 = (L / a) * (L / a);
+    }
+    if constexpr (FREE) {
+        sincos((par[MCD_P_RA_CENTER] - P.ra0_deg) * kDeg2Rad, &W.sb, &W.cb);
+        sincos(par[MCD_P_DEC_CENTER] * kDeg2Rad, &W.sdc, &W.cdc);
+    } else {
+        W.sb = 0.0; W.cb = 1.0; W.sdc = 0.0; W.cdc = 1.0;
+    }
+    W.vb = par[MCD_P_V_BACK];
+    W.sb2 = par[MCD_P_SIGMA_BACK] * par[MCD_P_SIGMA_BACK];
+    W.fb = par[MCD_P_F_BACK];
+}
+
+// ------------------------------------------------------------------------------------------
+// per-thread accumulators
+// ------------------------------------------------------------------------------------------
+template <int BG, int MATH>
+struct Accum;
+
+template <>
+struct Accum<MCD_BG_NONE, MCD_MATH_FAST> {
+    double chi;
+    LogProduct norm;
+    __device__ __forceinline__ void reset() { chi = 0.0; norm.reset(); }
+    __device__ __forceinline__ void end_tile() { norm.renormalise(); }
+    __device__ __forceinline__ double value() { return -0.5 * (chi + norm.ln()); }
+};
+template <int BG>
+struct Accum<BG, MCD_MATH_FAST> {
+    LogProduct num, den;
+    int invalid;
+    __device__ __forceinline__ void reset() { num.reset(); den.reset(); invalid = 0; }
+    __device__ __forceinline__ void end_tile() { num.renormalise(); den.renormalise(); }
+    __device__ __forceinline__ double value() {
+        num.bad |= invalid;
+        const double n = num.ln();
+        return BG == MCD_BG_FIXED_PMEMBER ? n : n - den.ln();
+    }
+};
+template <int BG>
+struct Accum<BG, MCD_MATH_PLAIN> {
+    double sum;
+    __device__ __forceinline__ void reset() { sum = 0.0; }
+    __device__ __forceinline__ void end_tile() {}
+    __device__ __forceinline__ double value() { return sum; }
+};
+
+// ------------------------------------------------------------------------------------------
+// one (walker, star) term
+// ------------------------------------------------------------------------------------------
+// `c` points at the packed columns of the current stage in shared memory (column stride = tile),
+// `i` is the star's index inside the tile.
+template <int ROT, int FREE, int BG, int MATH>
+__device__ __forceinline__ void term(const Walker &W, const double *__restrict__ c, const int32_t *__restrict__ ci,
+                                     int tile, int i, Accum<BG, MATH> &A) {
+    constexpr int NB = base_columns(ROT, FREE);
+    constexpr bool FAST = MATH == MCD_MATH_FAST;
+    // ---- geometry: numerator `num` and denominator `D1` of the rotation term, r^2 ------------
+    double num, r2 = 0.0;
+    if constexpr (FREE) {
+        const double p1 = c[i], p2 = c[tile + i], sd = c[2 * tile + i];
+        const double dx = fma(p2, W.sb, -p1 * W.cb);            // -cos(dec) sin(ra - ra_c)
+        const double u = fma(p2, W.cb, p1 * W.sb);              //  cos(dec) cos(ra - ra_c)
+        const double dy = fma(sd, W.cdc, -u * W.sdc);
+        r2 = fma(dx, dx, dy * dy);
+        num = fma(dy, W.cy, dx * W.cx);
+        if constexpr (ROT == MCD_ROT_CONSTANT) {
+            // sin(theta_i - theta_0) needs the unit vector: divide by r; atan2(0,0) = 0 => (1, 0)
+            const bool origin = (__double2hiint(r2) | __double2loint(r2)) == 0;
+            const double rinv = FAST ? fast_rsqrt(origin ? 1.0 : r2) : 1.0 / sqrt(origin ? 1.0 : r2);
+            num = origin ? W.cx : num * rinv;
+        }
+    } else if constexpr (ROT == MCD_ROT_CONSTANT) {
+        num = fma(c[tile + i], W.cy, c[i] * W.cx);
+    } else {
+        num = fma(c[tile + i], W.cy, c[i] * W.cx);
+        r2 = c[2 * tile + i];
+    }
+    const double v = c[(NB - 2) * tile + i], e2 = c[(NB - 1) * tile + i];
+    const double dv = v - W.vsys;
+
+    if constexpr (FAST) {
+        // ---- dispersion and the combined variance ----------------------------------------
+        double norm, D1 = 1.0;
+        if constexpr (ROT == MCD_ROT_RADIAL) {
+            D1 = fma(r2, W.ip2, 1.0);
+            const double D2 = fma(r2, W.ia2, 1.0);
+            norm = fma(W.s2, fast_rsqrt(D2), e2);          // sigma_max^2 / sqrt(1 + r^2/a^2) + verr^2
+        } else {
+            norm = e2 + W.s2;
+        }
+        // residual times D1: (v - v_sys) D1 - num  (= (v - v_los) D1)
+        const double t = ROT == MCD_ROT_RADIAL ? fma(dv, D1, -num) : dv - num;
+        if constexpr (BG == MCD_BG_NONE) {
+            // chi^2 = t^2 / (D1^2 norm): one reciprocal per term, no log (running product)
+            const double q = ROT == MCD_ROT_RADIAL ? (D1 * D1) * norm : norm;
+            A.chi = fma(t * t, fast_rcp(q), A.chi);
+            A.norm.mul(norm);
+        } else {
+            // member Gaussian without its 1/sqrt(2 pi): y exp(-z^2/2), y = norm^-1/2, z = t y / D1
+            const double q = ROT == MCD_ROT_RADIAL ? (D1 * D1) * norm : norm;
+            const double yq = fast_rsqrt(q);
+            const double z = t * yq;
+            const double y = ROT == MCD_ROT_RADIAL ? yq * D1 : yq;
+            double em;
+            int ee;
+            exp_split(-0.5 * (z * z), em, ee, A.invalid);
+            double wm, bm;
+            int be;
+            if constexpr (BG == MCD_BG_FIXED_PMEMBER) {
+                wm = c[NB * tile + i];
+                bm = c[(NB + 1) * tile + i];
+                be = ci[i];
+            } else if constexpr (BG == MCD_BG_FIXED_DENSITY) {
+                wm = c[NB * tile + i];
+                bm = W.fb * c[(NB + 1) * tile + i];
+                be = ci[i];
+                A.den.mul(wm + W.fb);
+            } else {
+                wm = c[NB * tile + i];
+                const double nb = e2 + W.sb2;
+                const double yb = fast_rsqrt(nb);
+                const double zb = (v - W.vb) * yb;
+                double ebm;
+                exp_split(-0.5 * (zb * zb), ebm, be, A.invalid);
+                bm = W.fb * yb * ebm;
+                A.den.mul(wm + W.fb);
+            }
+            double m;
+            int e;
+            ext_add(wm * y * em, ee, bm, be, m, e);
+            A.num.mul_ext(m, e);
+        }
+    } else {
+        // ---- PLAIN: the reference's formulas with library div / sqrt / log / exp ----------
+        double sig2, vlos;
+        if constexpr (ROT == MCD_ROT_RADIAL) {
+            vlos = W.vsys + num / (1.0 + r2 * W.ip2);                 // model.py:180
+            sig2 = W.s2 / sqrt(1.0 + r2 * W.ia2);                     // model.py:128, squared
+        } else {
+            vlos = W.vsys + num;                                      // constant.py:111
+            sig2 = W.s2;                                              // constant.py:74
+        }
+        const double norm = e2 + sig2;                                // runner.py:261
+        const double resid = v - vlos;
+        const double lm = -0.5 * log(kTwoPi * norm) + (-0.5 * (resid * resid) / norm);   // runner.py:262-271
+        if constexpr (BG == MCD_BG_NONE) {
+            A.sum += lm;
+        } else {
+            double wm, lb;
+            if constexpr (BG == MCD_BG_FIXED_PMEMBER) {
+                wm = c[NB * tile + i];
+                lb = c[(NB + 1) * tile + i];
+            } else if constexpr (BG == MCD_BG_FIXED_DENSITY) {
+                const double d = c[NB * tile + i];
+                wm = d / (d + W.fb);                                  // model.py:589
+                lb = c[(NB + 1) * tile + i];
+            } else {
+                const double d = c[NB * tile + i];
+                wm = d / (d + W.fb);                                  // constant.py:339, model.py:427
+                const double nb = e2 + W.sb2;                         // constant.py:333-336
+                const double rb = v - W.vb;
+                lb = -0.5 * log(kTwoPi * nb) + (-0.5 * (rb * rb) / nb);
+            }
+            // runner.py:279-284, constant.py:320-323, model.py:452-454,614-618
+            const double mx = fmax(lm, lb);
+            A.sum += mx + log(wm * exp(lm - mx) + (1.0 - wm) * exp(lb - mx));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA bulk copy + mbarrier plumbing
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy through the TMA unit; completion is signalled on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// the lnlike / lnprob kernel
+// ------------------------------------------------------------------------------------------
+template <int ROT, int FREE, int BG, int MATH>
+__global__ void __launch_bounds__(kBlock) lnlike_kernel(const __grid_constant__ LaunchParams P) {
+    constexpr int NC = total_columns(ROT, FREE, BG);
+    constexpr bool ICOL = has_icol(BG, MATH);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bars[kStages];
+    __shared__ double red[kBlock];
+    __shared__ int s_last;
+
+    const int tile = P.tile;
+    double *sd = reinterpret_cast<double *>(smem_raw);                         // [kStages][NC][tile]
+    int32_t *si = reinterpret_cast<int32_t *>(sd + (size_t)kStages * NC * tile);   // [kStages][tile]
+
+    const int tid = threadIdx.x;
+    const int chunk = blockIdx.x, group = blockIdx.y;
+    const int lane = tid % P.wl, slice = tid / P.wl;
+    const int w = group * P.wl + lane;
+    const bool valid = slice < P.slices && w < P.n_walkers;
+
+    const int t_begin = chunk * P.tiles_per_chunk;
+    const int t_end = min(P.n_tiles, t_begin + P.tiles_per_chunk);
+    const int n_my_tiles = max(0, t_end - t_begin);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t stage_bytes = (uint32_t)tile * (NC * 8u + (ICOL ? 4u : 0u));
+    auto issue = [&](int k) {   // tid 0 only
+        const int stage = k % kStages;
+        const size_t off = (size_t)(t_begin + k) * tile;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&bars[stage], stage_bytes);
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            bulk_g2s(sd + ((size_t)stage * NC + c) * tile, P.cols[c] + off, (uint32_t)tile * 8u, &bars[stage]);
+        if (ICOL) bulk_g2s(si + (size_t)stage * tile, P.icol + off, (uint32_t)tile * 4u, &bars[stage]);
+    };
+
+    if (tid == 0 && n_my_tiles > 0) issue(0);
+
+    Walker W;
+    W.prior_ok = 0;
+    if (valid) load_walker<ROT, FREE, BG>(P, w, W);
+    // a walker outside its box prior is never evaluated by the reference (runner.py:303-306)
+    const bool active = valid && (W.prior_ok || !P.apply_prior);
+
+    Accum<BG, MATH> A;
+    A.reset();
+
+    for (int k = 0; k < n_my_tiles; ++k) {
+        const int stage = k % kStages;
+        if (tid == 0 && k + 1 < n_my_tiles) issue(k + 1);
+        mbar_wait(&bars[stage], (uint32_t)(k / kStages) & 1u);
+        const long long first = (long long)(t_begin + k) * tile;
+        const int n = (int)min((long long)tile, P.n_stars - first);
+        if (active) {
+            const double *c = sd + (size_t)stage * NC * tile;
+            const int32_t *ci = si + (size_t)stage * tile;
+#pragma unroll 2
+            for (int i = slice; i < n; i += P.slices) term<ROT, FREE, BG, MATH>(W, c, ci, tile, i, A);
+            A.end_tile();
+        }
+        __syncthreads();   // everyone is done with `stage` before it is refilled
+    }
+
+    // ---- slices -> one value per walker of this CTA ----------------------------------------
+    red[tid] = active ? A.value() : 0.0;
+    __syncthreads();
+    if (valid && slice == 0) {
+        double s = red[lane];
+        for (int j = 1; j < P.slices; ++j) s += red[j * P.wl + lane];
+        P.partials[(size_t)chunk * P.n_walkers + w] = s;
+    }
+
+    // ---- chunks -> result: the last CTA of the walker group adds the partials in chunk order ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int ticket = atomicAdd(&P.counters[group], 1u);
+        s_last = (ticket == (unsigned int)P.n_chunks - 1u);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (valid && slice == 0) {
+        double s = 0.0;
+        for (int cidx = 0; cidx < P.n_chunks; ++cidx) s += __ldcg(&P.partials[(size_t)cidx * P.n_walkers + w]);
+        if (MATH == MCD_MATH_FAST) s = fma((double)P.n_stars, -0.5 * kLn2Pi, s);
+        const bool rejected = P.apply_prior && !W.prior_ok;
+        P.out[w] = rejected ? __longlong_as_double(0xfff0000000000000LL) : s;
+    }
+    if (tid == 0) P.counters[group] = 0u;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-star lnlike of one parameter vector (`no_sum=True`, model.py:565,620-621)
+// ------------------------------------------------------------------------------------------
+template <int ROT, int FREE, int BG>
+__global__ void per_star_kernel(const __grid_constant__ LaunchParams P, double *__restrict__ out) {
+    constexpr int NC = total_columns(ROT, FREE, BG);
+    __shared__ Walker Ws;
+    if (threadIdx.x == 0) load_walker<ROT, FREE, BG>(P, 0, Ws);
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_stars) return;
+    // stage the star's packed values as a one-star "tile" in registers
+    double c[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) c[k] = P.cols[k][i];
+    Accum<BG, MCD_MATH_PLAIN> A;
+    A.reset();
+    const Walker W = Ws;
+    term<ROT, FREE, BG, MCD_MATH_PLAIN>(W, c, nullptr, 1, 0, A);
+    out[i] = A.value();
+}
+
+// ------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------
+template <int ROT, int FREE, int BG, int MATH>
+static cudaError_t launch_one(const LaunchParams &p, cudaStream_t stream) {
+    constexpr int NC = total_columns(ROT, FREE, BG);
+    const size_t smem = (size_t)kStages * p.tile * (NC * 8 + (has_icol(BG, MATH) ? 4 : 0));
+    dim3 grid((unsigned)p.n_chunks, (unsigned)p.n_groups);
+    lnlike_kernel<ROT, FREE, BG, MATH><<<grid, kBlock, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int ROT, int FREE, int BG, int MATH>
+static int occupancy_one() {
+    constexpr int NC = total_columns(ROT, FREE, BG);
+    const size_t smem = (size_t)kStages * kMaxTile * (NC * 8 + (has_icol(BG, MATH) ? 4 : 0));
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lnlike_kernel<ROT, FREE, BG, MATH>, kBlock, smem) !=
+        cudaSuccess)
+        return 1;
+    return n > 0 ? n : 1;
+}
+
+#define MCD_DISPATCH_BG(ROT, FREE, MATH, FN, ...)                                            \
+    switch (v.background) {                                                                   \
+        case MCD_BG_NONE: return FN<ROT, FREE, MCD_BG_NONE, MATH>(__VA_ARGS__);               \
+        case MCD_BG_FIXED_PMEMBER: return FN<ROT, FREE, MCD_BG_FIXED_PMEMBER, MATH>(__VA_ARGS__); \
+        case MCD_BG_FIXED_DENSITY: return FN<ROT, FREE, MCD_BG_FIXED_DENSITY, MATH>(__VA_ARGS__); \
+        default: return FN<ROT, FREE, MCD_BG_GAUSSIAN, MATH>(__VA_ARGS__);                    \
+    }
+#define MCD_DISPATCH_GEO(MATH, FN, ...)                                                       \
+    if (v.rotation == MCD_ROT_CONSTANT) {                                                     \
+        if (v.free_centre) { MCD_DISPATCH_BG(MCD_ROT_CONSTANT, 1, MATH, FN, __VA_ARGS__) }    \
+        else { MCD_DISPATCH_BG(MCD_ROT_CONSTANT, 0, MATH, FN, __VA_ARGS__) }                  \
+    } else {                                                                                  \
+        if (v.free_centre) { MCD_DISPATCH_BG(MCD_ROT_RADIAL, 1, MATH, FN, __VA_ARGS__) }      \
+        else { MCD_DISPATCH_BG(MCD_ROT_RADIAL, 0, MATH, FN, __VA_ARGS__) }                    \
+    }
+
+cudaError_t launch_lnlike(const Variant &v, const LaunchParams &p, cudaStream_t stream) {
+    if (v.math_mode == MCD_MATH_PLAIN) { MCD_DISPATCH_GEO(MCD_MATH_PLAIN, launch_one, p, stream) }
+    else { MCD_DISPATCH_GEO(MCD_MATH_FAST, launch_one, p, stream) }
+}
+
+int lnlike_blocks_per_sm(const Variant &v) {
+    if (v.math_mode == MCD_MATH_PLAIN) { MCD_DISPATCH_GEO(MCD_MATH_PLAIN, occupancy_one) }
+    else { MCD_DISPATCH_GEO(MCD_MATH_FAST, occupancy_one) }
+}
+
+template <int ROT, int FREE, int BG, int MATH_UNUSED>
+static cudaError_t per_star_one(const LaunchParams &p, double *out, cudaStream_t stream) {
+    if (p.n_stars <= 0) return cudaSuccess;
+    const int block = 256;
+    const long long grid = (p.n_stars + block - 1) / block;
+    per_star_kernel<ROT, FREE, BG><<<(unsigned)grid, block, 0, stream>>>(p, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out, cudaStream_t stream) {
+    MCD_DISPATCH_GEO(MCD_MATH_PLAIN, per_star_one, p, out, stream)
+}
+
+}  // namespace mcd

@@ -1,0 +1,174 @@
+// FP64 device arithmetic for the likelihood kernels (sm_100a).
+//
+// The B200 FP64 pipe issues one warp-wide DFMA every 2 cycles per SM sub-partition, and the
+// compiler's IEEE division / sqrt / log / exp expand to 10-30 such instructions each plus
+// slow-path branches.  The likelihood only needs ~1e-14 relative accuracy, not correct
+// rounding, so the hot loop uses:
+//   * MUFU.RCP64H / MUFU.RSQ64H seeds (rel. error ~2^-22, issued on the otherwise idle XU
+//     pipe) refined by ONE cubic Newton step (3 resp. 5 DFMA) -> rel. error < 2^-60;
+//   * no per-star log at all: sum_i ln(x_i) = ln(prod_i x_i), the running product is kept
+//     as a mantissa in [1, 2^k) plus an integer exponent that is maintained with integer-pipe
+//     bit operations on the high word;
+//   * exp() only in the mixture variants, as 2^n * 2^f with n in an integer register and
+//     2^f a degree-12 polynomial; the two mixture components are combined in this
+//     (mantissa, exponent) form, i.e. a base-2 log-sum-exp without log or exp calls.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mcd {
+
+constexpr double kLn2 = 0.693147180559945309417232121458;
+constexpr double kLog2e = 1.44269504088896340735992468100;
+constexpr double kLn2Pi = 1.83787706640934548356065947281;      // ln(2 pi)
+constexpr double kSqrt2Pi = 2.50662827463100050241576528481;    // sqrt(2 pi)
+constexpr double kInvSqrt2Pi = 0.398942280401432677939946059934;
+constexpr double kTwoPi = 6.28318530717958647692528676656;
+
+__device__ __forceinline__ double rcp_seed(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+
+__device__ __forceinline__ double rsqrt_seed(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+
+// 1/x for normal positive x: seed + cubic step, 3 DFMA.  e = 1 - x*y0, 1/x = y0 (1 + e + e^2 + O(e^3)).
+__device__ __forceinline__ double fast_rcp(double x) {
+    const double y0 = rcp_seed(x);
+    const double e = fma(-x, y0, 1.0);
+    const double p = fma(e, e, e);
+    return fma(y0, p, y0);
+}
+
+// x^(-1/2) for normal positive x: seed + cubic step, 5 DFMA.
+// e = 1 - x*y0^2, x^(-1/2) = y0 (1 + e/2 + 3 e^2/8 + O(e^3)).
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    const double y0 = rsqrt_seed(x);
+    const double t = x * y0;
+    const double e = fma(-t, y0, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double ye = y0 * e;
+    return fma(ye, p, y0);
+}
+
+// 2^d for integer d <= 0; exact, flushed to zero below the normal range.
+__device__ __forceinline__ double pow2_nonpos(int d) {
+    const int hi = (d + 1023) << 20;
+    return d < -1022 ? 0.0 : __hiloint2double(hi, 0);
+}
+
+// Running product kept as mantissa * 2^exponent: sum_i ln(x_i) without a log per factor.
+// The exponent bookkeeping is integer-pipe work; the FP64 pipe sees one DMUL per factor.
+struct LogProduct {
+    double mant;        // product of the factors' mantissas since the last renormalisation
+    long long expo;     // sum of the factors' unbiased exponents
+    int bad;            // a factor was negative, denormal, inf or NaN (result: NaN)
+    int zero;           // a factor was exactly zero (result: -inf)
+
+    __device__ __forceinline__ void reset() { mant = 1.0; expo = 0; bad = 0; zero = 0; }
+
+    // multiply by x, a normal positive double
+    __device__ __forceinline__ void mul(double x) {
+        const int hi = __double2hiint(x);
+        bad |= ((unsigned)(hi - 0x00100000) >= 0x7fe00000u);
+        expo += (hi >> 20) - 1023;
+        mant *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    }
+
+    // multiply by m * 2^e with m >= 0; m == 0 marks the whole product as zero
+    __device__ __forceinline__ void mul_ext(double m, int e) {
+        const int hi = __double2hiint(m);
+        const bool is_zero = (hi | __double2loint(m)) == 0;
+        zero |= is_zero;
+        bad |= (!is_zero && (unsigned)(hi - 0x00100000) >= 0x7fe00000u);
+        expo += is_zero ? 0 : (long long)((hi >> 20) - 1023 + e);
+        mant *= is_zero ? 1.0 : __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(m));
+    }
+
+    // fold the mantissa's own exponent into `expo`; call at least every 1000 factors
+    __device__ __forceinline__ void renormalise() {
+        const int hi = __double2hiint(mant);
+        expo += (hi >> 20) - 1023;
+        mant = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(mant));
+    }
+
+    // ln of the product
+    __device__ __forceinline__ double ln() {
+        renormalise();
+        const double r = fma((double)expo, kLn2, log(mant));
+        return bad ? __longlong_as_double(0x7ff8000000000000LL)
+                   : (zero ? __longlong_as_double(0xfff0000000000000LL) : r);
+    }
+};
+
+// 2^f for |f| <= 0.5 (Taylor in f*ln2, degree 12: truncation 2e-16 relative), 12 DFMA.
+__device__ __forceinline__ double exp2_frac(double f) {
+    const double c1 = 6.93147180559945286e-01, c2 = 2.40226506959100694e-01, c3 = 5.55041086648215762e-02,
+                 c4 = 9.61812910762847687e-03, c5 = 1.33335581464284411e-03, c6 = 1.54035303933816099e-04,
+                 c7 = 1.52527338040598403e-05, c8 = 1.32154867901443095e-06, c9 = 1.01780860092396998e-07,
+                 c10 = 7.05491162080112333e-09, c11 = 4.44553827187081150e-10, c12 = 2.56784359934882051e-11;
+    double p = c12;
+    p = fma(p, f, c11);
+    p = fma(p, f, c10);
+    p = fma(p, f, c9);
+    p = fma(p, f, c8);
+    p = fma(p, f, c7);
+    p = fma(p, f, c6);
+    p = fma(p, f, c5);
+    p = fma(p, f, c4);
+    p = fma(p, f, c3);
+    p = fma(p, f, c2);
+    p = fma(p, f, c1);
+    return fma(p, f, 1.0);
+}
+
+// exp(x) = mant * 2^expo for x <= 0 (moderate x > 0 works too); mant in [2^-0.5, 2^0.5].
+// x <= -2^30 ln2 (including -inf) saturates to an exponent that flushes to zero downstream;
+// NaN or x >= 2^30 ln2 sets `invalid`.  All range handling is integer-pipe work on the high
+// word, the FP64 pipe only sees the 15 multiply-adds.
+__device__ __forceinline__ void exp_split(double x, double &mant, int &expo, int &invalid) {
+    const double kMagic = 6755399441055744.0;            // 1.5 * 2^52: round-to-nearest-integer trick
+    const double t = x * kLog2e;
+    const int thi = __double2hiint(t);
+    const unsigned uthi = (unsigned)thi & 0x7fffffffu;
+    const bool huge = uthi >= 0x41d00000u;               // |t| >= 2^30, inf or NaN
+    const bool isnan = uthi > 0x7ff00000u || (uthi == 0x7ff00000u && __double2loint(t) != 0);
+    const double shifted = t + kMagic;
+    const int n = __double2loint(shifted);
+    const double nf = shifted - kMagic;
+    // f = x*log2e - n with the rounding error of the product recovered by the fma
+    const double f = fma(x, kLog2e, -nf);
+    const double m = exp2_frac(f);
+    expo = huge ? -(1 << 30) : n;
+    mant = huge ? 1.0 : m;
+    invalid |= (huge && (thi >= 0 || isnan)) ? 1 : 0;
+}
+
+// a_m*2^a_e + b_m*2^b_e as (mantissa, exponent); both mantissas >= 0.
+// The component with the smaller exponent is scaled down and flushed to zero beyond 2^-1022 --
+// the analogue of exp() underflowing in the reference's max-shifted form (analysis/runner.py:280-286).
+// If the component with the larger exponent has zero weight the other one is returned exactly
+// as long as the reference's exp(l_small - l_big) would not have underflowed (|d| <= 1074).
+__device__ __forceinline__ void ext_add(double a_m, int a_e, double b_m, int b_e, double &m, int &e) {
+    const int d = a_e - b_e;
+    const bool a_big = d >= 0;
+    const double big = a_big ? a_m : b_m;
+    const double small = a_big ? b_m : a_m;
+    const int k = a_big ? a_e : b_e;
+    const int ks = a_big ? b_e : a_e;
+    const int ad = abs(d);
+    const double sum = fma(small, pow2_nonpos(-ad), big);
+    const bool big_zero = (__double2hiint(big) | __double2loint(big)) == 0;
+    // both components saturated (exp of something below -2^29 ln2): the sum is zero for every purpose
+    const bool vanished = k < -(1 << 29);
+    const bool keep_small = big_zero && ad <= 1074 && ks >= -(1 << 29);
+    e = vanished ? 0 : (keep_small ? ks : k);
+    m = vanished ? 0.0 : (keep_small ? small : sum);
+}
+
+}  // namespace mcd

@@ -1,0 +1,339 @@
+// Device-resident affine-invariant ensemble sampler: emcee's default red/blue StretchMove(a = 2)
+// as the reference drives it (analysis/runner.py:403,416-419), with positions, log-probabilities,
+// random numbers, proposals and accept/reject all on the GPU.  One emcee iteration is
+//     split (random red/blue partition) -> [propose -> lnprob kernel -> accept] x 2 -> store
+// captured once as a CUDA graph and replayed per step: no host round trip inside a chain.
+//
+// emcee is a third-party dependency of the reference (unpinned, not vendored); the algorithm
+// restated here is its published one (Goodman & Weare 2010; emcee 3 `RedBlueMove.propose`):
+//   z = ((a-1) u + 1)^2 / a,  q = c_j - (c_j - s) z,  accept if (P-1) ln z + lnp(q) - lnp(s) > ln u'
+// with the complementary walker j drawn uniformly and the second half seeing the updated first.
+// Random numbers: Philox4x32-10, counter = (step, half, walker, stream id), key = seed.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "mcd_internal.h"
+
+using namespace mcd;
+
+namespace {
+
+constexpr int kMaxWalkers = 4096;   // split_kernel keeps one 64-bit key per walker in 32 KiB of shared memory
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += W0;
+        k.y += W1;
+    }
+    return c;
+}
+
+// two uniforms in [0, 1) with 53 random bits each
+__device__ __forceinline__ void uniforms(uint64_t seed, uint32_t step, uint32_t half, uint32_t walker, uint32_t purpose,
+                                         double &u0, double &u1) {
+    const uint4 r = philox4x32_10(make_uint4(step, half, walker, purpose), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint64_t a = ((uint64_t)r.x << 32) | r.y, b = ((uint64_t)r.z << 32) | r.w;
+    u0 = (double)(a >> 11) * (1.0 / 9007199254740992.0);
+    u1 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
+}
+
+struct Ensemble {
+    int n_walkers, n_theta, n0, n1;     // n0 = first ("red") half, n1 = second
+    uint64_t seed;
+    double a;
+    double *pos;          // [W][P]
+    double *lnp;          // [W]
+    double *q;            // [n0][P] proposals of the current half
+    double *lnp_q;        // [n0]
+    double *logz;         // [n0]
+    int *perm;            // [W]: perm[0:n0] = red walkers, perm[n0:W] = blue
+    long long *n_accepted;   // [W]
+    unsigned int *step;      // [2]: global step counter, step inside the current run() chunk
+    double *chain;        // [chunk][W][P] or nullptr
+    double *chain_lnp;    // [chunk][W]
+};
+
+// random red/blue partition: rank of a random key (emcee: inds = arange(W) % 2; shuffle(inds))
+__global__ void split_kernel(Ensemble E) {
+    extern __shared__ unsigned long long keys[];
+    const uint32_t step = E.step[0];
+    for (int w = threadIdx.x; w < E.n_walkers; w += blockDim.x) {
+        const uint4 r = philox4x32_10(make_uint4(step, 2u, (uint32_t)w, 7u), make_uint2((uint32_t)E.seed, (uint32_t)(E.seed >> 32)));
+        keys[w] = (((unsigned long long)r.x << 32) | r.y);
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < E.n_walkers; w += blockDim.x) {
+        const unsigned long long mine = keys[w];
+        int rank = 0;
+        for (int o = 0; o < E.n_walkers; ++o) {
+            const unsigned long long other = keys[o];
+            rank += (other < mine) || (other == mine && o < w);
+        }
+        E.perm[rank] = w;
+    }
+}
+
+__global__ void propose_kernel(Ensemble E, int half) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ns = half == 0 ? E.n0 : E.n1;
+    const int nc = E.n_walkers - ns;
+    if (k >= ns) return;
+    const int *active = E.perm + (half == 0 ? 0 : E.n0);
+    const int *other = E.perm + (half == 0 ? E.n0 : 0);
+    double u0, u1;
+    uniforms(E.seed, E.step[0], (uint32_t)half, (uint32_t)k, 0u, u0, u1);
+    const double t = (E.a - 1.0) * u0 + 1.0;
+    const double z = t * t / E.a;
+    int j = (int)(u1 * nc);
+    j = j >= nc ? nc - 1 : j;
+    const double *s = E.pos + (size_t)active[k] * E.n_theta;
+    const double *c = E.pos + (size_t)other[j] * E.n_theta;
+    double *q = E.q + (size_t)k * E.n_theta;
+    for (int p = 0; p < E.n_theta; ++p) q[p] = c[p] - (c[p] - s[p]) * z;
+    E.logz[k] = (E.n_theta - 1.0) * log(z);
+}
+
+__global__ void accept_kernel(Ensemble E, int half) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ns = half == 0 ? E.n0 : E.n1;
+    if (k >= ns) return;
+    const int w = E.perm[(half == 0 ? 0 : E.n0) + k];
+    double u0, u1;
+    uniforms(E.seed, E.step[0], (uint32_t)half, (uint32_t)k, 1u, u0, u1);
+    const double new_lp = E.lnp_q[k];
+    const double diff = E.logz[k] + new_lp - E.lnp[w];
+    if (diff > log(u0)) {     // NaN never accepts
+        const double *q = E.q + (size_t)k * E.n_theta;
+        double *s = E.pos + (size_t)w * E.n_theta;
+        for (int p = 0; p < E.n_theta; ++p) s[p] = q[p];
+        E.lnp[w] = new_lp;
+        E.n_accepted[w] += 1;
+    }
+}
+
+__global__ void store_kernel(Ensemble E) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int local = E.step[1];
+    const int total = E.n_walkers * E.n_theta;
+    if (E.chain) {
+        if (i < total) E.chain[(size_t)local * total + i] = E.pos[i];
+        if (i < E.n_walkers) E.chain_lnp[(size_t)local * E.n_walkers + i] = E.lnp[i];
+    }
+}
+
+__global__ void advance_kernel(Ensemble E) {
+    E.step[0] += 1u;
+    E.step[1] += 1u;
+}
+
+}  // namespace
+
+struct mcd_ensemble {
+    mcd_handle *h = nullptr;
+    int device = 0;
+    Ensemble E{};
+    cudaStream_t stream = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool graph_stores = false;
+    size_t chain_cap_steps = 0;
+    bool have_state = false;
+};
+
+static void free_ensemble(mcd_ensemble *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->exec) cudaGraphExecDestroy(e->exec);
+    if (e->graph) cudaGraphDestroy(e->graph);
+    cudaFree(e->E.pos);
+    cudaFree(e->E.lnp);
+    cudaFree(e->E.q);
+    cudaFree(e->E.lnp_q);
+    cudaFree(e->E.logz);
+    cudaFree(e->E.perm);
+    cudaFree(e->E.n_accepted);
+    cudaFree(e->E.step);
+    cudaFree(e->E.chain);
+    cudaFree(e->E.chain_lnp);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" void mcd_ensemble_destroy(mcd_ensemble *e) { free_ensemble(e); }
+
+#define ENS_CUDA(call)                        \
+    do {                                      \
+        if ((call) != cudaSuccess) return -2; \
+    } while (0)
+
+extern "C" int mcd_ensemble_create(mcd_handle *h, int32_t n_walkers, uint64_t seed, double stretch_a, mcd_ensemble **out) {
+    if (!h || !out) return -1;
+    *out = nullptr;
+    mcd_info info;
+    if (mcd_get_info(h, &info) != 0) return -1;
+    // emcee: "nwalkers >= 2 * ndim" (RuntimeError otherwise)
+    if (n_walkers < 2 || n_walkers > kMaxWalkers || n_walkers < 2 * info.n_theta || !(stretch_a > 1.0)) return -1;
+    mcd_ensemble *e = new (std::nothrow) mcd_ensemble();
+    if (!e) return -4;
+    e->h = h;
+    e->device = handle_device(h);
+    Ensemble &E = e->E;
+    E.n_walkers = n_walkers;
+    E.n_theta = info.n_theta;
+    E.n0 = (n_walkers + 1) / 2;
+    E.n1 = n_walkers - E.n0;
+    E.seed = seed;
+    E.a = stretch_a;
+    const size_t P = (size_t)std::max(1, E.n_theta);
+    bool ok = cudaSetDevice(e->device) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&E.pos, sizeof(double) * n_walkers * P) == cudaSuccess;
+    ok = ok && cudaMalloc(&E.lnp, sizeof(double) * n_walkers) == cudaSuccess;
+    ok = ok && cudaMalloc(&E.q, sizeof(double) * E.n0 * P) == cudaSuccess;
+    ok = ok && cudaMalloc(&E.lnp_q, sizeof(double) * E.n0) == cudaSuccess;
+    ok = ok && cudaMalloc(&E.logz, sizeof(double) * E.n0) == cudaSuccess;
+    ok = ok && cudaMalloc(&E.perm, sizeof(int) * n_walkers) == cudaSuccess;
+    ok = ok && cudaMalloc(&E.n_accepted, sizeof(long long) * n_walkers) == cudaSuccess;
+    ok = ok && cudaMalloc(&E.step, sizeof(unsigned int) * 2) == cudaSuccess;
+    ok = ok && cudaMemset(E.n_accepted, 0, sizeof(long long) * n_walkers) == cudaSuccess;
+    ok = ok && cudaMemset(E.step, 0, sizeof(unsigned int) * 2) == cudaSuccess;
+    if (!ok) {
+        free_ensemble(e);
+        return -2;
+    }
+    *out = e;
+    return 0;
+}
+
+extern "C" int mcd_ensemble_set_state(mcd_ensemble *e, const double *pos_host) {
+    if (!e || !pos_host) return -1;
+    ENS_CUDA(cudaSetDevice(e->device));
+    Ensemble &E = e->E;
+    ENS_CUDA(cudaMemcpyAsync(E.pos, pos_host, sizeof(double) * E.n_walkers * E.n_theta, cudaMemcpyHostToDevice, e->stream));
+    if (int rc = launch_ensemble(e->h, E.pos, E.n_walkers, E.lnp, 1, e->stream)) return rc;
+    ENS_CUDA(cudaStreamSynchronize(e->stream));
+    e->have_state = true;
+    return 0;
+}
+
+static int enqueue_step(mcd_ensemble *e) {
+    Ensemble &E = e->E;
+    const int threads = 128;
+    const int split_threads = std::min(1024, ((E.n_walkers + 31) / 32) * 32);
+    split_kernel<<<1, split_threads, sizeof(unsigned long long) * E.n_walkers, e->stream>>>(E);
+    for (int half = 0; half < 2; ++half) {
+        const int ns = half == 0 ? E.n0 : E.n1;
+        if (ns == 0) continue;
+        propose_kernel<<<(ns + threads - 1) / threads, threads, 0, e->stream>>>(E, half);
+        if (int rc = launch_ensemble(e->h, E.q, ns, E.lnp_q, 1, e->stream)) return rc;
+        accept_kernel<<<(ns + threads - 1) / threads, threads, 0, e->stream>>>(E, half);
+    }
+    const int total = E.n_walkers * std::max(1, E.n_theta);
+    store_kernel<<<(total + 255) / 256, 256, 0, e->stream>>>(E);
+    advance_kernel<<<1, 1, 0, e->stream>>>(E);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+static int build_graph(mcd_ensemble *e) {
+    if (e->exec) {
+        cudaGraphExecDestroy(e->exec);
+        e->exec = nullptr;
+    }
+    if (e->graph) {
+        cudaGraphDestroy(e->graph);
+        e->graph = nullptr;
+    }
+    // size the likelihood scratch for both half-ensemble shapes outside the capture
+    Ensemble &E = e->E;
+    if (int rc = launch_ensemble(e->h, E.pos, E.n0, E.lnp_q, 1, e->stream)) return rc;
+    if (E.n1 > 0)
+        if (int rc = launch_ensemble(e->h, E.pos, E.n1, E.lnp_q, 1, e->stream)) return rc;
+    ENS_CUDA(cudaStreamSynchronize(e->stream));
+    ENS_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_step(e);
+    cudaGraph_t g = nullptr;
+    const cudaError_t end = cudaStreamEndCapture(e->stream, &g);
+    if (rc != 0 || end != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        return rc ? rc : -2;
+    }
+    e->graph = g;
+    ENS_CUDA(cudaGraphInstantiate(&e->exec, e->graph, 0));
+    return 0;
+}
+
+extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_host, double *lnprob_host,
+                                int64_t *n_accepted_host) {
+    if (!e || n_steps < 0) return -1;
+    if (!e->have_state) return -1;
+    ENS_CUDA(cudaSetDevice(e->device));
+    Ensemble &E = e->E;
+    const size_t P = (size_t)std::max(1, E.n_theta);
+    const size_t per_step = (size_t)E.n_walkers * P;
+    const bool store = chain_host != nullptr || lnprob_host != nullptr;
+    // chain chunks of at most 256 MiB on the device
+    size_t chunk = std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, n_steps), ((size_t)256 << 20) / (per_step * 8)));
+    if (store && chunk > e->chain_cap_steps) {
+        cudaFree(E.chain);
+        cudaFree(E.chain_lnp);
+        E.chain = E.chain_lnp = nullptr;
+        e->chain_cap_steps = 0;
+        ENS_CUDA(cudaMalloc(&E.chain, sizeof(double) * chunk * per_step));
+        ENS_CUDA(cudaMalloc(&E.chain_lnp, sizeof(double) * chunk * E.n_walkers));
+        e->chain_cap_steps = chunk;
+        if (e->exec) {   // pointers baked into the graph changed
+            cudaGraphExecDestroy(e->exec);
+            e->exec = nullptr;
+        }
+    }
+    if (store) chunk = std::min(chunk, e->chain_cap_steps);
+    // the graph bakes in whether the chain is stored (E.chain pointer): rebuild when that changes
+    double *saved_chain = E.chain, *saved_lnp = E.chain_lnp;
+    if (!store) E.chain = E.chain_lnp = nullptr;
+    if (!e->exec || e->graph_stores != store) {
+        const int rc = build_graph(e);
+        if (rc) {
+            E.chain = saved_chain;
+            E.chain_lnp = saved_lnp;
+            return rc;
+        }
+        e->graph_stores = store;
+    }
+    int rc = 0;
+    for (int done = 0; done < n_steps && rc == 0;) {
+        const int todo = (int)std::min<size_t>(chunk, (size_t)(n_steps - done));
+        if (cudaMemsetAsync(E.step + 1, 0, sizeof(unsigned int), e->stream) != cudaSuccess) { rc = -2; break; }
+        for (int s = 0; s < todo; ++s)
+            if (cudaGraphLaunch(e->exec, e->stream) != cudaSuccess) { rc = -2; break; }
+        if (rc) break;
+        if (chain_host && cudaMemcpyAsync(chain_host + (size_t)done * per_step, E.chain, sizeof(double) * todo * per_step,
+                                          cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) rc = -2;
+        if (lnprob_host && cudaMemcpyAsync(lnprob_host + (size_t)done * E.n_walkers, E.chain_lnp,
+                                           sizeof(double) * todo * E.n_walkers, cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) rc = -2;
+        if (cudaStreamSynchronize(e->stream) != cudaSuccess) rc = -2;
+        done += todo;
+    }
+    E.chain = saved_chain;
+    E.chain_lnp = saved_lnp;
+    if (rc == 0 && n_accepted_host) {
+        if (cudaMemcpy(n_accepted_host, E.n_accepted, sizeof(long long) * E.n_walkers, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -2;
+    }
+    if (rc == 0 && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = -2;
+    return rc;
+}
+
+extern "C" int mcd_ensemble_get_state(mcd_ensemble *e, double *pos_host, double *lnprob_host) {
+    if (!e) return -1;
+    ENS_CUDA(cudaSetDevice(e->device));
+    ENS_CUDA(cudaStreamSynchronize(e->stream));
+    if (pos_host) ENS_CUDA(cudaMemcpy(pos_host, e->E.pos, sizeof(double) * e->E.n_walkers * e->E.n_theta, cudaMemcpyDeviceToHost));
+    if (lnprob_host) ENS_CUDA(cudaMemcpy(lnprob_host, e->E.lnp, sizeof(double) * e->E.n_walkers, cudaMemcpyDeviceToHost));
+    return 0;
+}

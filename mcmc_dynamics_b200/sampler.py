@@ -1,0 +1,232 @@
+"""Ensemble samplers behind ``Runner.__call__``.
+
+The reference hands ``self.lnprob`` to ``emcee.EnsembleSampler`` (``analysis/runner.py:403``) and
+drives it with ``run_mcmc`` (``runner.py:416-419``).  emcee is an unpinned third-party dependency
+that is not vendored by the reference; two stand-ins with the part of its interface the reference
+uses (``run_mcmc``, ``chain``, ``lnprobability``, ``iteration``, ``acceptance_fraction``):
+
+* :class:`HostEnsembleSampler` -- the red/blue stretch move (Goodman & Weare 2010; emcee 3
+  ``RedBlueMove`` / ``StretchMove(a=2)``) on the host, calling the model's ``lnprob`` once per
+  half-ensemble with an ``[n, ndim]`` array (``vectorize=True`` semantics).  If emcee is importable,
+  :func:`make_host_sampler` returns a real ``emcee.EnsembleSampler(..., vectorize=True)`` instead.
+* :class:`DeviceEnsembleSampler` -- the same move with state, random numbers, proposals and
+  accept/reject on the GPU (``csrc/mcd_sampler.cu``), one CUDA graph launch per step.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native
+
+
+class HostEnsembleSampler(object):
+    """Minimal emcee-compatible ensemble sampler (vectorised log-probability calls)."""
+
+    def __init__(self, nwalkers, ndim, log_prob_fn, a=2.0, seed=None, vectorize=True):
+        if nwalkers < 2 * ndim:
+            raise RuntimeError("It is unadvisable to use a red-blue move with fewer walkers than twice the number "
+                               "of dimensions.")
+        self.nwalkers = int(nwalkers)
+        self.ndim = int(ndim)
+        self.log_prob_fn = log_prob_fn
+        self.a = float(a)
+        self.vectorize = vectorize
+        self._random = np.random.RandomState(seed)
+        self.iteration = 0
+        self._chain = []
+        self._lnprob = []
+        self.naccepted = np.zeros(self.nwalkers, dtype=np.int64)
+        self.n_log_prob_calls = 0
+
+    # -- emcee accessors used by the reference (runner.py:422,429,471-472) -----------------------
+    @property
+    def chain(self):
+        """[nwalkers, nsteps, ndim]"""
+        if not self._chain:
+            return np.empty((self.nwalkers, 0, self.ndim))
+        return np.swapaxes(np.asarray(self._chain), 0, 1)
+
+    @property
+    def lnprobability(self):
+        """[nwalkers, nsteps]"""
+        if not self._lnprob:
+            return np.empty((self.nwalkers, 0))
+        return np.asarray(self._lnprob).T
+
+    def get_chain(self, discard=0, flat=False):
+        chain = np.asarray(self._chain)[discard:]
+        return chain.reshape((-1, self.ndim)) if flat else chain
+
+    def get_log_prob(self, discard=0, flat=False):
+        lnp = np.asarray(self._lnprob)[discard:]
+        return lnp.reshape(-1) if flat else lnp
+
+    @property
+    def acceptance_fraction(self):
+        return self.naccepted / float(max(1, self.iteration))
+
+    @property
+    def random_state(self):
+        return self._random.get_state()
+
+    # -- sampling -----------------------------------------------------------------------------
+    def compute_log_prob(self, coords):
+        coords = np.asarray(coords, dtype=np.float64)
+        if np.any(np.isinf(coords)):
+            raise ValueError("At least one parameter value was infinite")
+        if np.any(np.isnan(coords)):
+            raise ValueError("At least one parameter value was NaN")
+        self.n_log_prob_calls += 1
+        if self.vectorize:
+            log_prob = np.asarray(self.log_prob_fn(coords), dtype=np.float64)
+        else:
+            log_prob = np.array([float(self.log_prob_fn(row)) for row in coords], dtype=np.float64)
+        if np.any(np.isnan(log_prob)):
+            raise ValueError("Probability function returned NaN")
+        return log_prob
+
+    def run_mcmc(self, initial_state, nsteps, log_prob0=None, rstate0=None, progress=False, store=True, **kwargs):
+        coords = np.array(initial_state, dtype=np.float64)
+        if coords.shape != (self.nwalkers, self.ndim):
+            raise ValueError("incompatible input dimensions {0}".format(coords.shape))
+        if rstate0 is not None:
+            self._random.set_state(rstate0)
+        if self.nwalkers > 1 and np.linalg.cond(np.atleast_2d(np.cov(coords, rowvar=False))) > 1e8:
+            raise ValueError("Initial state has a large condition number. Make sure that your walkers are "
+                             "linearly independent for the best performance")
+        log_prob = self.compute_log_prob(coords) if log_prob0 is None else np.array(log_prob0, dtype=np.float64)
+        if np.any(np.isnan(log_prob)):
+            raise ValueError("The initial log_prob was NaN")
+
+        rng = self._random
+        for _ in range(int(nsteps)):
+            inds = np.arange(self.nwalkers) % 2
+            rng.shuffle(inds)
+            for split in range(2):
+                s_mask = inds == split
+                s = coords[s_mask]
+                c = coords[~s_mask]
+                ns, nc = len(s), len(c)
+                zz = ((self.a - 1.0) * rng.rand(ns) + 1) ** 2.0 / self.a
+                factors = (self.ndim - 1.0) * np.log(zz)
+                rint = rng.randint(nc, size=(ns,))
+                q = c[rint] - (c[rint] - s) * zz[:, None]
+                new_log_prob = self.compute_log_prob(q)
+                with np.errstate(invalid='ignore'):
+                    lnpdiff = factors + new_log_prob - log_prob[s_mask]
+                accepted = lnpdiff > np.log(rng.rand(ns))
+                idx = np.flatnonzero(s_mask)[accepted]
+                coords[idx] = q[accepted]
+                log_prob[idx] = new_log_prob[accepted]
+                self.naccepted[idx] += 1
+            self.iteration += 1
+            if store:
+                self._chain.append(coords.copy())
+                self._lnprob.append(log_prob.copy())
+        return coords, log_prob, rng.get_state()
+
+
+def make_host_sampler(nwalkers, ndim, log_prob_fn, seed=None):
+    """emcee in vectorised mode when it is installed, else :class:`HostEnsembleSampler`."""
+    try:
+        import emcee
+    except ImportError:
+        return HostEnsembleSampler(nwalkers, ndim, log_prob_fn, seed=seed)
+    sampler = emcee.EnsembleSampler(nwalkers, ndim, log_prob_fn, vectorize=True)
+    if seed is not None:
+        sampler._random = np.random.RandomState(seed)
+    return sampler
+
+
+class DeviceEnsembleSampler(object):
+    """Stretch-move ensemble whose whole state lives on the GPU (``mcd_ensemble_*`` in
+    ``include/mcd_b200.h``).  ``packed`` is the :class:`~mcmc_dynamics_b200.pack.PackedModel` whose
+    ``lnprob`` the walkers sample."""
+
+    def __init__(self, nwalkers, ndim, packed, a=2.0, seed=None):
+        if nwalkers < 2 * ndim:
+            raise RuntimeError("It is unadvisable to use a red-blue move with fewer walkers than twice the number "
+                               "of dimensions.")
+        if ndim != packed.n_theta:
+            raise ValueError('ndim does not match the packed model')
+        self.nwalkers = int(nwalkers)
+        self.ndim = int(ndim)
+        self._packed = packed          # keeps the handle alive
+        self._lib = _native.load_library()
+        if seed is None:
+            seed = int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0])
+        handle = ctypes.c_void_p()
+        rc = self._lib.mcd_ensemble_create(packed.handle, self.nwalkers, ctypes.c_uint64(int(seed)), float(a),
+                                           ctypes.byref(handle))
+        if rc != 0:
+            raise _native.NativeError('mcd_ensemble_create failed with code {0}'.format(rc))
+        self._handle = handle
+        self.iteration = 0
+        self._chain = []
+        self._lnprob = []
+        self.naccepted = np.zeros(self.nwalkers, dtype=np.int64)
+        self._have_state = False
+
+    @property
+    def chain(self):
+        if not self._chain:
+            return np.empty((self.nwalkers, 0, self.ndim))
+        return np.swapaxes(np.concatenate(self._chain, axis=0), 0, 1)
+
+    @property
+    def lnprobability(self):
+        if not self._lnprob:
+            return np.empty((self.nwalkers, 0))
+        return np.concatenate(self._lnprob, axis=0).T
+
+    def get_chain(self, discard=0, flat=False):
+        chain = np.concatenate(self._chain, axis=0)[discard:] if self._chain else np.empty((0, self.nwalkers, self.ndim))
+        return chain.reshape((-1, self.ndim)) if flat else chain
+
+    @property
+    def acceptance_fraction(self):
+        return self.naccepted / float(max(1, self.iteration))
+
+    def run_mcmc(self, initial_state, nsteps, log_prob0=None, rstate0=None, progress=False, store=True, **kwargs):
+        nsteps = int(nsteps)
+        if initial_state is not None and (not self._have_state or not np.array_equal(initial_state, self._last_pos)):
+            pos = _native.contiguous(initial_state)
+            if pos.shape != (self.nwalkers, self.ndim):
+                raise ValueError("incompatible input dimensions {0}".format(pos.shape))
+            rc = self._lib.mcd_ensemble_set_state(self._handle, _native.as_double_ptr(pos))
+            if rc != 0:
+                raise _native.NativeError('mcd_ensemble_set_state failed with code {0}'.format(rc))
+            self._have_state = True
+        chain = np.empty((nsteps, self.nwalkers, self.ndim), dtype=np.float64) if store else None
+        lnp = np.empty((nsteps, self.nwalkers), dtype=np.float64) if store else None
+        nacc = np.zeros(self.nwalkers, dtype=np.int64)
+        rc = self._lib.mcd_ensemble_run(
+            self._handle, nsteps, _native.as_double_ptr(chain) if store else None,
+            _native.as_double_ptr(lnp) if store else None, nacc.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
+        if rc != 0:
+            raise _native.NativeError('mcd_ensemble_run failed with code {0}'.format(rc))
+        self.naccepted = nacc
+        self.iteration += nsteps
+        if store:
+            self._chain.append(chain)
+            self._lnprob.append(lnp)
+        pos = np.empty((self.nwalkers, self.ndim), dtype=np.float64)
+        last = np.empty(self.nwalkers, dtype=np.float64)
+        rc = self._lib.mcd_ensemble_get_state(self._handle, _native.as_double_ptr(pos), _native.as_double_ptr(last))
+        if rc != 0:
+            raise _native.NativeError('mcd_ensemble_get_state failed with code {0}'.format(rc))
+        if np.any(np.isnan(last)):
+            raise ValueError("Probability function returned NaN")
+        self._last_pos = pos.copy()
+        return pos, last, None
+
+    def close(self):
+        if self._handle is not None:
+            self._lib.mcd_ensemble_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,73 @@
+"""Star-sharded likelihood across the GPUs of one box.
+
+Per-star terms are independent and ``lnlike_w = sum_i term(w, i)``, so rank ``g`` of ``G`` packs the
+contiguous star range ``[g N / G, (g + 1) N / G)`` of the catalogue, evaluates ALL walkers of a call
+over its shard (``mcd_lnprob_partial_device``) and the per-walker partial sums -- ``n_walkers``
+float64 values, 4 KiB for 512 walkers -- are combined with one ``all_reduce(SUM)`` over NCCL
+(NVLink 5 / NVSwitch).  A walker outside its box prior is ``-inf`` on every rank, so the sum is
+``-inf`` too.  This replaces the walker-parallel process pool of the reference
+(``analysis/runner.py:398-403``) at multi-GPU scale.
+
+``torch.distributed`` is plumbing: process group, NCCL communicator, device tensors.
+"""
+import numpy as np
+
+
+def shard_range(n_stars, rank, world_size):
+    """Contiguous star range of `rank`: sizes differ by at most one star."""
+    base, extra = divmod(int(n_stars), int(world_size))
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_columns(columns, rank, world_size):
+    n = len(next(iter(columns.values())))
+    lo, hi = shard_range(n, rank, world_size)
+    return {name: np.ascontiguousarray(values[lo:hi]) for name, values in columns.items()}
+
+
+class ShardedLikelihood(object):
+    """``lnprob`` of a model whose catalogue is split over the ranks of a process group.
+
+    Parameters
+    ----------
+    model : a model object built on THIS rank's shard of the catalogue (device = this rank's GPU)
+    group : torch.distributed process group or None (default group); with world size 1 no
+        collective is issued.
+    """
+
+    def __init__(self, model, group=None):
+        import torch
+        import torch.distributed as dist
+        self._torch = torch
+        self._dist = dist
+        self.model = model
+        self.group = group
+        self.world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.device = torch.device('cuda', model.device)
+        self._pinned_in = None
+        self._pinned_out = None
+
+    def lnprob_tensor(self, theta):
+        """theta: [n_walkers, n_free] float64 CUDA tensor, identical on every rank.  Returns the
+        full-catalogue lnprob on every rank (asynchronous on the current stream)."""
+        partial = self.model.pack().lnprob_partial_tensor(theta)
+        if self.world_size > 1:
+            self._dist.all_reduce(partial, op=self._dist.ReduceOp.SUM, group=self.group)
+        return partial
+
+    def lnprob(self, theta):
+        """Host array in, host array out (what the sampler calls): pinned staging, H2D, shard kernel,
+        all-reduce, D2H."""
+        torch = self._torch
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        n, p = theta.shape
+        if self._pinned_in is None or self._pinned_in.shape[0] < n or self._pinned_in.shape[1] != p:
+            self._pinned_in = torch.empty((max(n, 64), p), dtype=torch.float64).pin_memory()
+            self._pinned_out = torch.empty((max(n, 64),), dtype=torch.float64).pin_memory()
+        self._pinned_in[:n].copy_(torch.from_numpy(theta))
+        dev = self._pinned_in[:n].to(self.device, non_blocking=True)
+        out = self.lnprob_tensor(dev)
+        self._pinned_out[:n].copy_(out, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._pinned_out[:n].numpy().copy()
