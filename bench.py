@@ -37,7 +37,7 @@ SEED = 4
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--stars', type=int, default=10_000_000)
@@ -317,6 +317,7 @@ def gpu_run(args):
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     hbm_source = 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
 
+    info = packed.info()
     terms_per_launch = float(half) * float(n_shard)
     flops_per_launch = terms_per_launch * info['flops_per_term']
     achieved_tflops = flops_per_launch / (kernel_ms * 1e-3) / 1e12

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_lib', 'libmcd_b200.so')
+#: MCD_B200_LIB selects another build of the same library (A/B runs of kernel tuning knobs)
+LIB_PATH = os.environ.get('MCD_B200_LIB') or os.path.join(_HERE, '_lib', 'libmcd_b200.so')
 TORCH_LIB_PATH = os.path.join(_HERE, '_lib', 'libmcd_torch.so')
 
 ABI_VERSION = 1

@@ -43,8 +43,8 @@ struct mcd_handle {
     int32_t *icol = nullptr;
     double ra0_deg = 0.0;
     // launch scratch
-    double *partials = nullptr;
-    size_t partials_cap = 0;
+    double *partials = nullptr, *partials2 = nullptr;
+    size_t partials_cap = 0, partials2_cap = 0;
     unsigned int *counters = nullptr;
     int counters_cap = 0;
     // staging for the host-buffer entry points
@@ -138,6 +138,7 @@ extern "C" void mcd_destroy(mcd_handle *h) {
     for (auto &p : h->cols) cudaFree(p);
     cudaFree(h->icol);
     cudaFree(h->partials);
+    cudaFree(h->partials2);
     cudaFree(h->counters);
     cudaFree(h->theta_dev);
     cudaFree(h->out_dev);
@@ -238,19 +239,24 @@ static void choose_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p)
     p.wl = best_wl;
     p.slices = best_s;
     p.n_groups = best_g;
-    // one wave of CTAs: star chunks per walker group
+    // star chunks per walker group: kWaves waves of CTAs when the catalogue is large enough, so that
+    // SMs whose CTAs finish early pick up new ones (a single wave leaves the FP64 pipe idle in the tail)
     const int wave = std::max(1, h->sm_count * h->blocks_per_sm);
-    const int chunks_target = std::max(1, wave / p.n_groups);
+    const int per_wave = std::max(1, wave / p.n_groups);
     // stars per stage: large enough that every slice has work, small enough to spread a small
     // catalogue over the machine
-    long long tile = (h->n + chunks_target - 1) / chunks_target;
-    tile = std::max<long long>(tile, p.slices);
+    long long tile = (h->n + per_wave - 1) / per_wave;
+    tile = std::max<long long>(tile, 2LL * p.slices);
     tile = ((tile + 15) / 16) * 16;
     tile = std::min<long long>(std::max<long long>(tile, 16), kMaxTile);
     p.tile = (int)tile;
     p.n_tiles = (int)((h->n + tile - 1) / tile);
+    const int chunks_target = per_wave * kWaves;
     p.tiles_per_chunk = std::max(1, (p.n_tiles + chunks_target - 1) / chunks_target);
+    p.tiles_per_chunk = std::max(p.tiles_per_chunk, std::min(4, std::max(1, p.n_tiles / per_wave)));
     p.n_chunks = std::max(1, (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk);
+    p.super = kSuper;
+    p.n_super = (p.n_chunks + kSuper - 1) / kSuper;
 }
 
 static int ensure_scratch(mcd_handle *h, const LaunchParams &p) {
@@ -262,11 +268,20 @@ static int ensure_scratch(mcd_handle *h, const LaunchParams &p) {
         MCD_CUDA(cudaMalloc(&h->partials, sizeof(double) * need));
         h->partials_cap = need;
     }
-    if (p.n_groups > h->counters_cap) {
+    const size_t need2 = (size_t)p.n_super * p.n_walkers;
+    if (need2 > h->partials2_cap) {
+        MCD_CUDA(cudaFree(h->partials2));
+        h->partials2 = nullptr;
+        h->partials2_cap = 0;
+        MCD_CUDA(cudaMalloc(&h->partials2, sizeof(double) * need2));
+        h->partials2_cap = need2;
+    }
+    const int n_counters = p.n_groups * (p.n_super + 1);
+    if (n_counters > h->counters_cap) {
         MCD_CUDA(cudaFree(h->counters));
         h->counters = nullptr;
         h->counters_cap = 0;
-        const int cap = std::max(64, p.n_groups);
+        const int cap = std::max(256, n_counters);
         MCD_CUDA(cudaMalloc(&h->counters, sizeof(unsigned int) * cap));
         MCD_CUDA(cudaMemset(h->counters, 0, sizeof(unsigned int) * cap));
         h->counters_cap = cap;
@@ -310,6 +325,7 @@ static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double 
     choose_geometry(h, n_walkers, p);
     if (int rc = ensure_scratch(h, p)) return rc;
     p.partials = h->partials;
+    p.partials2 = h->partials2;
     p.counters = h->counters;
     MCD_CUDA(launch_lnlike(h->var, p, stream));
     h->info.last_grid_x = p.n_chunks;

@@ -12,6 +12,8 @@ constexpr int kBlock = 256;        // threads per CTA of the lnlike kernel
 constexpr int kMaxCols = 8;        // packed float64 columns per star
 constexpr int kMaxTile = 256;      // stars per shared-memory stage
 constexpr int kStages = 2;         // TMA bulk-copy stages in flight per CTA
+constexpr int kSuper = 32;         // chunks per super-chunk of the two-level cross-CTA reduction
+constexpr int kWaves = 8;          // CTA waves a large catalogue is cut into (tail balance)
 constexpr double kDeg2Rad = 0.017453292519943295769236907684886;
 constexpr double kR0Arcmin = 3437.7467707849392526078892888463;   // 10800/pi, calc_xy_offset.py:11
 
@@ -50,8 +52,11 @@ struct LaunchParams {
     int apply_prior;          // 1: lnprob (box prior fused), 0: lnlike
     int fixed_prior_ok;
     const double *theta;      // [n_walkers][n_theta]
+    int super;                // chunks per super-chunk (level 1 of the cross-CTA reduction)
+    int n_super;              // super-chunks per walker group
     double *partials;         // [n_chunks][n_walkers]
-    unsigned int *counters;   // [n_groups], zero between launches
+    double *partials2;        // [n_super][n_walkers]
+    unsigned int *counters;   // [n_groups][n_super + 1], zero between launches
     double *out;              // [n_walkers]
     int slot[MCD_NPARAM];
     double fixed_scaled[MCD_NPARAM];   // fixed value already multiplied by its unit scale

@@ -17,13 +17,24 @@
 //           reads the stars of its slice as shared-memory broadcasts.
 //   thread= one walker: its derived constants live in registers for the whole launch, its
 //           partial sums are register accumulators (no shuffles in the star loop).
-//   reduce= slices -> shared memory, chunks -> `partials` in global memory; the last CTA of a
-//           walker group to finish (atomic ticket) adds the chunk partials in chunk order, so the
-//           result does not depend on CTA scheduling.
+//   reduce= slices -> shared memory, chunks -> `partials` in global memory, then two ticketed
+//           levels (last CTA of a super-chunk, last super-chunk of a walker group) that add in
+//           index order, so the result does not depend on CTA scheduling.
 #include <math.h>
 
 #include "mcd_internal.h"
 #include "mcd_math.cuh"
+
+// tuning knobs (overridable at compile time for A/B runs: -DMCD_MIN_BLOCKS=.. -DMCD_PAIRS=..)
+// Measured on the headline workload (gpurun_out/ab*.log): 6.27e11 terms/s with
+// (1 pair, 4 CTA/SM), 6.44e11 with (2 pairs, 3 CTA/SM); more occupancy or ILP changes nothing
+// further -- the kernel sits on the FP64 pipe's operand-bandwidth limit.
+#ifndef MCD_MIN_BLOCKS
+#define MCD_MIN_BLOCKS 3      // __launch_bounds__ minimum resident CTAs per SM, no-background variants
+#endif
+#ifndef MCD_PAIRS
+#define MCD_PAIRS 2           // star pairs per inner-loop iteration (1 or 2), no-background variants
+#endif
 
 namespace mcd {
 
@@ -198,7 +209,9 @@ struct Accum<MCD_BG_NONE, MCD_MATH_FAST> {
     double chi;
     LogProduct norm;
     __device__ __forceinline__ void reset() { chi = 0.0; norm.reset(); }
-    __device__ __forceinline__ void end_tile() { norm.renormalise(); }
+    // called after every group of at most kGroup factors multiplied in with mul_raw()
+    __device__ __forceinline__ void end_group() { norm.renormalise_checked(); }
+    __device__ __forceinline__ void end_tile() {}
     __device__ __forceinline__ double value() { return -0.5 * (chi + norm.ln()); }
 };
 template <int BG>
@@ -206,7 +219,11 @@ struct Accum<BG, MCD_MATH_FAST> {
     LogProduct num, den;
     int invalid;
     __device__ __forceinline__ void reset() { num.reset(); den.reset(); invalid = 0; }
-    __device__ __forceinline__ void end_tile() { num.renormalise(); den.renormalise(); }
+    __device__ __forceinline__ void end_group() {
+        num.renormalise();
+        if (BG != MCD_BG_FIXED_PMEMBER) den.renormalise_checked();
+    }
+    __device__ __forceinline__ void end_tile() {}
     __device__ __forceinline__ double value() {
         num.bad |= invalid;
         const double n = num.ln();
@@ -217,24 +234,29 @@ template <int BG>
 struct Accum<BG, MCD_MATH_PLAIN> {
     double sum;
     __device__ __forceinline__ void reset() { sum = 0.0; }
+    __device__ __forceinline__ void end_group() {}
     __device__ __forceinline__ void end_tile() {}
     __device__ __forceinline__ double value() { return sum; }
+};
+
+// The packed values of one star, in registers.
+template <int NC>
+struct Star {
+    double c[NC];
+    int e;        // exponent column (FAST fixed-background variants)
 };
 
 // ------------------------------------------------------------------------------------------
 // one (walker, star) term
 // ------------------------------------------------------------------------------------------
-// `c` points at the packed columns of the current stage in shared memory (column stride = tile),
-// `i` is the star's index inside the tile.
 template <int ROT, int FREE, int BG, int MATH>
-__device__ __forceinline__ void term(const Walker &W, const double *__restrict__ c, const int32_t *__restrict__ ci,
-                                     int tile, int i, Accum<BG, MATH> &A) {
+__device__ __forceinline__ void term(const Walker &W, const Star<total_columns(ROT, FREE, BG)> &S, Accum<BG, MATH> &A) {
     constexpr int NB = base_columns(ROT, FREE);
     constexpr bool FAST = MATH == MCD_MATH_FAST;
-    // ---- geometry: numerator `num` and denominator `D1` of the rotation term, r^2 ------------
+    // ---- geometry: numerator `num` of the rotation term, r^2 ---------------------------------
     double num, r2 = 0.0;
     if constexpr (FREE) {
-        const double p1 = c[i], p2 = c[tile + i], sd = c[2 * tile + i];
+        const double p1 = S.c[0], p2 = S.c[1], sd = S.c[2];
         const double dx = fma(p2, W.sb, -p1 * W.cb);            // -cos(dec) sin(ra - ra_c)
         const double u = fma(p2, W.cb, p1 * W.sb);              //  cos(dec) cos(ra - ra_c)
         const double dy = fma(sd, W.cdc, -u * W.sdc);
@@ -247,12 +269,12 @@ __device__ __forceinline__ void term(const Walker &W, const double *__restrict__
             num = origin ? W.cx : num * rinv;
         }
     } else if constexpr (ROT == MCD_ROT_CONSTANT) {
-        num = fma(c[tile + i], W.cy, c[i] * W.cx);
+        num = fma(S.c[1], W.cy, S.c[0] * W.cx);
     } else {
-        num = fma(c[tile + i], W.cy, c[i] * W.cx);
-        r2 = c[2 * tile + i];
+        num = fma(S.c[1], W.cy, S.c[0] * W.cx);
+        r2 = S.c[2];
     }
-    const double v = c[(NB - 2) * tile + i], e2 = c[(NB - 1) * tile + i];
+    const double v = S.c[NB - 2], e2 = S.c[NB - 1];
     const double dv = v - W.vsys;
 
     if constexpr (FAST) {
@@ -267,40 +289,37 @@ __device__ __forceinline__ void term(const Walker &W, const double *__restrict__
         }
         // residual times D1: (v - v_sys) D1 - num  (= (v - v_los) D1)
         const double t = ROT == MCD_ROT_RADIAL ? fma(dv, D1, -num) : dv - num;
+        const double q = ROT == MCD_ROT_RADIAL ? (D1 * D1) * norm : norm;
         if constexpr (BG == MCD_BG_NONE) {
             // chi^2 = t^2 / (D1^2 norm): one reciprocal per term, no log (running product)
-            const double q = ROT == MCD_ROT_RADIAL ? (D1 * D1) * norm : norm;
             A.chi = fma(t * t, fast_rcp(q), A.chi);
-            A.norm.mul(norm);
+            A.norm.mul_raw(norm);
         } else {
             // member Gaussian without its 1/sqrt(2 pi): y exp(-z^2/2), y = norm^-1/2, z = t y / D1
-            const double q = ROT == MCD_ROT_RADIAL ? (D1 * D1) * norm : norm;
             const double yq = fast_rsqrt(q);
             const double z = t * yq;
             const double y = ROT == MCD_ROT_RADIAL ? yq * D1 : yq;
             double em;
             int ee;
             exp_split(-0.5 * (z * z), em, ee, A.invalid);
-            double wm, bm;
+            const double wm = S.c[NB];
+            double bm;
             int be;
             if constexpr (BG == MCD_BG_FIXED_PMEMBER) {
-                wm = c[NB * tile + i];
-                bm = c[(NB + 1) * tile + i];
-                be = ci[i];
+                bm = S.c[NB + 1];
+                be = S.e;
             } else if constexpr (BG == MCD_BG_FIXED_DENSITY) {
-                wm = c[NB * tile + i];
-                bm = W.fb * c[(NB + 1) * tile + i];
-                be = ci[i];
-                A.den.mul(wm + W.fb);
+                bm = W.fb * S.c[NB + 1];
+                be = S.e;
+                A.den.mul_raw(wm + W.fb);
             } else {
-                wm = c[NB * tile + i];
                 const double nb = e2 + W.sb2;
                 const double yb = fast_rsqrt(nb);
                 const double zb = (v - W.vb) * yb;
                 double ebm;
                 exp_split(-0.5 * (zb * zb), ebm, be, A.invalid);
                 bm = W.fb * yb * ebm;
-                A.den.mul(wm + W.fb);
+                A.den.mul_raw(wm + W.fb);
             }
             double m;
             int e;
@@ -325,14 +344,14 @@ __device__ __forceinline__ void term(const Walker &W, const double *__restrict__
         } else {
             double wm, lb;
             if constexpr (BG == MCD_BG_FIXED_PMEMBER) {
-                wm = c[NB * tile + i];
-                lb = c[(NB + 1) * tile + i];
+                wm = S.c[NB];
+                lb = S.c[NB + 1];
             } else if constexpr (BG == MCD_BG_FIXED_DENSITY) {
-                const double d = c[NB * tile + i];
+                const double d = S.c[NB];
                 wm = d / (d + W.fb);                                  // model.py:589
-                lb = c[(NB + 1) * tile + i];
+                lb = S.c[NB + 1];
             } else {
-                const double d = c[NB * tile + i];
+                const double d = S.c[NB];
                 wm = d / (d + W.fb);                                  // constant.py:339, model.py:427
                 const double nb = e2 + W.sb2;                         // constant.py:333-336
                 const double rb = v - W.vb;
@@ -343,6 +362,33 @@ __device__ __forceinline__ void term(const Walker &W, const double *__restrict__
             A.sum += mx + log(wm * exp(lm - mx) + (1.0 - wm) * exp(lb - mx));
         }
     }
+}
+
+// two adjacent stars of the current stage: one 16-byte shared-memory load per column
+template <int NC, bool ICOL>
+__device__ __forceinline__ void load_pair(const double *__restrict__ c, const int32_t *__restrict__ ci, int tile, int i,
+                                          Star<NC> &a, Star<NC> &b) {
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const double2 v = *reinterpret_cast<const double2 *>(c + k * tile + i);
+        a.c[k] = v.x;
+        b.c[k] = v.y;
+    }
+    if (ICOL) {
+        const int2 e = *reinterpret_cast<const int2 *>(ci + i);
+        a.e = e.x;
+        b.e = e.y;
+    } else {
+        a.e = b.e = 0;
+    }
+}
+
+template <int NC, bool ICOL>
+__device__ __forceinline__ void load_one(const double *__restrict__ c, const int32_t *__restrict__ ci, int tile, int i,
+                                         Star<NC> &a) {
+#pragma unroll
+    for (int k = 0; k < NC; ++k) a.c[k] = c[k * tile + i];
+    a.e = ICOL ? ci[i] : 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -380,7 +426,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // the lnlike / lnprob kernel
 // ------------------------------------------------------------------------------------------
 template <int ROT, int FREE, int BG, int MATH>
-__global__ void __launch_bounds__(kBlock) lnlike_kernel(const __grid_constant__ LaunchParams P) {
+__global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 2)) lnlike_kernel(const __grid_constant__ LaunchParams P) {
     constexpr int NC = total_columns(ROT, FREE, BG);
     constexpr bool ICOL = has_icol(BG, MATH);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -388,9 +434,11 @@ __global__ void __launch_bounds__(kBlock) lnlike_kernel(const __grid_constant__ 
     __shared__ double red[kBlock];
     __shared__ int s_last;
 
-    const int tile = P.tile;
-    double *sd = reinterpret_cast<double *>(smem_raw);                         // [kStages][NC][tile]
-    int32_t *si = reinterpret_cast<int32_t *>(sd + (size_t)kStages * NC * tile);   // [kStages][tile]
+    const int tile = P.tile;                     // stars per stage actually copied (<= kMaxTile)
+    constexpr int TS = kMaxTile;                 // column stride in shared memory: compile-time, so
+                                                 // that the LDS offsets of the star loop are immediates
+    double *sd = reinterpret_cast<double *>(smem_raw);                       // [kStages][NC][TS]
+    int32_t *si = reinterpret_cast<int32_t *>(sd + (size_t)kStages * NC * TS);   // [kStages][TS]
 
     const int tid = threadIdx.x;
     const int chunk = blockIdx.x, group = blockIdx.y;
@@ -417,8 +465,8 @@ __global__ void __launch_bounds__(kBlock) lnlike_kernel(const __grid_constant__ 
         mbar_expect_tx(&bars[stage], stage_bytes);
 #pragma unroll
         for (int c = 0; c < NC; ++c)
-            bulk_g2s(sd + ((size_t)stage * NC + c) * tile, P.cols[c] + off, (uint32_t)tile * 8u, &bars[stage]);
-        if (ICOL) bulk_g2s(si + (size_t)stage * tile, P.icol + off, (uint32_t)tile * 4u, &bars[stage]);
+            bulk_g2s(sd + ((size_t)stage * NC + c) * TS, P.cols[c] + off, (uint32_t)tile * 8u, &bars[stage]);
+        if (ICOL) bulk_g2s(si + (size_t)stage * TS, P.icol + off, (uint32_t)tile * 4u, &bars[stage]);
     };
 
     if (tid == 0 && n_my_tiles > 0) issue(0);
@@ -439,10 +487,38 @@ __global__ void __launch_bounds__(kBlock) lnlike_kernel(const __grid_constant__ 
         const long long first = (long long)(t_begin + k) * tile;
         const int n = (int)min((long long)tile, P.n_stars - first);
         if (active) {
-            const double *c = sd + (size_t)stage * NC * tile;
-            const int32_t *ci = si + (size_t)stage * tile;
-#pragma unroll 2
-            for (int i = slice; i < n; i += P.slices) term<ROT, FREE, BG, MATH>(W, c, ci, tile, i, A);
+            const double *c = sd + (size_t)stage * NC * TS;
+            const int32_t *ci = si + (size_t)stage * TS;
+            const int step = 2 * P.slices;
+            // pairs of adjacent stars: (2 slice, 2 slice + 1), then stride 2 slices
+            const int n2 = n & ~1;
+            int i = 2 * slice;
+            // two pairs per iteration (no-background variants only: the mixtures need the
+            // registers): four independent dependency chains per thread
+            if constexpr (MCD_PAIRS == 2 && BG == MCD_BG_NONE) for (; i + step < n2; i += 2 * step) {
+                Star<NC> s0, s1, s2, s3;
+                load_pair<NC, ICOL>(c, ci, TS, i, s0, s1);
+                load_pair<NC, ICOL>(c, ci, TS, i + step, s2, s3);
+                term<ROT, FREE, BG, MATH>(W, s0, A);
+                term<ROT, FREE, BG, MATH>(W, s1, A);
+                A.end_group();
+                term<ROT, FREE, BG, MATH>(W, s2, A);
+                term<ROT, FREE, BG, MATH>(W, s3, A);
+                A.end_group();
+            }
+            for (; i < n2; i += step) {
+                Star<NC> s0, s1;
+                load_pair<NC, ICOL>(c, ci, TS, i, s0, s1);
+                term<ROT, FREE, BG, MATH>(W, s0, A);
+                term<ROT, FREE, BG, MATH>(W, s1, A);
+                A.end_group();
+            }
+            if ((n & 1) && (n2 / 2) % P.slices == slice) {   // odd tail of the last tile
+                Star<NC> s0;
+                load_one<NC, ICOL>(c, ci, TS, n2, s0);
+                term<ROT, FREE, BG, MATH>(W, s0, A);
+                A.end_group();
+            }
             A.end_tile();
         }
         __syncthreads();   // everyone is done with `stage` before it is refilled
@@ -457,24 +533,47 @@ __global__ void __launch_bounds__(kBlock) lnlike_kernel(const __grid_constant__ 
         P.partials[(size_t)chunk * P.n_walkers + w] = s;
     }
 
-    // ---- chunks -> result: the last CTA of the walker group adds the partials in chunk order ----
+    // ---- chunks -> result, two levels, both in index order (independent of CTA scheduling) ------
+    // level 1: the last CTA of a super-chunk (P.super consecutive chunks) adds their partials;
+    // level 2: the last super-chunk to finish adds the super-chunk sums and writes the result.
+    unsigned int *cnt = P.counters + (size_t)group * (P.n_super + 1);
+    const int sup = chunk / P.super;
+    const int c_begin = sup * P.super;
+    const int c_end = min(P.n_chunks, c_begin + P.super);
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        const unsigned int ticket = atomicAdd(&P.counters[group], 1u);
-        s_last = (ticket == (unsigned int)P.n_chunks - 1u);
+        const unsigned int ticket = atomicAdd(&cnt[sup], 1u);
+        s_last = (ticket == (unsigned int)(c_end - c_begin) - 1u);
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
     if (valid && slice == 0) {
         double s = 0.0;
-        for (int cidx = 0; cidx < P.n_chunks; ++cidx) s += __ldcg(&P.partials[(size_t)cidx * P.n_walkers + w]);
+#pragma unroll 4
+        for (int cidx = c_begin; cidx < c_end; ++cidx) s += __ldcg(&P.partials[(size_t)cidx * P.n_walkers + w]);
+        P.partials2[(size_t)sup * P.n_walkers + w] = s;
+    }
+    if (tid == 0) cnt[sup] = 0u;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int ticket = atomicAdd(&cnt[P.n_super], 1u);
+        s_last = (ticket == (unsigned int)P.n_super - 1u);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (valid && slice == 0) {
+        double s = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < P.n_super; ++k) s += __ldcg(&P.partials2[(size_t)k * P.n_walkers + w]);
         if (MATH == MCD_MATH_FAST) s = fma((double)P.n_stars, -0.5 * kLn2Pi, s);
         const bool rejected = P.apply_prior && !W.prior_ok;
         P.out[w] = rejected ? __longlong_as_double(0xfff0000000000000LL) : s;
     }
-    if (tid == 0) P.counters[group] = 0u;
+    if (tid == 0) cnt[P.n_super] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -488,14 +587,14 @@ __global__ void per_star_kernel(const __grid_constant__ LaunchParams P, double *
     __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_stars) return;
-    // stage the star's packed values as a one-star "tile" in registers
-    double c[NC];
+    Star<NC> S;
 #pragma unroll
-    for (int k = 0; k < NC; ++k) c[k] = P.cols[k][i];
+    for (int k = 0; k < NC; ++k) S.c[k] = P.cols[k][i];
+    S.e = 0;
     Accum<BG, MCD_MATH_PLAIN> A;
     A.reset();
     const Walker W = Ws;
-    term<ROT, FREE, BG, MCD_MATH_PLAIN>(W, c, nullptr, 1, 0, A);
+    term<ROT, FREE, BG, MCD_MATH_PLAIN>(W, S, A);
     out[i] = A.value();
 }
 
@@ -505,7 +604,7 @@ __global__ void per_star_kernel(const __grid_constant__ LaunchParams P, double *
 template <int ROT, int FREE, int BG, int MATH>
 static cudaError_t launch_one(const LaunchParams &p, cudaStream_t stream) {
     constexpr int NC = total_columns(ROT, FREE, BG);
-    const size_t smem = (size_t)kStages * p.tile * (NC * 8 + (has_icol(BG, MATH) ? 4 : 0));
+    const size_t smem = (size_t)kStages * kMaxTile * (NC * 8 + (has_icol(BG, MATH) ? 4 : 0));
     dim3 grid((unsigned)p.n_chunks, (unsigned)p.n_groups);
     lnlike_kernel<ROT, FREE, BG, MATH><<<grid, kBlock, smem, stream>>>(p);
     return cudaGetLastError();

@@ -37,23 +37,43 @@ __device__ __forceinline__ double rsqrt_seed(double x) {
     return y;
 }
 
-// 1/x for normal positive x: seed + cubic step, 3 DFMA.  e = 1 - x*y0, 1/x = y0 (1 + e + e^2 + O(e^3)).
+// Newton order of the reciprocal / reciprocal square root refinements:
+//   3 (cubic step, default): rel. error ~ d^3 with d = seed error (measured 2^-20 for both MUFU
+//                            seeds on B200) -> 2.2e-16 / 2.7e-16 measured; 3 / 5 DFMA
+//   2 (quadratic step)     : measured 9.8e-13 / 1.3e-12; 2 / 3 DFMA (+1 integer op); only 2.5 %
+//                            faster on the headline workload, so not the default
+// Measurements: tools/microbench/seeds.cu, DESIGN.md ("arithmetic").
+#ifndef MCD_NEWTON
+#define MCD_NEWTON 3
+#endif
+
+// 1/x for normal positive x.  e = 1 - x*y0, 1/x = y0 (1 + e + e^2 + O(e^3)).
 __device__ __forceinline__ double fast_rcp(double x) {
     const double y0 = rcp_seed(x);
     const double e = fma(-x, y0, 1.0);
+#if MCD_NEWTON == 3
     const double p = fma(e, e, e);
     return fma(y0, p, y0);
+#else
+    return fma(y0, e, y0);
+#endif
 }
 
-// x^(-1/2) for normal positive x: seed + cubic step, 5 DFMA.
-// e = 1 - x*y0^2, x^(-1/2) = y0 (1 + e/2 + 3 e^2/8 + O(e^3)).
+// x^(-1/2) for normal positive x.  e = 1 - x*y0^2, x^(-1/2) = y0 (1 + e/2 + 3 e^2/8 + O(e^3)).
 __device__ __forceinline__ double fast_rsqrt(double x) {
     const double y0 = rsqrt_seed(x);
     const double t = x * y0;
     const double e = fma(-t, y0, 1.0);
+#if MCD_NEWTON == 3
     const double p = fma(0.375, e, 0.5);
     const double ye = y0 * e;
     return fma(ye, p, y0);
+#else
+    // y0/2 by an exponent decrement on the integer pipe (y0 is a normal number far from the
+    // denormal range: it is the rsqrt of a normal double)
+    const double h = __hiloint2double(__double2hiint(y0) - 0x00100000, __double2loint(y0));
+    return fma(h, e, y0);
+#endif
 }
 
 // 2^d for integer d <= 0; exact, flushed to zero below the normal range.
@@ -90,9 +110,23 @@ struct LogProduct {
         mant *= is_zero ? 1.0 : __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(m));
     }
 
-    // fold the mantissa's own exponent into `expo`; call at least every 1000 factors
+    // multiply by x without touching the exponent: the caller renormalises after a small group of
+    // factors (each within 2^+-500 for a group of two), which moves the exponent bookkeeping from
+    // once per factor to once per group
+    __device__ __forceinline__ void mul_raw(double x) { mant *= x; }
+
+    // fold the mantissa's own exponent into `expo`; call at least every 1000 mul()/mul_ext() factors
     __device__ __forceinline__ void renormalise() {
         const int hi = __double2hiint(mant);
+        expo += (hi >> 20) - 1023;
+        mant = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(mant));
+    }
+
+    // the same after mul_raw(): additionally flags a product that left the normal positive range
+    // (zero, denormal, negative, inf, NaN factor)
+    __device__ __forceinline__ void renormalise_checked() {
+        const int hi = __double2hiint(mant);
+        bad |= ((unsigned)(hi - 0x00100000) >= 0x7fe00000u);
         expo += (hi >> 20) - 1023;
         mant = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(mant));
     }
