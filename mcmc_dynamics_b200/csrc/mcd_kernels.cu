@@ -101,9 +101,10 @@ __global__ void pack_kernel(const PackParams P) {
         const double dx = -kR0Arcmin * cd * sda;
         const double dy = kR0Arcmin * (sd * cdc - cd * sdc * cda);
         if (P.rotation == MCD_ROT_CONSTANT) {
-            // theta_i = atan2(dy, dx) (constant.py:107); atan2(0, 0) = 0
+            // theta_i = atan2(dy, dx) (constant.py:107).  A star exactly at the centre has
+            // dx = -r0 cos(dec) sin(+0) = -0.0 and dy = +0.0, i.e. theta_i = atan2(+0, -0) = pi.
             const double r = sqrt(dx * dx + dy * dy);
-            P.cols[c++][i] = r > 0.0 ? dx / r : 1.0;
+            P.cols[c++][i] = r > 0.0 ? dx / r : -1.0;
             P.cols[c++][i] = r > 0.0 ? dy / r : 0.0;
         } else {
             P.cols[c++][i] = dx;
@@ -263,10 +264,11 @@ __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(R
         r2 = fma(dx, dx, dy * dy);
         num = fma(dy, W.cy, dx * W.cx);
         if constexpr (ROT == MCD_ROT_CONSTANT) {
-            // sin(theta_i - theta_0) needs the unit vector: divide by r; atan2(0,0) = 0 => (1, 0)
+            // sin(theta_i - theta_0) needs the unit vector: divide by r; at r = 0 the reference has
+            // theta_i = atan2(+0, -0) = pi, i.e. the unit vector (-1, 0)
             const bool origin = (__double2hiint(r2) | __double2loint(r2)) == 0;
             const double rinv = FAST ? fast_rsqrt(origin ? 1.0 : r2) : 1.0 / sqrt(origin ? 1.0 : r2);
-            num = origin ? W.cx : num * rinv;
+            num = origin ? -W.cx : num * rinv;
         }
     } else if constexpr (ROT == MCD_ROT_CONSTANT) {
         num = fma(S.c[1], W.cy, S.c[0] * W.cx);

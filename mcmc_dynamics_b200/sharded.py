@@ -36,7 +36,7 @@ class ShardedLikelihood(object):
         collective is issued.
     """
 
-    def __init__(self, model, group=None):
+    def __init__(self, model, group=None, device=None):
         import torch
         import torch.distributed as dist
         self._torch = torch
@@ -44,7 +44,8 @@ class ShardedLikelihood(object):
         self.model = model
         self.group = group
         self.world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-        self.device = torch.device('cuda', model.device)
+        # `device` is overridden only by the CPU (gloo) tests of the reduction logic
+        self.device = torch.device('cuda', model.device) if device is None else torch.device(device)
         self._pinned_in = None
         self._pinned_out = None
 
@@ -62,12 +63,17 @@ class ShardedLikelihood(object):
         torch = self._torch
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         n, p = theta.shape
+        on_gpu = self.device.type == 'cuda'
         if self._pinned_in is None or self._pinned_in.shape[0] < n or self._pinned_in.shape[1] != p:
-            self._pinned_in = torch.empty((max(n, 64), p), dtype=torch.float64).pin_memory()
-            self._pinned_out = torch.empty((max(n, 64),), dtype=torch.float64).pin_memory()
+            self._pinned_in = torch.empty((max(n, 64), p), dtype=torch.float64)
+            self._pinned_out = torch.empty((max(n, 64),), dtype=torch.float64)
+            if on_gpu:
+                self._pinned_in = self._pinned_in.pin_memory()
+                self._pinned_out = self._pinned_out.pin_memory()
         self._pinned_in[:n].copy_(torch.from_numpy(theta))
         dev = self._pinned_in[:n].to(self.device, non_blocking=True)
         out = self.lnprob_tensor(dev)
         self._pinned_out[:n].copy_(out, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        if on_gpu:
+            torch.cuda.current_stream(self.device).synchronize()
         return self._pinned_out[:n].numpy().copy()

@@ -1,0 +1,216 @@
+"""Host-side boundary, no GPU: parameter/config compatibility, model-class protocol and error
+behaviour, the host ensemble sampler, and that the C-ABI library loads and exports every symbol
+``include/mcd_b200.h`` declares (no compute calls)."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from mcmc_dynamics_b200 import DataReader, Parameters, _native, pack, sampler, synthetic
+from mcmc_dynamics_b200 import units as u
+from mcmc_dynamics_b200.analysis import (ConstantFit, ConstantFitGB, ModelFit, ModelFitGB,
+                                         ModelFitConstantBackground)
+from oracle import reference_np as ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------------------------------------
+# C ABI
+# ---------------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol(native_lib):
+    header = open(os.path.join(ROOT, 'include', 'mcd_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(mcd_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 20
+    for name in sorted(declared):
+        assert hasattr(native_lib, name), 'libmcd_b200.so does not export ' + name
+    assert declared == set(_native.SYMBOLS), declared.symmetric_difference(_native.SYMBOLS)
+    assert native_lib.mcd_abi_version() == _native.ABI_VERSION
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirrors of mcd_pack_desc / mcd_info: field order and sizes follow the header."""
+    header = open(os.path.join(ROOT, 'include', 'mcd_b200.h')).read()
+    body = header[header.index('typedef struct mcd_pack_desc {'):header.index('} mcd_pack_desc;')]
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    fields = re.findall(r'\b(?:int32_t|int64_t|double|const double \*)\s*\*?(\w+)(?:\[\w+\])?;', body)
+    assert fields == [name for name, _ in _native.PackDesc._fields_]
+    import ctypes
+    assert ctypes.sizeof(_native.PackDesc) == 16 + 8 + 7 * 8 + 11 * 4 + 4 + 2 * 11 * 8 + 2 * 16 * 8 + 8 + 8
+
+
+@pytest.mark.skipif(__import__('torch').cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_no_gpu_fails_loudly():
+    data, truth = synthetic.mock_cluster(50, seed=1)
+    model = ModelFit(data)
+    with pytest.raises(_native.NativeError, match='no CUDA device|CPU fallback'):
+        model.lnprob(model.get_initials(4))
+
+
+# ---------------------------------------------------------------------------------------------
+# parameters / config
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('cls,table', [(ConstantFit, 'constant'), (ConstantFitGB, 'constant_with_background'),
+                                       (ModelFit, 'model'), (ModelFitGB, 'model_with_background'),
+                                       (ModelFitConstantBackground, 'model_with_background')])
+def test_default_parameter_files_match_reference_tables(cls, table):
+    pars = cls.default_parameters()
+    want = ref.DEFAULT_TABLES[table]
+    assert list(pars.keys()) == [row[0] for row in want]
+    for name, unit, lo, hi in want:
+        par = pars[name]
+        assert par.min == lo and par.max == hi and not par.fixed
+        assert (par.unit is None and unit is None) or str(par.unit).replace(' ', '') == unit
+    # value = (min + max) / 2 if both bounds finite else 0 (parameter.py:794-798)
+    assert pars['ra_center'].value == 180.0 and pars['dec_center'].value == 0.0
+
+
+def test_parameters_json_round_trip(tmp_path):
+    pars = ModelFit.default_parameters()
+    pars['ra_center'].set(value=201.697, fixed=True)
+    pars['a'].set(value=u.Quantity(0.5, u.arcmin))          # converted to the parameter's unit
+    assert pars['a'].value == pytest.approx(30.0)
+    text = pars.dumps()
+    doc = json.loads(text.replace('Infinity', '1e999'))
+    assert [row[0] for row in doc['params']] == list(pars.keys())
+    again = Parameters().loads(text)
+    for name in pars:
+        assert again[name].value == pars[name].value and again[name].fixed == pars[name].fixed
+        assert again[name].min == pars[name].min and again[name].max == pars[name].max
+    path = tmp_path / 'p.json'
+    with open(path, 'w') as f:
+        pars.dump(f)
+    assert Parameters().load(str(path))['ra_center'].fixed
+
+
+def test_initials_and_lnprior_expressions():
+    pars = Parameters(rng_seed=7)
+    pars.add('sigma_max', unit='km/s', min=0, initials='rng.lognormal(mean=2.3, sigma=0.5, size=n)')
+    pars.add('v_sys', unit='km/s', value=3.0, min=-10, max=10, lnprior='norm.logpdf(val, loc=0, scale=2)')
+    start = pars['sigma_max'].evaluate_initials(100)
+    assert start.shape == (100,) and np.all(start > 0)
+    assert pars['v_sys'].evaluate_lnprior(11.0) == -np.inf
+    from scipy import stats
+    assert pars['v_sys'].evaluate_lnprior(1.0) == pytest.approx(stats.norm.logpdf(1.0, 0, 2))
+    draws = pars['v_sys'].evaluate_initials(2000)             # truncnorm(loc=value, scale=1) in [-10, 10]
+    assert abs(draws.mean() - 3.0) < 0.1 and draws.min() >= -10 and draws.max() <= 10
+
+
+# ---------------------------------------------------------------------------------------------
+# model-class protocol (no GPU work)
+# ---------------------------------------------------------------------------------------------
+def test_constructor_errors_follow_the_reference():
+    data, _ = synthetic.mock_cluster(20, seed=1)
+    with pytest.raises(AssertionError):
+        ModelFit({'v': [1.0]})                                 # not a DataReader (runner.py:66)
+    with pytest.raises(AssertionError):
+        ModelFit(data, bogus=1)                                # unknown kwargs (runner.py:56)
+    with pytest.raises(IOError):
+        ModelFit(DataReader({'v': [1.0], 'verr': [1.0]}))      # no coordinates (runner.py:72)
+    pars = ConstantFit.default_parameters()
+    with pytest.raises(IOError):
+        ModelFit(data, parameters=pars)                        # missing a, r_peak (runner.py:89)
+    with pytest.raises(AssertionError):
+        ModelFitGB(data)                                       # density column missing (runner.py:76)
+
+
+def test_fitted_parameters_and_batched_prior():
+    data, truth = synthetic.mock_cluster(20, seed=1)
+    model = ModelFit(data)
+    assert model.fitted_parameters == ['v_sys', 'sigma_max', 'a', 'v_maxx', 'ra_center', 'dec_center', 'v_maxy',
+                                       'r_peak']
+    model.parameters['ra_center'].set(value=truth['ra_center'], fixed=True)
+    model.parameters['dec_center'].set(value=truth['dec_center'], fixed=True)
+    assert model.n_fitted_parameters == 6 and model.n_data == 20
+    theta = synthetic.initial_ball(truth, model.fitted_parameters, 5)
+    theta[1, 1] = -1.0
+    lp = model.lnprior(theta)
+    assert lp.shape == (5,) and lp[1] == -np.inf and np.all(lp[[0, 2, 3, 4]] == 0)
+    assert model.lnprior(theta[0]) == 0 and model.lnprior(theta[1]) == -np.inf
+    values = model.fetch_parameter_values(theta[0])
+    assert list(values) == list(model.parameters) and values['ra_center'].value == truth['ra_center']
+    with pytest.raises(AssertionError):
+        model.fetch_parameter_values(np.append(theta[0], 1.0))     # runner.py:178
+    # oracle prior agrees row by row
+    from oracle import harness
+    assert np.array_equal(harness.oracle_for(model).lnprior_many(theta), lp)
+
+
+def test_descriptor_routing_and_units():
+    data, truth = synthetic.mock_cluster(20, seed=1)
+    model = ModelFitGB(synthetic.reader_from_columns(dict(
+        synthetic.mock_cluster(20, seed=1, as_reader=False)[0], density=np.ones(20))))
+    model.parameters['ra_center'].set(value=truth['ra_center'], fixed=True)
+    model.parameters['dec_center'].set(value=truth['dec_center'], fixed=True)
+    model.parameters['v_sys'].set(value=1.0, fixed=True)
+    desc, keep = model._descriptor()
+    free = model.fitted_parameters
+    assert desc.n_theta == len(free) == 8 and desc.n_stars == 20
+    slots = dict(zip(_native.PARAM_SLOTS, list(desc.slot)))
+    assert slots['v_sys'] == -1 and slots['ra_center'] == -1
+    assert slots['sigma_max'] == free.index('sigma_max') and slots['f_back'] == free.index('f_back')
+    scale = dict(zip(_native.PARAM_SLOTS, list(desc.unit_scale)))
+    assert scale['a'] == pytest.approx(1 / 60.0) and scale['r_peak'] == pytest.approx(1 / 60.0) and scale['v_sys'] == 1.0
+    assert desc.lower[free.index('sigma_max')] == 0.0 and desc.upper[free.index('f_back')] == 1.0
+    assert desc.fixed_prior_ok == 1
+    model.parameters['v_sys'].min = 2.0                       # fixed value 1.0 now violates its bounds
+    assert model._descriptor()[0].fixed_prior_ok == 0
+    model.parameters['v_sys'].min = -np.inf
+    model.parameters['a'].set(expr='2 * r_peak')              # per-walker constraint: rejected at pack time
+    with pytest.raises(pack.PackError):
+        model._descriptor()
+
+
+def test_superfluous_free_parameters_are_prior_checked_only():
+    """ModelFitConstantBackground loads model_with_background.json whose v_back, sigma_back are not
+    model parameters (model.py:526,529): they stay free dimensions of theta."""
+    cols = dict(synthetic.mock_cluster(20, seed=1, as_reader=False)[0], density=np.ones(20))
+
+    class Flat(object):                                       # background callable evaluated on the host
+        def __call__(self, v, verr):
+            return np.full(len(np.asarray(getattr(v, 'value', v))), -5.0)
+    model = ModelFitConstantBackground(synthetic.reader_from_columns(cols), background=Flat())
+    assert 'v_back' in model.fitted_parameters and 'v_back' not in model.MODEL_PARAMETERS
+    desc, _ = model._descriptor()
+    assert desc.n_theta == 11 and dict(zip(_native.PARAM_SLOTS, list(desc.slot)))['v_back'] == -1
+    assert desc.lower[model.fitted_parameters.index('sigma_back')] == 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# host ensemble sampler (emcee stand-in), vectorised calls
+# ---------------------------------------------------------------------------------------------
+def test_host_sampler_recovers_a_gaussian():
+    mean = np.array([1.0, -2.0, 0.5])
+    sigma = np.array([0.5, 2.0, 1.0])
+    calls = []
+
+    def lnprob(theta):
+        calls.append(theta.shape)
+        return -0.5 * np.sum(((theta - mean) / sigma) ** 2, axis=1)
+    s = sampler.HostEnsembleSampler(32, 3, lnprob, seed=3)
+    rng = np.random.default_rng(0)
+    pos, lnp, state = s.run_mcmc(mean + 0.1 * rng.standard_normal((32, 3)), 1500)
+    assert s.chain.shape == (32, 1500, 3) and s.lnprobability.shape == (32, 1500) and s.iteration == 1500
+    assert calls[0] == (32, 3) and set(calls[1:]) == {(16, 3)}      # W once, then half-ensembles
+    flat = s.chain[:, 500:, :].reshape(-1, 3)
+    assert np.allclose(flat.mean(axis=0), mean, atol=0.15)
+    assert np.allclose(flat.std(axis=0), sigma, rtol=0.15)
+    assert 0.2 < s.acceptance_fraction.mean() < 0.9
+    with pytest.raises(RuntimeError):
+        sampler.HostEnsembleSampler(4, 3, lnprob)                    # nwalkers < 2 ndim
+    with pytest.raises(ValueError):
+        s.compute_log_prob(np.full((2, 3), np.nan))
+
+
+def test_radial_bins_partition():
+    data, truth = synthetic.mock_cluster(600, seed=2)
+    data.make_radial_bins(truth['ra_center'], truth['dec_center'], nstars=50, dlogr=0.1)
+    bins = np.asarray(data.data['bin'].value if hasattr(data.data['bin'], 'value') else data.data['bin'])
+    assert bins.min() == 0 and len(bins) == 600
+    sizes = np.bincount(bins.astype(int))
+    assert np.all(sizes >= 25) and sizes.sum() == 600
+    sub = data.fetch_radial_bin(1)
+    assert sub.sample_size == sizes[1]

@@ -1,0 +1,106 @@
+"""Device-resident ensemble sampler (csrc/mcd_sampler.cu) and the end-to-end sampling call."""
+import numpy as np
+import pytest
+
+from common import build
+from mcmc_dynamics_b200 import sampler as samplers
+from mcmc_dynamics_b200 import synthetic
+from mcmc_dynamics_b200.analysis import ConstantFit, ModelFit
+
+pytestmark = pytest.mark.gpu
+
+
+def _mock_model(n_stars=1500, seed=21, cls=ModelFit):
+    data, truth = synthetic.mock_cluster(n_stars, seed=seed)
+    model = cls(data)
+    model.parameters['ra_center'].set(value=truth['ra_center'], fixed=True)
+    model.parameters['dec_center'].set(value=truth['dec_center'], fixed=True)
+    return model, truth
+
+
+def test_device_chain_is_self_consistent_and_reproducible():
+    model, truth = _mock_model()
+    pos = synthetic.initial_ball(truth, model.fitted_parameters, 32, seed=3)
+    runs = []
+    for _ in range(2):
+        s = samplers.DeviceEnsembleSampler(32, model.n_fitted_parameters, model.pack(), seed=1234)
+        s.run_mcmc(pos, 40)
+        runs.append((s.chain.copy(), s.lnprobability.copy(), s.naccepted.copy()))
+    chain, lnp, nacc = runs[0]
+    assert chain.shape == (32, 40, 6) and lnp.shape == (32, 40)
+    assert np.array_equal(chain, runs[1][0]) and np.array_equal(lnp, runs[1][1])     # same seed, same chain
+    # the stored log-probabilities belong to the stored positions
+    for step in (0, 17, 39):
+        again = model.lnprob(np.ascontiguousarray(chain[:, step, :]))
+        assert np.allclose(again, lnp[:, step], rtol=1e-12, atol=0)
+    assert np.all(np.isfinite(lnp))
+    frac = nacc / 40.0
+    assert 0.1 < frac.mean() < 0.95
+    # walkers only ever move to accepted proposals: consecutive equal positions <=> equal lnprob
+    moved = np.any(chain[:, 1:, :] != chain[:, :-1, :], axis=2)
+    assert np.array_equal(moved, lnp[:, 1:] != lnp[:, :-1])
+    assert moved.sum() == nacc.sum() - np.any(chain[:, 0, :] != pos, axis=1).sum()
+
+
+def test_device_and_host_samplers_agree_and_recover_the_truth():
+    """Mock recovery (bin/run_tests.py:36-41 scenario): posterior percentiles (runner.py:566-613) of
+    the device sampler and of the host stretch move driving the same GPU lnprob agree within
+    Monte-Carlo error, and bracket the truth."""
+    model, truth = _mock_model(n_stars=4000, seed=8)
+    n_walkers, n_steps, n_burn = 64, 700, 250
+    pos = synthetic.initial_ball(truth, model.fitted_parameters, n_walkers, seed=4, scale=0.1)
+    dev = model(n_walkers=n_walkers, n_steps=n_steps, pos=pos, sampler='device', seed=11, prefix=None)
+    host = model(n_walkers=n_walkers, n_steps=n_steps, pos=pos, sampler='host', seed=12, prefix=None)
+    assert dev.chain.shape == host.chain.shape == (n_walkers, n_steps, 6)
+    pd = model.compute_percentiles(dev.chain, n_burn)
+    ph = model.compute_percentiles(host.chain, n_burn)
+    for name in model.fitted_parameters:
+        lo_d, med_d, hi_d = pd[name]
+        lo_h, med_h, hi_h = ph[name]
+        width = 0.5 * ((hi_d - lo_d) + (hi_h - lo_h)) / 2.0
+        assert abs(med_d - med_h) < 0.35 * 2 * width, (name, pd[name], ph[name])
+        assert 0.6 < (hi_d - lo_d) / (hi_h - lo_h) < 1.6, (name, pd[name], ph[name])
+        # truth within ~3.5 sigma of the posterior
+        assert abs(med_d - truth[name]) < 3.5 * width + 1e-9, (name, pd[name], truth[name])
+
+
+def test_runner_call_signature_and_checkpoint(tmp_path):
+    model, truth = _mock_model(n_stars=300, cls=ConstantFit)
+    model.parameters['sigma_max'].set(initials='rng.lognormal(mean=2.3, sigma=0.3, size=n)')
+    prefix = str(tmp_path / 'run')
+    s = model(n_walkers=16, n_steps=30, n_out=10, prefix=prefix)
+    assert s.iteration == 30 and s.chain.shape == (16, 30, 4)
+    chain = model.read_chain(prefix + '_chain.pkl')
+    assert chain.shape == (16, 30, 4)
+    last = model.read_final_chain(prefix + '_chain.pkl')
+    assert np.array_equal(last, s.chain[:, -1, :])
+    # resume from the stored positions (run.py:419-422,450)
+    s2 = model(n_walkers=16, n_steps=5, pos=last, prefix=None)
+    assert s2.chain.shape == (16, 5, 4)
+    bad = last.copy()
+    bad[3, model.fitted_parameters.index('sigma_max')] = -1.0
+    with pytest.raises(ValueError, match='Invalid initial guesses'):
+        model(n_walkers=16, n_steps=5, pos=bad, prefix=None)
+
+
+def test_emulated_star_shards_add_up():
+    """Two shard handles on one GPU: partial sums add up to the whole-catalogue lnprob (the
+    multi-GPU data path minus the collective)."""
+    import torch
+    columns, truth = synthetic.mock_cluster(5001, seed=5, as_reader=False)
+    from mcmc_dynamics_b200 import sharded
+
+    def make(cols):
+        m = ModelFit(synthetic.reader_from_columns(cols))
+        m.parameters['ra_center'].set(value=truth['ra_center'])
+        m.parameters['dec_center'].set(value=truth['dec_center'])
+        return m
+    whole = make(columns)
+    theta = synthetic.initial_ball(truth, whole.fitted_parameters, 40, seed=6)
+    theta[7, whole.fitted_parameters.index('a')] = -1.0
+    th = torch.as_tensor(theta, device='cuda:0')
+    total = whole.lnprob_tensor(th)
+    parts = sum(make(sharded.shard_columns(columns, r, 3)).pack().lnprob_partial_tensor(th) for r in range(3))
+    assert parts[7] == -np.inf and total[7] == -np.inf
+    keep = np.arange(40) != 7
+    assert np.allclose(parts.cpu().numpy()[keep], total.cpu().numpy()[keep], rtol=1e-12, atol=0)
