@@ -37,7 +37,7 @@ SEED = 4
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=40)
+    ap.add_argument('--steps', type=int, default=60)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--stars', type=int, default=10_000_000)
@@ -137,31 +137,48 @@ class ClockSampler(object):
         self.rows = []
         self._stop = threading.Event()
         self._thread = None
-
-    def _loop(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
-                if out.returncode == 0 and out.stdout.strip():
-                    self.rows.append([c.strip() for c in out.stdout.strip().splitlines()[0].split(',')])
-            except Exception:
-                pass
-            self._stop.wait(0.15)
+        self._proc = None
 
     def __enter__(self):
-        self._thread = threading.Thread(target=self._loop, daemon=True)
+        # one long-lived nvidia-smi in loop mode (a fresh process per sample takes ~1 s on these boxes)
+        try:
+            self._proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self._proc = None
+            return self
+        self._thread = threading.Thread(target=self._read, daemon=True)
         self._thread.start()
         return self
 
+    def _read(self):
+        for line in self._proc.stdout:
+            if self._stop.is_set():
+                break
+            cells = [c.strip() for c in line.strip().split(',')]
+            if len(cells) >= 7:
+                self.rows.append((time.perf_counter(), cells))
+
     def __exit__(self, *exc):
         self._stop.set()
-        self._thread.join(timeout=10)
+        if self._proc is not None:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=5)
+            except Exception:
+                self._proc.kill()
+            self._thread.join(timeout=5)
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
+        """Median SM clock and the throttle reasons seen between perf_counter times t0 and t1 (the
+        timed region); falls back to every sample taken under load if the window caught none."""
         sm, smax, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for row in self.rows:
+        rows = [cells for (t, cells) in self.rows if t0 is None or (t0 <= t <= t1)]
+        if not rows:
+            rows = [cells for (_, cells) in self.rows]
+        for row in rows:
             try:
                 sm.append(float(row[0]))
                 smax.append(float(row[1]))
@@ -238,15 +255,14 @@ def gpu_run(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    for _ in range(max(args.warmup, 3)):
-        one_step()
-    sync_all()
-
     lib = _native.load_library()
-    launches_before = packed.info()['launches']
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     with ClockSampler(local_rank) as clocks:
+        for _ in range(max(args.warmup, 3)):
+            one_step()
+        sync_all()
+        launches_before = packed.info()['launches']
         sync_all()
         wall0 = time.perf_counter()
         for k in range(args.steps):
@@ -256,7 +272,11 @@ def gpu_run(args):
             result = one_step()
             stops[k].record()
         sync_all()
-        wall = time.perf_counter() - wall0
+        wall1 = time.perf_counter()
+        wall = wall1 - wall0
+        if wall < 0.5:
+            time.sleep(0.3)       # let the sampler deliver what it measured during a short region
+    clock_summary = clocks.summary(wall0, wall1)
     launches = packed.info()['launches'] - launches_before
     device_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
     t = torch.tensor([device_ms], dtype=torch.float64, device=device)
@@ -345,7 +365,7 @@ def gpu_run(args):
                 'api': 'ModelFit.lnprob(theta ndarray) -> C ABI mcd_lnprob (host buffers)' if world == 1 else
                        'ShardedLikelihood.lnprob(theta ndarray): pinned H2D, shard kernel, NCCL all_reduce, D2H'},
         'gpu_launches': int(launches),
-        'clocks': clocks.summary(),
+        'clocks': clock_summary,
         'roofline': {
             'bound': 'fp64', 'achieved': achieved_tflops, 'peak': fp64_peak, 'unit': 'TFLOP/s',
             'frac': (achieved_tflops / fp64_peak) if fp64_peak else None, 'traffic': None,
