@@ -5,11 +5,19 @@ Nothing under ``oracle/`` may be imported by the product package
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` use it, and only as
 the checker / the timed CPU baseline.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for
-this path, and it cannot be imported in this image (astropy, emcee, asteval,
-lmfit are absent and there is no network).  The oracle is therefore pinned only
-by (i) op-for-op restatement of the cited reference lines, (ii) hand-derived
-known-answer tests in ``tests/test_oracle_kat.py`` and (iii) the reference's own
-source files executed against minimal stand-ins for the missing third-party
-modules (``tests/golden/make_golden.py``).
+How the oracle is pinned.  The reference ships no tests, golden vectors or
+fixtures for this path, and it cannot be imported in this image (astropy, emcee,
+asteval, lmfit, pathos, corner, matplotlib are absent; no network).  Parity is
+therefore anchored on outputs of the reference's OWN source files:
+``tests/golden/make_golden.py`` loads ``parameter.py``, ``analysis/runner.py``,
+``constant.py``, ``model.py``, ``background/*.py``, ``calc_xy_offset.py`` and
+``data_reader.py`` unmodified from ``/root/reference`` against minimal stand-ins
+for the missing third-party modules (``tests/golden/ref_shims``) and records
+``lnprior / lnlike / lnprob`` for all five model classes (fixed and free centre,
+every background mode, prior rejections, ``no_sum``).  ``tests/test_golden_cpu.py``
+checks this restatement against those vectors to 1e-12 relative.  Caveat, stated
+here and in DESIGN.md: the stand-in for ``astropy.units`` restates astropy's
+conversion rules; real astropy was never run, so the
+unit handling is pinned only as far as that restatement is right.  Independent
+hand-derived known answers: ``tests/test_oracle_kat.py``.
 """

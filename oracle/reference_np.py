@@ -1,6 +1,7 @@
 """Literal NumPy float64 restatement of the reference hot path.  TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED (see ``oracle/__init__.py``): no golden vectors exist upstream.
+Pinned against outputs of the reference's own source files (``tests/golden``, see
+``oracle/__init__.py`` for how and for the one caveat about astropy's unit rules).
 
 Every function follows the cited reference lines op for op, in the same order,
 including the work the reference repeats (``calc_xy_offset`` is evaluated once
