@@ -1,0 +1,174 @@
+#!/usr/bin/env python
+"""All five BASELINE.json configurations on one B200: parity against the NumPy oracle, terms/s of the
+lnprob call (device-resident theta and through the host-buffer C ABI), emcee steps/s with the host
+stretch-move loop and with the device-resident sampler, and the CPU oracle beside them.
+
+    python tools/config_sweep.py [--out profiles/rNN_configs.md] [--quick]
+
+This is a reporting tool (bench.py is the contract benchmark); it prints a Markdown table.
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from mcmc_dynamics_b200 import sampler as samplers  # noqa: E402
+from mcmc_dynamics_b200 import synthetic  # noqa: E402
+from mcmc_dynamics_b200.analysis import ConstantFit, ModelFit, ModelFitGB  # noqa: E402
+from mcmc_dynamics_b200.background import SingleStars  # noqa: E402
+from oracle import harness  # noqa: E402
+
+
+def fix_centre(model, truth, free=False):
+    model.parameters['ra_center'].set(value=truth['ra_center'], fixed=not free)
+    model.parameters['dec_center'].set(value=truth['dec_center'], fixed=not free)
+
+
+def config_c1():
+    d = np.load(os.path.join(ROOT, 'tests', 'golden', 'c1_example_catalogue.npz'))
+    data = synthetic.reader_from_columns({k: d[k] for k in ('ra', 'dec', 'v', 'verr')})
+    truth = {'ra_center': float(d['ra_center']), 'dec_center': float(d['dec_center']), 'v_sys': 0.0,
+             'sigma_max': 30.0, 'v_maxx': 2.0, 'v_maxy': -2.0}
+    m = ConstantFit(data)
+    fix_centre(m, truth)
+    m.parameters['v_sys'].set(value=0.0, fixed=True)        # bin/run.py:487-491
+    return 'C1 example catalogue, ConstantFit, v_sys fixed', m, truth, 16
+
+
+def config_c2():
+    data, truth = synthetic.mock_cluster(10_000, seed=1)
+    m = ModelFit(data)
+    fix_centre(m, truth)
+    return 'C2 1e4 stars, ModelFit fixed centre', m, truth, 128
+
+
+def config_c3(gb=False):
+    cols, truth = synthetic.mock_cluster(100_000, seed=2, as_reader=False)
+    cols, sample_field = synthetic.add_background(cols, truth, seed=102)
+    truth = dict(truth, v_back=5.0, sigma_back=55.0, f_back=0.3)
+    data = synthetic.reader_from_columns(cols)
+    if gb:
+        m = ModelFitGB(data)
+        name = 'C3b 1e5 stars, ModelFitGB (fitted Gaussian background)'
+    else:
+        t0 = time.perf_counter()
+        bg = SingleStars(sample_field(2000, seed=202))
+        m = ModelFit(data, background=bg)
+        name = 'C3 1e5 stars, ModelFit + SingleStars(M=2000) mixture [bg precompute %.0f ms]' % (
+            1e3 * (time.perf_counter() - t0))
+    fix_centre(m, truth)
+    return name, m, truth, 256
+
+
+def config_c4():
+    data, truth = synthetic.mock_cluster(300_000, seed=3, ra_center=201.696718746, dec_center=-47.479909445555,
+                                         v_sys=232.5)
+    m = ModelFit(data)
+    fix_centre(m, truth, free=True)
+    m.parameters['v_sys'].set(value=232.5, fixed=True)      # bin/run_test_5139_center.py:157-165
+    m.parameters['sigma_max'].set(min=0, max=100)
+    m.parameters['a'].set(min=0, max=300)
+    m.parameters['v_maxx'].set(min=-100, max=100)
+    m.parameters['v_maxy'].set(min=-100, max=100)
+    m.parameters['r_peak'].set(min=0, max=500)
+    return 'C4 3e5 stars, ModelFit free centre, omega Cen-like bounds', m, truth, 128
+
+
+def config_c5(free=False, n=10_000_000):
+    data, truth = synthetic.mock_cluster(n, seed=4)
+    m = ModelFit(data)
+    fix_centre(m, truth, free=free)
+    return 'C5 %.0e stars, ModelFit %s centre' % (n, 'free' if free else 'fixed'), m, truth, 1024
+
+
+def time_device(model, theta_dev, reps):
+    for _ in range(3):
+        model.lnprob_tensor(theta_dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        model.lnprob_tensor(theta_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
+def time_host(model, theta, reps):
+    for _ in range(3):
+        model.lnprob(theta)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        model.lnprob(theta)
+    return (time.perf_counter() - t0) / reps
+
+
+def run(name, model, truth, n_walkers, quick):
+    n = model.n_data
+    half = n_walkers // 2
+    theta = synthetic.initial_ball(truth, model.fitted_parameters, n_walkers, seed=5, scale=0.05)
+    got = model.lnprob(theta[:half])
+    n_check = min(half, 4 if n > 1_000_000 else 16)
+    oracle = harness.oracle_for(model)
+    t0 = time.perf_counter()
+    want = oracle.lnprob_many(theta[:n_check])
+    cpu_s = (time.perf_counter() - t0) / n_check
+    err = harness.relative_error(got[:n_check], want)
+    reps = 5 if n >= 1_000_000 else 50
+    dev_s = time_device(model, torch.as_tensor(theta[:half], device='cuda:0'), reps)
+    host_s = time_host(model, theta[:half], reps)
+    terms = half * n
+    # sampler steps/s (one step = two half-ensemble calls)
+    steps = 20 if n >= 1_000_000 else (100 if quick else 300)
+    s = samplers.DeviceEnsembleSampler(n_walkers, model.n_fitted_parameters, model.pack(), seed=1)
+    s.run_mcmc(theta, 5, store=False)
+    t0 = time.perf_counter()
+    s.run_mcmc(None, steps, store=False)
+    dev_steps = steps / (time.perf_counter() - t0)
+    h = samplers.HostEnsembleSampler(n_walkers, model.n_fitted_parameters, model.lnprob, seed=1)
+    pos, lnp, _ = h.run_mcmc(theta, 3, store=False)
+    t0 = time.perf_counter()
+    h.run_mcmc(pos, steps, log_prob0=lnp, store=False)
+    host_steps = steps / (time.perf_counter() - t0)
+    cpu_terms = n / cpu_s
+    return ('| %s | %d | %d | %.1e | %.3g | %.3g | %.3g | %.1f | %.1f | %.3g | %.2f |' % (
+        name, n, n_walkers, err, terms / dev_s, terms / host_s, 1e6 * host_s, dev_steps, host_steps, cpu_terms,
+        n_walkers * n / cpu_terms))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--out', default=None)
+    ap.add_argument('--quick', action='store_true')
+    args = ap.parse_args()
+    lines = [
+        '| config | stars | walkers | max rel. err vs oracle | terms/s (device theta) | terms/s (host buffers, C ABI) | '
+        'µs per half-ensemble call (host) | steps/s device sampler | steps/s host sampler | CPU oracle terms/s '
+        '(1 process) | CPU s per emcee step (1 process) |',
+        '|---|---|---|---|---|---|---|---|---|---|---|']
+    builders = [config_c1, config_c2, config_c3, lambda: config_c3(gb=True), config_c4, config_c5,
+                lambda: config_c5(free=True)]
+    if args.quick:
+        builders = builders[:5]
+    for build in builders:
+        name, model, truth, n_walkers = build()
+        line = run(name, model, truth, n_walkers, args.quick)
+        print(line, flush=True)
+        lines.append(line)
+        model.pack().close()
+        del model
+    text = '\n'.join(lines) + '\n'
+    if args.out:
+        with open(args.out, 'w') as f:
+            f.write('# BASELINE.json configurations on one B200 (tools/config_sweep.py)\n\n' + text)
+
+
+if __name__ == '__main__':
+    main()
