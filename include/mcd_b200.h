@@ -139,6 +139,12 @@ int mcd_lnprob_partial_device(mcd_handle *h, const double *theta_dev, int32_t n_
 int mcd_lnlike_per_star(mcd_handle *h, const double *theta_host, double *out_host /* [N] */);
 int mcd_lnlike_per_star_device(mcd_handle *h, const double *theta_dev, double *out_dev, void *stream);
 
+/* A-posteriori membership probability of every star at ONE parameter vector (the posterior median
+ * in the reference): m e^lc / (m e^lc + (1-m) e^lb), max-shifted -- constant.py:366-374,
+ * model.py:458-510,625-687.  Needs a background mode other than MCD_BG_NONE. */
+int mcd_membership_per_star(mcd_handle *h, const double *theta_host, double *out_host /* [N] */);
+int mcd_membership_per_star_device(mcd_handle *h, const double *theta_dev, double *out_dev, void *stream);
+
 /* Background precompute: SingleStars.__call__ (background/single_stars.py:42-77) without the
  * M x N intermediate.  v_bg[M], v[N], verr[N] are HOST arrays; out[N]. */
 int mcd_single_stars_lnlike(int32_t device, const double *v_bg, int64_t m, const double *v, const double *verr,

@@ -368,10 +368,61 @@ class Runner(object):
         return chain[:, -1, :]
 
     def compute_percentiles(self, chain, n_burn, pct=None):
-        """``analysis/runner.py:566-613``: percentiles [16, 50, 84] of the post-burn-in samples of every
-        fitted parameter; returns {name: array}."""
+        """``analysis/runner.py:566-613``: the requested percentiles (default 16, 50, 84) of the
+        post-burn-in samples of every fitted parameter, shape ``[len(pct), n_fitted]``."""
         if pct is None:
             pct = [16, 50, 84]
-        samples = np.asarray(chain)[:, n_burn:, :].reshape((-1, self.n_fitted_parameters))
-        values = np.percentile(samples, pct, axis=0)
-        return {name: values[:, i] for i, name in enumerate(self.fitted_parameters)}
+        _samples = np.asarray(chain)[:, n_burn:, :].reshape((-1, self.n_fitted_parameters))
+        return np.percentile(_samples, pct, axis=0)
+
+    def compute_bestfit_values(self, chain, n_burn):
+        """``analysis/runner.py:615-660``: median and upper / lower uncertainty of every fitted
+        parameter.  The reference returns an indexed astropy table; this returns a
+        :class:`BestFit` with the same access pattern (``bestfit.columns``,
+        ``bestfit.loc['median'][name]``) and, like the reference, stores the medians as the
+        parameters' current values."""
+        percentiles = self.compute_percentiles(chain, n_burn=n_burn, pct=[16, 50, 84])
+        columns = {}
+        i = 0
+        for name, parameter in self.parameters.items():
+            if parameter.fixed:
+                continue
+            parameter.value = percentiles[1, i]
+            columns[name] = (percentiles[1, i], percentiles[2, i] - percentiles[1, i],
+                             percentiles[1, i] - percentiles[0, i])
+            i += 1
+        return BestFit(columns, {name: self.parameters[name].unit for name in columns})
+
+    def calculate_membership_probabilities(self, chain, n_burn):
+        """A-posteriori cluster membership probability of every star at the posterior median
+        (``constant.py:366-374``, ``model.py:458-510,625-687``): one per-star kernel launch.
+        Available for every model with a background component."""
+        if self._background_mode() == _native.BG_NONE:
+            raise NotImplementedError('membership probabilities need a background component')
+        median = self.compute_percentiles(chain, n_burn=n_burn, pct=[50])[0]
+        self.compute_bestfit_values(chain, n_burn)          # the reference updates parameter values here
+        return self.pack().membership_per_star(median)
+
+
+class BestFit(object):
+    """Rows ``median / uperr / loerr`` by parameter (stand-in for the indexed table of
+    ``analysis/runner.py:640-660``)."""
+
+    ROWS = ('median', 'uperr', 'loerr')
+
+    def __init__(self, columns, units):
+        self._columns = columns
+        self.units = units
+        self.columns = ['value'] + list(columns)
+
+    @property
+    def loc(self):
+        return {row: dict([('value', row)] + [(name, u.Quantity(values[k], self.units[name]) if self.units[name]
+                                               is not None else values[k])
+                                              for name, values in self._columns.items()])
+                for k, row in enumerate(self.ROWS)}
+
+    def __getitem__(self, name):
+        if name == 'value':
+            return list(self.ROWS)
+        return np.asarray(self._columns[name])

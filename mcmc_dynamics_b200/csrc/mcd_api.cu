@@ -406,7 +406,7 @@ extern "C" int mcd_lnprob_partial_device(mcd_handle *h, const double *theta_dev,
 // ------------------------------------------------------------------------------------------
 // per-star lnlike (no_sum)
 // ------------------------------------------------------------------------------------------
-static int per_star(mcd_handle *h, const double *theta_dev, double *out_dev, cudaStream_t stream) {
+static int per_star(mcd_handle *h, const double *theta_dev, double *out_dev, int membership, cudaStream_t stream) {
     LaunchParams p{};
     fill_params(h, p);
     p.n_walkers = 1;
@@ -415,7 +415,8 @@ static int per_star(mcd_handle *h, const double *theta_dev, double *out_dev, cud
     // the FAST packing keeps a mantissa
     const int nb = variant_columns(h->var) - (h->var.background == MCD_BG_NONE ? 0 : (h->var.background == MCD_BG_GAUSSIAN ? 1 : 2));
     if (h->var.background == MCD_BG_FIXED_PMEMBER || h->var.background == MCD_BG_FIXED_DENSITY) p.cols[nb + 1] = h->raw[RAW_LBG];
-    MCD_CUDA(launch_per_star(h->var, p, out_dev, stream));
+    if (membership && h->var.background == MCD_BG_NONE) return fail(-1, "membership probabilities need a background component");
+    MCD_CUDA(launch_per_star(h->var, p, out_dev, membership, stream));
     h->info.launches += 1;
     return 0;
 }
@@ -423,10 +424,16 @@ static int per_star(mcd_handle *h, const double *theta_dev, double *out_dev, cud
 extern "C" int mcd_lnlike_per_star_device(mcd_handle *h, const double *theta_dev, double *out_dev, void *stream) {
     if (!h || !out_dev) return fail(-1, "null argument");
     MCD_CUDA(cudaSetDevice(h->device));
-    return per_star(h, theta_dev, out_dev, static_cast<cudaStream_t>(stream));
+    return per_star(h, theta_dev, out_dev, 0, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int mcd_lnlike_per_star(mcd_handle *h, const double *theta_host, double *out_host) {
+extern "C" int mcd_membership_per_star_device(mcd_handle *h, const double *theta_dev, double *out_dev, void *stream) {
+    if (!h || !out_dev) return fail(-1, "null argument");
+    MCD_CUDA(cudaSetDevice(h->device));
+    return per_star(h, theta_dev, out_dev, 1, static_cast<cudaStream_t>(stream));
+}
+
+static int per_star_host(mcd_handle *h, const double *theta_host, double *out_host, int membership) {
     if (!h || !out_host) return fail(-1, "null argument");
     MCD_CUDA(cudaSetDevice(h->device));
     if (h->n == 0) return 0;
@@ -436,8 +443,15 @@ extern "C" int mcd_lnlike_per_star(mcd_handle *h, const double *theta_host, doub
         memcpy(h->theta_pin, theta_host, sizeof(double) * h->desc.n_theta);
         MCD_CUDA(cudaMemcpyAsync(h->theta_dev, h->theta_pin, sizeof(double) * h->desc.n_theta, cudaMemcpyHostToDevice, h->stream));
     }
-    if (int rc = per_star(h, h->theta_dev, h->star_dev, h->stream)) return rc;
+    if (int rc = per_star(h, h->theta_dev, h->star_dev, membership, h->stream)) return rc;
     MCD_CUDA(cudaMemcpyAsync(out_host, h->star_dev, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
     MCD_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+extern "C" int mcd_lnlike_per_star(mcd_handle *h, const double *theta_host, double *out_host) {
+    return per_star_host(h, theta_host, out_host, 0);
+}
+extern "C" int mcd_membership_per_star(mcd_handle *h, const double *theta_host, double *out_host) {
+    return per_star_host(h, theta_host, out_host, 1);
 }

@@ -76,8 +76,9 @@ int variant_flops_per_term(const Variant &v);
 
 cudaError_t launch_pack(const PackParams &p, cudaStream_t stream);
 cudaError_t launch_lnlike(const Variant &v, const LaunchParams &p, cudaStream_t stream);
-// per-star lnlike of walker 0 of p.theta into out[N] (always PLAIN arithmetic)
-cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out, cudaStream_t stream);
+// per-star lnlike (membership = 0) or membership probability (1) of walker 0 of p.theta into out[N]
+// (always PLAIN arithmetic)
+cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out, int membership, cudaStream_t stream);
 // resident CTAs per SM of the lnlike kernel of this variant (occupancy API)
 int lnlike_blocks_per_sm(const Variant &v);
 

@@ -234,7 +234,8 @@ struct Accum<BG, MCD_MATH_FAST> {
 template <int BG>
 struct Accum<BG, MCD_MATH_PLAIN> {
     double sum;
-    __device__ __forceinline__ void reset() { sum = 0.0; }
+    double pmember;     // a-posteriori membership of the last star (per-star kernel only; dead elsewhere)
+    __device__ __forceinline__ void reset() { sum = 0.0; pmember = 1.0; }
     __device__ __forceinline__ void end_group() {}
     __device__ __forceinline__ void end_tile() {}
     __device__ __forceinline__ double value() { return sum; }
@@ -361,7 +362,9 @@ __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(R
             }
             // runner.py:279-284, constant.py:320-323, model.py:452-454,614-618
             const double mx = fmax(lm, lb);
-            A.sum += mx + log(wm * exp(lm - mx) + (1.0 - wm) * exp(lb - mx));
+            const double pm = wm * exp(lm - mx), pb = (1.0 - wm) * exp(lb - mx);
+            A.sum += mx + log(pm + pb);
+            A.pmember = pm / (pm + pb);     // constant.py:374, model.py:509-510,686-687
         }
     }
 }
@@ -579,10 +582,12 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
 }
 
 // ------------------------------------------------------------------------------------------
-// per-star lnlike of one parameter vector (`no_sum=True`, model.py:565,620-621)
+// per-star lnlike of one parameter vector (`no_sum=True`, model.py:565,620-621) or, with
+// `membership`, the a-posteriori membership probability of every star at that parameter vector
+// (constant.py:366-374, model.py:458-510,625-687)
 // ------------------------------------------------------------------------------------------
 template <int ROT, int FREE, int BG>
-__global__ void per_star_kernel(const __grid_constant__ LaunchParams P, double *__restrict__ out) {
+__global__ void per_star_kernel(const __grid_constant__ LaunchParams P, double *__restrict__ out, int membership) {
     constexpr int NC = total_columns(ROT, FREE, BG);
     __shared__ Walker Ws;
     if (threadIdx.x == 0) load_walker<ROT, FREE, BG>(P, 0, Ws);
@@ -597,7 +602,7 @@ __global__ void per_star_kernel(const __grid_constant__ LaunchParams P, double *
     A.reset();
     const Walker W = Ws;
     term<ROT, FREE, BG, MCD_MATH_PLAIN>(W, S, A);
-    out[i] = A.value();
+    out[i] = membership ? A.pmember : A.value();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -650,16 +655,16 @@ int lnlike_blocks_per_sm(const Variant &v) {
 }
 
 template <int ROT, int FREE, int BG, int MATH_UNUSED>
-static cudaError_t per_star_one(const LaunchParams &p, double *out, cudaStream_t stream) {
+static cudaError_t per_star_one(const LaunchParams &p, double *out, int membership, cudaStream_t stream) {
     if (p.n_stars <= 0) return cudaSuccess;
     const int block = 256;
     const long long grid = (p.n_stars + block - 1) / block;
-    per_star_kernel<ROT, FREE, BG><<<(unsigned)grid, block, 0, stream>>>(p, out);
+    per_star_kernel<ROT, FREE, BG><<<(unsigned)grid, block, 0, stream>>>(p, out, membership);
     return cudaGetLastError();
 }
 
-cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out, cudaStream_t stream) {
-    MCD_DISPATCH_GEO(MCD_MATH_PLAIN, per_star_one, p, out, stream)
+cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out, int membership, cudaStream_t stream) {
+    MCD_DISPATCH_GEO(MCD_MATH_PLAIN, per_star_one, p, out, membership, stream)
 }
 
 }  // namespace mcd

@@ -185,6 +185,15 @@ class PackedModel(object):
                                                     _native.as_double_ptr(out)))
         return out
 
+    def membership_per_star(self, theta):
+        theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1)
+        if theta.size != self.n_theta:
+            raise ValueError('theta must have {0} entries'.format(self.n_theta))
+        out = np.empty(self.n_stars, dtype=np.float64)
+        _native.check(self._lib.mcd_membership_per_star(self.handle, _native.as_double_ptr(theta),
+                                                        _native.as_double_ptr(out)))
+        return out
+
     # ---- device tensors (torch operator library; current CUDA stream) ----------------------
     def lnprob_tensor(self, theta):
         return _native.load_torch_ops().lnprob(self.handle.value, theta)

@@ -280,6 +280,13 @@ class OracleRunner(object):
         return -0.5 * np.log(2. * np.pi * norm) + exponent
 
     @staticmethod
+    def _membership(lnlike_cluster, lnlike_back, m):
+        """constant.py:374 (max-shifted like model.py:507-510, 684-687), per star."""
+        max_lnlike = np.max([lnlike_cluster, lnlike_back], axis=0)
+        return m * np.exp(lnlike_cluster - max_lnlike) / (
+            m * np.exp(lnlike_cluster - max_lnlike) + (1. - m) * np.exp(lnlike_back - max_lnlike))
+
+    @staticmethod
     def _mixture(lnlike_cluster, lnlike_back, m):
         """constant.py:320-323 / model.py:452-454 / model.py:614-618, per star."""
         max_lnlike = np.max([lnlike_cluster, lnlike_back], axis=0)
@@ -338,6 +345,15 @@ class OracleConstantFitGB(OracleConstantFit):
     def lnlike(self, values):
         """constant.py:316-324."""
         return self.lnlike_per_star(values).sum()
+
+    def membership(self, values):
+        """constant.py:366-374 at the parameter vector `values`."""
+        par = self.fetch_parameter_values(values)
+        lnlike_back = self._fitted_background(self._kms('v_back', par['v_back']),
+                                              self._kms('sigma_back', par['sigma_back']))
+        m = self.density / (self.density + par['f_back'])
+        v_los, sigma_los = self._models(par)
+        return self._membership(self._cluster_gaussian(v_los, sigma_los), lnlike_back, m)
 
 
 class OracleModelFit(OracleRunner):
@@ -402,6 +418,15 @@ class OracleModelFitGB(OracleModelFit):
         """model.py:414-456."""
         return self.lnlike_per_star(values).sum()
 
+    def membership(self, values):
+        """model.py:458-510 at the parameter vector `values`."""
+        par = self.fetch_parameter_values(values)
+        lnlike_back = self._fitted_background(self._kms('v_back', par['v_back']),
+                                              self._kms('sigma_back', par['sigma_back']))
+        m = self.density / (self.density + par['f_back'])
+        v_los, sigma_los = self._models(par)
+        return self._membership(self._cluster_gaussian(v_los, sigma_los), lnlike_back, m)
+
 
 class OracleModelFitConstantBackground(OracleModelFit):
     """analysis/model.py:513-623; `lnlike_background` is the precomputed column of
@@ -418,6 +443,13 @@ class OracleModelFitConstantBackground(OracleModelFit):
         if no_sum:
             return lnlike
         return lnlike.sum()
+
+    def membership(self, values):
+        """model.py:625-687 at the parameter vector `values`."""
+        par = self.fetch_parameter_values(values)
+        m = self.density / (self.density + par['f_back'])
+        v_los, sigma_los = self._models(par)
+        return self._membership(self._cluster_gaussian(v_los, sigma_los), self.lnlike_background, m)
 
     def _calculate_lnlike(self, v_los, sigma_los):   # not used by this class (model.py:565-623)
         raise NotImplementedError

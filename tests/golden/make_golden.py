@@ -167,6 +167,25 @@ def main():
             if no_sum:
                 per_star = model.lnlike(theta[0], no_sum=True)
                 per_star = [float(x) for x in np.asarray(getattr(per_star, 'value', per_star))]
+        membership = None
+        if hasattr(model, 'calculate_membership_probabilities') and cls_name != 'ConstantFit' and cls_name != 'ModelFit':
+            # the reference evaluates the membership at the posterior median of a chain: hand it a
+            # chain whose every sample is theta[0] and a minimal stand-in for its indexed best-fit table
+            class _BestFit(object):
+                def __init__(self, names, values, units):
+                    self.columns = ['value'] + list(names)
+                    self.loc = {'median': dict([('value', 'median')] + [
+                        (n_, (u.Quantity(v_, un) if un is not None else v_)) for n_, v_, un in zip(names, values, units)])}
+            units = [model.parameters[n_].unit for n_ in names]
+            model.compute_bestfit_values = lambda chain, n_burn: _BestFit(names, theta[0], units)
+            if cls_name == 'ConstantFitGB':
+                # constant.py:370 hands only the fitted medians on; its helper needs the fixed centre too
+                orig = model._calculate_lnlike_cluster_back
+                fixed = {n_: u.Quantity(p_.value, p_.unit) for n_, p_ in model.parameters.items() if p_.fixed}
+                model._calculate_lnlike_cluster_back = lambda pars: orig(dict(pars, **fixed))
+            with np.errstate(all='ignore'):
+                pm = model.calculate_membership_probabilities(chain=None, n_burn=0)
+            membership = [float(x) for x in np.asarray(getattr(pm, 'value', pm))]
         case = {
             'name': name, 'class': cls_name, 'free_centre': free_centre, 'background': bg_desc,
             'columns': {k: [float(x) for x in v] for k, v in columns.items()},
@@ -179,6 +198,8 @@ def main():
             case['lnlike_background'] = [float(x) for x in np.asarray(getattr(lbg, 'value', lbg))]
         if per_star is not None:
             case['lnlike_per_star_theta0'] = per_star
+        if membership is not None:
+            case['membership_theta0'] = membership
         cases.append(case)
         print('%-44s lnprob[0] = %.12g' % (name, out['lnprob'][0]))
 

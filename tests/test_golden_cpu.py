@@ -33,6 +33,14 @@ def test_oracle_reproduces_reference_outputs(case):
     if 'lnlike_per_star_theta0' in case:
         per_star = oracle.lnlike(theta[0], no_sum=True)
         assert np.allclose(per_star, case['lnlike_per_star_theta0'], rtol=1e-12, atol=1e-13)
+    if 'membership_theta0' in case:
+        with np.errstate(all='ignore'):
+            assert np.allclose(oracle.membership(theta[0]), case['membership_theta0'], rtol=1e-11, atol=1e-15)
+
+
+def test_membership_vectors_cover_the_three_classes_that_define_them():
+    have = {c['class'] for c in GOLDEN['cases'] if 'membership_theta0' in c}
+    assert have == {'ConstantFitGB', 'ModelFitGB', 'ModelFitConstantBackground'}
 
 
 def test_prior_rejections_are_present_in_the_vectors():

@@ -31,3 +31,10 @@ def test_cuda_reproduces_reference_outputs(case, math_mode):
     if 'lnlike_per_star_theta0' in case:
         got = model.lnlike(theta[0], no_sum=True)
         assert np.allclose(got, case['lnlike_per_star_theta0'], rtol=1e-9, atol=1e-12)
+    if 'membership_theta0' in case:
+        # calculate_membership_probabilities evaluates at the posterior median: a chain whose every
+        # sample is theta[0] has that median
+        chain = np.broadcast_to(theta[0], (4, 3, theta.shape[1])).copy()
+        got = model.calculate_membership_probabilities(chain, n_burn=1)
+        assert np.allclose(got, case['membership_theta0'], rtol=1e-9, atol=1e-13)
+        assert np.all((got >= 0) & (got <= 1))

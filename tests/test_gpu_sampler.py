@@ -52,16 +52,17 @@ def test_device_and_host_samplers_agree_and_recover_the_truth():
     dev = model(n_walkers=n_walkers, n_steps=n_steps, pos=pos, sampler='device', seed=11, prefix=None)
     host = model(n_walkers=n_walkers, n_steps=n_steps, pos=pos, sampler='host', seed=12, prefix=None)
     assert dev.chain.shape == host.chain.shape == (n_walkers, n_steps, 6)
-    pd = model.compute_percentiles(dev.chain, n_burn)
+    pd = model.compute_percentiles(dev.chain, n_burn)        # [3, n_fitted] like runner.py:566-613
     ph = model.compute_percentiles(host.chain, n_burn)
-    for name in model.fitted_parameters:
-        lo_d, med_d, hi_d = pd[name]
-        lo_h, med_h, hi_h = ph[name]
+    assert pd.shape == (3, 6)
+    for j, name in enumerate(model.fitted_parameters):
+        lo_d, med_d, hi_d = pd[:, j]
+        lo_h, med_h, hi_h = ph[:, j]
         width = 0.5 * ((hi_d - lo_d) + (hi_h - lo_h)) / 2.0
-        assert abs(med_d - med_h) < 0.35 * 2 * width, (name, pd[name], ph[name])
-        assert 0.6 < (hi_d - lo_d) / (hi_h - lo_h) < 1.6, (name, pd[name], ph[name])
+        assert abs(med_d - med_h) < 0.35 * 2 * width, (name, pd[:, j], ph[:, j])
+        assert 0.6 < (hi_d - lo_d) / (hi_h - lo_h) < 1.6, (name, pd[:, j], ph[:, j])
         # truth within ~3.5 sigma of the posterior
-        assert abs(med_d - truth[name]) < 3.5 * width + 1e-9, (name, pd[name], truth[name])
+        assert abs(med_d - truth[name]) < 3.5 * width + 1e-9, (name, pd[:, j], truth[name])
 
 
 def test_runner_call_signature_and_checkpoint(tmp_path):
