@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -239,21 +240,46 @@ static void choose_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p)
     p.wl = best_wl;
     p.slices = best_s;
     p.n_groups = best_g;
-    // star chunks per walker group: kWaves waves of CTAs when the catalogue is large enough, so that
-    // SMs whose CTAs finish early pick up new ones (a single wave leaves the FP64 pipe idle in the tail)
+    // Star tiling: stars per stage (`tile`, multiple of 16) and tiles per CTA are chosen together so
+    // that the grid fills whole waves of resident CTAs (a grid of 1.3 waves runs as long as one of
+    // 2.0) while the per-CTA prologue/epilogue stays amortised.  Cost model per candidate, in star
+    // iterations per thread: (waves + 0.3) * (tiles_per_chunk * (tile / slices + 3) + overhead); the 0.3
+    // accounts for CTAs of the last wave finishing at different times (measured: a single wave
+    // leaves the FP64 pipe partly idle in the tail), 3 for the barrier and stage hand-over of every
+    // tile, `overhead` for walker set-up and reduction.
     const int wave = std::max(1, h->sm_count * h->blocks_per_sm);
     const int per_wave = std::max(1, wave / p.n_groups);
-    // stars per stage: large enough that every slice has work, small enough to spread a small
-    // catalogue over the machine
-    long long tile = (h->n + per_wave - 1) / per_wave;
-    tile = std::max<long long>(tile, 2LL * p.slices);
-    tile = ((tile + 15) / 16) * 16;
-    tile = std::min<long long>(std::max<long long>(tile, 16), kMaxTile);
-    p.tile = (int)tile;
-    p.n_tiles = (int)((h->n + tile - 1) / tile);
-    const int chunks_target = per_wave * kWaves;
-    p.tiles_per_chunk = std::max(1, (p.n_tiles + chunks_target - 1) / chunks_target);
-    p.tiles_per_chunk = std::max(p.tiles_per_chunk, std::min(4, std::max(1, p.n_tiles / per_wave)));
+    const double overhead = 24.0;
+    const long long n = std::max<long long>(h->n, 1);
+    int min_tile = ((2 * p.slices + 15) / 16) * 16;
+    min_tile = std::min(std::max(min_tile, 16), kMaxTile);
+    double best = 1e300;
+    int best_tile = kMaxTile, best_tpc = 1;
+    for (int tile = min_tile; tile <= kMaxTile; tile += 16) {
+        const long long n_tiles = (n + tile - 1) / tile;
+        for (int target = 1; target <= kWaves; ++target) {
+            const long long slots = (long long)target * per_wave;
+            const long long tpc = std::max<long long>(1, (n_tiles + slots - 1) / slots);
+            const long long chunks = (n_tiles + tpc - 1) / tpc;
+            const long long waves = (chunks + per_wave - 1) / per_wave;
+            const double cost = ((double)waves + 0.3) * ((double)tpc * ((double)tile / p.slices + 3.0) + overhead);
+            if (cost < best * (1.0 - 1e-12)) {
+                best = cost;
+                best_tile = tile;
+                best_tpc = (int)tpc;
+            }
+        }
+    }
+    if (const char *env = getenv("MCD_GEOMETRY")) {   // "tile,tiles_per_chunk": experiments only
+        int t = 0, c = 0;
+        if (sscanf(env, "%d,%d", &t, &c) == 2 && t >= min_tile && t <= kMaxTile && t % 16 == 0 && c >= 1) {
+            best_tile = t;
+            best_tpc = c;
+        }
+    }
+    p.tile = best_tile;
+    p.n_tiles = (int)((h->n + best_tile - 1) / best_tile);
+    p.tiles_per_chunk = best_tpc;
     p.n_chunks = std::max(1, (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk);
     p.super = kSuper;
     p.n_super = (p.n_chunks + kSuper - 1) / kSuper;

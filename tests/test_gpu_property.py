@@ -1,0 +1,86 @@
+"""Property tests (hypothesis): random catalogues, random walker counts and random parameter vectors
+inside the priors, every model variant, against the oracle (1e-9 relative), plus C-ABI error paths."""
+import ctypes
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+from common import RTOL, VARIANTS, build
+from mcmc_dynamics_b200 import _native, synthetic
+from oracle import harness
+
+pytestmark = pytest.mark.gpu
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+@given(variant=st.sampled_from(VARIANTS), free_centre=st.booleans(), math_mode=st.sampled_from(['fast', 'plain']),
+       n_stars=st.integers(1, 700), n_walkers=st.integers(1, 70), seed=st.integers(0, 10_000),
+       scale=st.floats(0.01, 0.6))
+def test_random_inputs_match_oracle(variant, free_centre, math_mode, n_stars, n_walkers, seed, scale):
+    model, oracle, theta, _ = build(variant, n_stars=n_stars, free_centre=free_centre, seed=seed, math_mode=math_mode)
+    th = theta(n_walkers, seed=seed + 1, scale=scale)
+    got = model.lnprob(th)
+    want = oracle.lnprob_many(th)
+    assert not np.any(np.isnan(got))
+    assert np.array_equal(np.isinf(got), np.isinf(want))
+    assert harness.relative_error(got, want) < RTOL
+
+
+@settings(max_examples=15, deadline=None, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 1000), v_sys=st.floats(-300, 300), n_walkers=st.integers(2, 40))
+def test_offset_velocities_and_linearity_of_shards(seed, v_sys, n_walkers):
+    """lnlike is additive over disjoint star sets, for any systemic velocity offset."""
+    from mcmc_dynamics_b200.analysis import ConstantFit
+    cols, truth = synthetic.mock_cluster(400, seed=seed, as_reader=False, v_sys=v_sys)
+
+    def make(c):
+        m = ConstantFit(synthetic.reader_from_columns(c))
+        m.parameters['ra_center'].set(value=truth['ra_center'], fixed=True)
+        m.parameters['dec_center'].set(value=truth['dec_center'], fixed=True)
+        return m
+    whole = make(cols)
+    th = synthetic.initial_ball(truth, whole.fitted_parameters, n_walkers, seed=seed)
+    a = make({k: v[:123] for k, v in cols.items()}).lnlike(th)
+    b = make({k: v[123:] for k, v in cols.items()}).lnlike(th)
+    assert harness.relative_error(a + b, whole.lnlike(th)) < 1e-12
+
+
+def test_c_abi_error_paths(native_lib):
+    lib = native_lib
+    desc = _native.PackDesc()
+    handle = ctypes.c_void_p()
+    desc.rotation = 7
+    assert lib.mcd_pack_create(ctypes.byref(desc), ctypes.byref(handle)) != 0
+    assert b'rotation' in lib.mcd_last_error()
+    desc.rotation = 0
+    desc.n_theta = 99
+    assert lib.mcd_pack_create(ctypes.byref(desc), ctypes.byref(handle)) != 0
+    assert b'n_theta' in lib.mcd_last_error()
+    desc.n_theta = 1
+    desc.n_stars = 5                                     # columns missing
+    for k in range(_native.NPARAM):
+        desc.slot[k] = -1
+    assert lib.mcd_pack_create(ctypes.byref(desc), ctypes.byref(handle)) != 0
+    assert b'required' in lib.mcd_last_error()
+    assert handle.value is None
+    # a working handle rejects bad calls without crashing
+    model, _, theta, _ = build('ModelFit', n_stars=64)
+    packed = model.pack()
+    out = np.zeros(4)
+    th = theta(4)
+    assert lib.mcd_lnprob(packed.handle, _native.as_double_ptr(th), -1, _native.as_double_ptr(out)) != 0
+    assert lib.mcd_lnprob(packed.handle, None, 4, _native.as_double_ptr(out)) != 0
+    assert lib.mcd_lnprob(packed.handle, _native.as_double_ptr(th), 0, _native.as_double_ptr(out)) == 0
+    with pytest.raises(ValueError):
+        packed.lnprob(th[:, :-1])
+    with pytest.raises(_native.NativeError):
+        packed.membership_per_star(th[0])                # no background component
+    # an empty catalogue is legal: lnlike = 0 for accepted walkers
+    empty = type(model)(synthetic.reader_from_columns({k: np.zeros(0) for k in ('ra', 'dec', 'v', 'verr')}))
+    empty.parameters['ra_center'].set(value=10.0, fixed=True)
+    empty.parameters['dec_center'].set(value=0.0, fixed=True)
+    th[1, 1] = -1.0
+    res = empty.lnprob(th)
+    assert res[1] == -np.inf and np.all(np.delete(res, 1) == 0.0)
