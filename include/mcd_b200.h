@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 1
+#define MCD_ABI_VERSION 2
 
 /* Rotation / dispersion model.
  *   CONSTANT: analysis/constant.py:52-111  (ConstantFit.rotation_model / dispersion_model)
@@ -88,6 +88,14 @@ typedef struct mcd_pack_desc {
     int32_t fixed_prior_ok;           /* 0: a fixed parameter violates its bounds => all -inf   */
     int32_t device;                   /* CUDA device ordinal                                    */
     int64_t n_stars_total;            /* N of the whole catalogue when star-sharded, else 0     */
+    /* Segments: n_segments > 1 turns the handle into a batch of independent problems that share the
+     * model and the parameter routing -- the per-radial-bin fits of bin/run.py:179-190 and
+     * bin/run_tests.py:81-97, one ConstantFit per bin.  Stars [segment_offsets[s],
+     * segment_offsets[s+1]) of the columns belong to segment s; theta is then
+     * [n_segments][n_walkers][n_theta], results are [n_segments][n_walkers], and `n_walkers` in
+     * every call is the number of walkers PER segment. */
+    int32_t n_segments;               /* 0 or 1: one problem                                    */
+    const int64_t *segment_offsets;   /* [n_segments + 1] host array, or NULL                   */
 } mcd_pack_desc;
 
 typedef struct mcd_handle mcd_handle;
@@ -103,6 +111,7 @@ typedef struct mcd_info {
     int32_t last_grid_x, last_grid_y, last_block;   /* geometry of the most recent launch       */
     int32_t last_walker_tile;
     int64_t launches;             /* kernels launched through this handle so far                */
+    int32_t n_segments;
 } mcd_info;
 
 int mcd_abi_version(void);

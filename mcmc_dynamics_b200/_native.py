@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('MCD_B200_LIB') or os.path.join(_HERE, '_lib', 'libmcd_b200.so')
 TORCH_LIB_PATH = os.path.join(_HERE, '_lib', 'libmcd_torch.so')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 NPARAM = 11
 MAX_THETA = 16
 
@@ -41,6 +41,7 @@ class PackDesc(ctypes.Structure):
         ('unit_scale', ctypes.c_double * NPARAM),
         ('lower', ctypes.c_double * MAX_THETA), ('upper', ctypes.c_double * MAX_THETA),
         ('fixed_prior_ok', ctypes.c_int32), ('device', ctypes.c_int32), ('n_stars_total', ctypes.c_int64),
+        ('n_segments', ctypes.c_int32), ('segment_offsets', _c_int64_p),
     ]
 
 
@@ -51,6 +52,7 @@ class Info(ctypes.Structure):
         ('bytes_per_star', ctypes.c_int32), ('flops_per_term', ctypes.c_int32), ('free_centre', ctypes.c_int32),
         ('sm_count', ctypes.c_int32), ('last_grid_x', ctypes.c_int32), ('last_grid_y', ctypes.c_int32),
         ('last_block', ctypes.c_int32), ('last_walker_tile', ctypes.c_int32), ('launches', ctypes.c_int64),
+        ('n_segments', ctypes.c_int32),
     ]
 
 

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "mcd_internal.h"
 
@@ -39,6 +40,9 @@ struct mcd_handle {
     Variant var{};
     mcd_pack_desc desc{};          // routing part of the descriptor (column pointers cleared)
     long long n = 0, n_alloc = 0;
+    int n_segments = 1;            // independent star ranges (radial bins) evaluated by one launch
+    long long max_segment = 0;     // stars of the largest segment
+    long long *seg_begin = nullptr, *seg_packed = nullptr;   // device copies, n_segments > 1 only
     double *raw[RAW_COUNT] = {};
     double *cols[kMaxCols] = {};
     int32_t *icol = nullptr;
@@ -109,6 +113,9 @@ static int repack(mcd_handle *h) {
     for (int c = 0; c < kMaxCols; ++c) p.cols[c] = h->cols[c];
     p.icol = h->icol;
     p.n_stars = h->n;
+    p.n_segments = h->n_segments;
+    p.seg_begin = h->seg_begin;
+    p.seg_packed = h->seg_packed;
     p.rotation = d.rotation;
     p.background = d.background;
     p.free_centre = h->var.free_centre;
@@ -129,6 +136,7 @@ static int repack(mcd_handle *h) {
     h->info.flops_per_term = variant_flops_per_term(h->var);
     h->info.free_centre = h->var.free_centre;
     h->info.sm_count = h->sm_count;
+    h->info.n_segments = h->n_segments;
     return 0;
 }
 
@@ -138,6 +146,8 @@ extern "C" void mcd_destroy(mcd_handle *h) {
     for (auto &p : h->raw) cudaFree(p);
     for (auto &p : h->cols) cudaFree(p);
     cudaFree(h->icol);
+    cudaFree(h->seg_begin);
+    cudaFree(h->seg_packed);
     cudaFree(h->partials);
     cudaFree(h->partials2);
     cudaFree(h->counters);
@@ -148,6 +158,32 @@ extern "C" void mcd_destroy(mcd_handle *h) {
     cudaFreeHost(h->out_pin);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+}
+
+// Segments: every star range starts at a 16-star boundary of the packed columns so that the bulk
+// copies of each segment are 16-byte aligned for both the float64 and the int32 column.
+static int setup_segments(mcd_handle *h, const mcd_pack_desc *desc) {
+    const int S = desc->n_segments;
+    if (!desc->segment_offsets) return fail(-1, "n_segments > 1 needs segment_offsets");
+    std::vector<long long> begin(S + 1), packed(S);
+    long long pos = 0, longest = 0;
+    for (int s = 0; s <= S; ++s) begin[s] = desc->segment_offsets[s];
+    if (begin[0] != 0 || begin[S] != h->n) return fail(-1, "segment_offsets must run from 0 to n_stars");
+    for (int s = 0; s < S; ++s) {
+        const long long count = begin[s + 1] - begin[s];
+        if (count < 0) return fail(-1, "segment_offsets must be non-decreasing");
+        packed[s] = pos;
+        pos += ((count + 15) / 16) * 16;
+        longest = std::max(longest, count);
+    }
+    h->n_segments = S;
+    h->max_segment = longest;
+    h->n_alloc = ((pos + kMaxTile - 1) / kMaxTile + 1) * kMaxTile;
+    MCD_CUDA(cudaMalloc(&h->seg_begin, sizeof(long long) * (S + 1)));
+    MCD_CUDA(cudaMalloc(&h->seg_packed, sizeof(long long) * S));
+    MCD_CUDA(cudaMemcpy(h->seg_begin, begin.data(), sizeof(long long) * (S + 1), cudaMemcpyHostToDevice));
+    MCD_CUDA(cudaMemcpy(h->seg_packed, packed.data(), sizeof(long long) * S, cudaMemcpyHostToDevice));
+    return 0;
 }
 
 static int upload_column(mcd_handle *h, int which, const double *host) {
@@ -180,6 +216,10 @@ extern "C" int mcd_pack_create(const mcd_pack_desc *desc, mcd_handle **out) {
         if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(-2, "cudaStreamCreate failed"); break; }
         h->n = desc->n_stars;
         h->n_alloc = ((h->n + kMaxTile - 1) / kMaxTile + 1) * kMaxTile;   // full bulk copies at the tail
+        h->max_segment = h->n;
+        if (desc->n_segments > 1) {
+            if ((rc = setup_segments(h, desc))) break;
+        }
         h->desc = *desc;
         h->desc.ra = h->desc.dec = h->desc.v = h->desc.verr = nullptr;
         h->desc.pmember = h->desc.density = h->desc.lnlike_background = nullptr;
@@ -204,6 +244,7 @@ extern "C" int mcd_pack_reconfigure(mcd_handle *h, const mcd_pack_desc *desc) {
     if (!h || !desc) return fail(-1, "null argument");
     if (int rc = validate_routing(desc)) return rc;
     if (desc->n_stars != h->n) return fail(-1, "reconfigure cannot change the catalogue (n_stars %lld != %lld)", (long long)desc->n_stars, h->n);
+    if (desc->n_segments > 1 && desc->n_segments != h->n_segments) return fail(-1, "reconfigure cannot change the segments");
     MCD_CUDA(cudaSetDevice(h->device));
     h->desc = *desc;
     h->desc.ra = h->desc.dec = h->desc.v = h->desc.verr = nullptr;
@@ -248,9 +289,9 @@ static void choose_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p)
     // leaves the FP64 pipe partly idle in the tail), 3 for the barrier and stage hand-over of every
     // tile, `overhead` for walker set-up and reduction.
     const int wave = std::max(1, h->sm_count * h->blocks_per_sm);
-    const int per_wave = std::max(1, wave / p.n_groups);
+    const int per_wave = std::max(1, wave / (p.n_groups * h->n_segments));
     const double overhead = 24.0;
-    const long long n = std::max<long long>(h->n, 1);
+    const long long n = std::max<long long>(h->max_segment, 1);     // grid sized for the largest segment
     int min_tile = ((2 * p.slices + 15) / 16) * 16;
     min_tile = std::min(std::max(min_tile, 16), kMaxTile);
     double best = 1e300;
@@ -278,7 +319,7 @@ static void choose_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p)
         }
     }
     p.tile = best_tile;
-    p.n_tiles = (int)((h->n + best_tile - 1) / best_tile);
+    p.n_tiles = (int)((h->max_segment + best_tile - 1) / best_tile);
     p.tiles_per_chunk = best_tpc;
     p.n_chunks = std::max(1, (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk);
     p.super = kSuper;
@@ -286,7 +327,7 @@ static void choose_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p)
 }
 
 static int ensure_scratch(mcd_handle *h, const LaunchParams &p) {
-    const size_t need = (size_t)p.n_chunks * p.n_walkers;
+    const size_t need = (size_t)p.n_chunks * p.n_walkers * p.n_segments;
     if (need > h->partials_cap) {
         MCD_CUDA(cudaFree(h->partials));
         h->partials = nullptr;
@@ -294,7 +335,7 @@ static int ensure_scratch(mcd_handle *h, const LaunchParams &p) {
         MCD_CUDA(cudaMalloc(&h->partials, sizeof(double) * need));
         h->partials_cap = need;
     }
-    const size_t need2 = (size_t)p.n_super * p.n_walkers;
+    const size_t need2 = (size_t)p.n_super * p.n_walkers * p.n_segments;
     if (need2 > h->partials2_cap) {
         MCD_CUDA(cudaFree(h->partials2));
         h->partials2 = nullptr;
@@ -302,7 +343,7 @@ static int ensure_scratch(mcd_handle *h, const LaunchParams &p) {
         MCD_CUDA(cudaMalloc(&h->partials2, sizeof(double) * need2));
         h->partials2_cap = need2;
     }
-    const int n_counters = p.n_groups * (p.n_super + 1);
+    const int n_counters = p.n_segments * p.n_groups * (p.n_super + 1);
     if (n_counters > h->counters_cap) {
         MCD_CUDA(cudaFree(h->counters));
         h->counters = nullptr;
@@ -320,6 +361,9 @@ static void fill_params(const mcd_handle *h, LaunchParams &p) {
     for (int c = 0; c < kMaxCols; ++c) p.cols[c] = h->cols[c];
     p.icol = h->icol;
     p.n_stars = h->n;
+    p.n_segments = h->n_segments;
+    p.seg_begin = h->seg_begin;
+    p.seg_packed = h->seg_packed;
     p.n_theta = d.n_theta;
     p.fixed_prior_ok = d.fixed_prior_ok;
     for (int k = 0; k < MCD_NPARAM; ++k) {
@@ -392,16 +436,17 @@ static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, dou
     if (n_walkers == 0) return 0;
     if (!out_host || (!theta_host && h->desc.n_theta > 0)) return fail(-1, "null buffer");
     MCD_CUDA(cudaSetDevice(h->device));
-    const size_t nt = (size_t)n_walkers * h->desc.n_theta;
-    if (int rc = ensure_staging(h, nt, (size_t)n_walkers)) return rc;
+    const size_t rows = (size_t)n_walkers * h->n_segments;        // theta is [segments][walkers][theta]
+    const size_t nt = rows * h->desc.n_theta;
+    if (int rc = ensure_staging(h, nt, rows)) return rc;
     if (nt) {
         memcpy(h->theta_pin, theta_host, sizeof(double) * nt);
         MCD_CUDA(cudaMemcpyAsync(h->theta_dev, h->theta_pin, sizeof(double) * nt, cudaMemcpyHostToDevice, h->stream));
     }
     if (int rc = launch(h, h->theta_dev, n_walkers, h->out_dev, apply_prior, h->stream)) return rc;
-    MCD_CUDA(cudaMemcpyAsync(h->out_pin, h->out_dev, sizeof(double) * n_walkers, cudaMemcpyDeviceToHost, h->stream));
+    MCD_CUDA(cudaMemcpyAsync(h->out_pin, h->out_dev, sizeof(double) * rows, cudaMemcpyDeviceToHost, h->stream));
     MCD_CUDA(cudaStreamSynchronize(h->stream));
-    memcpy(out_host, h->out_pin, sizeof(double) * n_walkers);
+    memcpy(out_host, h->out_pin, sizeof(double) * rows);
     return 0;
 }
 
@@ -442,6 +487,7 @@ static int per_star(mcd_handle *h, const double *theta_dev, double *out_dev, int
     const int nb = variant_columns(h->var) - (h->var.background == MCD_BG_NONE ? 0 : (h->var.background == MCD_BG_GAUSSIAN ? 1 : 2));
     if (h->var.background == MCD_BG_FIXED_PMEMBER || h->var.background == MCD_BG_FIXED_DENSITY) p.cols[nb + 1] = h->raw[RAW_LBG];
     if (membership && h->var.background == MCD_BG_NONE) return fail(-1, "membership probabilities need a background component");
+    if (h->n_segments > 1) return fail(-1, "per-star entry points are not available for segmented handles");
     MCD_CUDA(launch_per_star(h->var, p, out_dev, membership, stream));
     h->info.launches += 1;
     return 0;

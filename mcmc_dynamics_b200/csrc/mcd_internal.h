@@ -27,6 +27,9 @@ struct RawColumns {
 // Everything the pack kernel needs to turn raw columns into the per-variant packed columns.
 struct PackParams {
     RawColumns raw;
+    int n_segments;                 // > 1: stars are scattered to 16-aligned segment positions
+    const long long *seg_begin;     // [n_segments + 1]
+    const long long *seg_packed;    // [n_segments]
     double *cols[kMaxCols];
     int32_t *icol;
     long long n_stars;
@@ -41,9 +44,12 @@ struct LaunchParams {
     const int32_t *icol;
     long long n_stars;
     int tile;                 // stars per stage (multiple of 16, <= kMaxTile)
-    int n_tiles;
+    int n_tiles;              // of the largest segment
     int tiles_per_chunk;
-    int n_chunks;             // gridDim.x
+    int n_chunks;             // gridDim.x: chunks of the largest segment
+    int n_segments;           // gridDim.z: independent (star range, walker set) problems, >= 1
+    const long long *seg_begin;   // [n_segments + 1] star index boundaries, or nullptr for one segment
+    const long long *seg_packed;  // [n_segments] 16-aligned position of each segment in the packed columns
     int n_groups;             // gridDim.y
     int n_walkers;
     int wl;                   // walkers per CTA
@@ -51,13 +57,13 @@ struct LaunchParams {
     int n_theta;
     int apply_prior;          // 1: lnprob (box prior fused), 0: lnlike
     int fixed_prior_ok;
-    const double *theta;      // [n_walkers][n_theta]
+    const double *theta;      // [n_segments][n_walkers][n_theta]
     int super;                // chunks per super-chunk (level 1 of the cross-CTA reduction)
     int n_super;              // super-chunks per walker group
-    double *partials;         // [n_chunks][n_walkers]
-    double *partials2;        // [n_super][n_walkers]
-    unsigned int *counters;   // [n_groups][n_super + 1], zero between launches
-    double *out;              // [n_walkers]
+    double *partials;         // [n_segments][n_chunks][n_walkers]
+    double *partials2;        // [n_segments][n_super][n_walkers]
+    unsigned int *counters;   // [n_segments][n_groups][n_super + 1], zero between launches
+    double *out;              // [n_segments][n_walkers]
     int slot[MCD_NPARAM];
     double fixed_scaled[MCD_NPARAM];   // fixed value already multiplied by its unit scale
     double scale[MCD_NPARAM];

@@ -10,7 +10,7 @@
 // and the walker-parallel process pool around it (analysis/runner.py:398-403).
 //
 // Work decomposition
-//   grid  = (star chunks, walker groups); a CTA owns `wl` walkers x `slices` star slices
+//   grid  = (star chunks, walker groups, segments); a CTA owns `wl` walkers x `slices` star slices
 //           (wl * slices <= 256 threads) and a contiguous run of star tiles.
 //   tile  = `tile` stars of every packed column, brought into shared memory by TMA bulk copies
 //           (cp.async.bulk, mbarrier completion), double buffered; every thread of the CTA then
@@ -21,6 +21,8 @@
 //           levels (last CTA of a super-chunk, last super-chunk of a walker group) that add in
 //           index order, so the result does not depend on CTA scheduling.
 #include <math.h>
+
+#include <algorithm>
 
 #include "mcd_internal.h"
 #include "mcd_math.cuh"
@@ -84,14 +86,24 @@ __global__ void pack_kernel(const PackParams P) {
     const double ra = P.raw.ra[i], dec = P.raw.dec[i];
     const double v = P.raw.v[i], verr = P.raw.verr[i];
     const double e2 = verr * verr;
+    // output position: identity, or the star's slot inside its 16-aligned segment
+    long long o = i;
+    if (P.n_segments > 1) {
+        int lo = 0, hi = P.n_segments;          // seg_begin[lo] <= i < seg_begin[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) / 2;
+            if (P.seg_begin[mid] <= i) lo = mid; else hi = mid;
+        }
+        o = P.seg_packed[lo] + (i - P.seg_begin[lo]);
+    }
     int c = 0;
     if (P.free_centre) {
         double sa, ca, sd, cd;
         sincos((ra - P.ra0_deg) * kDeg2Rad, &sa, &ca);
         sincos(dec * kDeg2Rad, &sd, &cd);
-        P.cols[c++][i] = cd * sa;
-        P.cols[c++][i] = cd * ca;
-        P.cols[c++][i] = sd;
+        P.cols[c++][o] = cd * sa;
+        P.cols[c++][o] = cd * ca;
+        P.cols[c++][o] = sd;
     } else {
         // utils/coordinates/calc_xy_offset.py:30-31, arcmin
         double sda, cda, sd, cd, sdc, cdc;
@@ -104,32 +116,32 @@ __global__ void pack_kernel(const PackParams P) {
             // theta_i = atan2(dy, dx) (constant.py:107).  A star exactly at the centre has
             // dx = -r0 cos(dec) sin(+0) = -0.0 and dy = +0.0, i.e. theta_i = atan2(+0, -0) = pi.
             const double r = sqrt(dx * dx + dy * dy);
-            P.cols[c++][i] = r > 0.0 ? dx / r : -1.0;
-            P.cols[c++][i] = r > 0.0 ? dy / r : 0.0;
+            P.cols[c++][o] = r > 0.0 ? dx / r : -1.0;
+            P.cols[c++][o] = r > 0.0 ? dy / r : 0.0;
         } else {
-            P.cols[c++][i] = dx;
-            P.cols[c++][i] = dy;
-            P.cols[c++][i] = dx * dx + dy * dy;
+            P.cols[c++][o] = dx;
+            P.cols[c++][o] = dy;
+            P.cols[c++][o] = dx * dx + dy * dy;
         }
     }
-    P.cols[c++][i] = v;
-    P.cols[c++][i] = e2;
+    P.cols[c++][o] = v;
+    P.cols[c++][o] = e2;
     if (P.background == MCD_BG_FIXED_PMEMBER || P.background == MCD_BG_FIXED_DENSITY) {
         const double w = P.background == MCD_BG_FIXED_PMEMBER ? P.raw.pmember[i] : P.raw.density[i];
         const double lbg = P.raw.lbg[i];
-        P.cols[c++][i] = w;
+        P.cols[c++][o] = w;
         if (P.math_mode == MCD_MATH_FAST) {
             double m;
             int e, invalid = 0;
             exp_split(lbg, m, e, invalid);
             const double wb = P.background == MCD_BG_FIXED_PMEMBER ? (1.0 - w) : 1.0;
-            P.cols[c++][i] = invalid ? __longlong_as_double(0x7ff8000000000000LL) : wb * kSqrt2Pi * m;
-            P.icol[i] = e;
+            P.cols[c++][o] = invalid ? __longlong_as_double(0x7ff8000000000000LL) : wb * kSqrt2Pi * m;
+            P.icol[o] = e;
         } else {
-            P.cols[c++][i] = lbg;
+            P.cols[c++][o] = lbg;
         }
     } else if (P.background == MCD_BG_GAUSSIAN) {
-        P.cols[c++][i] = P.raw.density[i];
+        P.cols[c++][o] = P.raw.density[i];
     }
 }
 
@@ -446,13 +458,23 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     int32_t *si = reinterpret_cast<int32_t *>(sd + (size_t)kStages * NC * TS);   // [kStages][TS]
 
     const int tid = threadIdx.x;
-    const int chunk = blockIdx.x, group = blockIdx.y;
+    const int chunk = blockIdx.x, group = blockIdx.y, seg = blockIdx.z;
     const int lane = tid % P.wl, slice = tid / P.wl;
     const int w = group * P.wl + lane;
     const bool valid = slice < P.slices && w < P.n_walkers;
 
+    // Segments (blockIdx.z): independent star ranges with their own walkers, e.g. the radial bins of
+    // bin/run.py:179-190 / bin/run_tests.py:81-97 fitted in one launch.  One segment = whole shard.
+    const long long seg_first = P.seg_begin ? P.seg_begin[seg] : 0;
+    const long long seg_stars = P.seg_begin ? P.seg_begin[seg + 1] - seg_first : P.n_stars;
+    const long long seg_offset = P.seg_begin ? P.seg_packed[seg] : 0;     // 16-star aligned position in the columns
+    const int n_tiles = (int)((seg_stars + tile - 1) / tile);
+    const int n_chunks = max(1, (n_tiles + P.tiles_per_chunk - 1) / P.tiles_per_chunk);
+    const int n_super = (n_chunks + P.super - 1) / P.super;
+    if (chunk >= n_chunks) return;          // the grid is sized for the largest segment
+
     const int t_begin = chunk * P.tiles_per_chunk;
-    const int t_end = min(P.n_tiles, t_begin + P.tiles_per_chunk);
+    const int t_end = min(n_tiles, t_begin + P.tiles_per_chunk);
     const int n_my_tiles = max(0, t_end - t_begin);
 
     if (tid == 0) {
@@ -465,7 +487,7 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     const uint32_t stage_bytes = (uint32_t)tile * (NC * 8u + (ICOL ? 4u : 0u));
     auto issue = [&](int k) {   // tid 0 only
         const int stage = k % kStages;
-        const size_t off = (size_t)(t_begin + k) * tile;
+        const size_t off = (size_t)seg_offset + (size_t)(t_begin + k) * tile;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&bars[stage], stage_bytes);
 #pragma unroll
@@ -478,7 +500,7 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
 
     Walker W;
     W.prior_ok = 0;
-    if (valid) load_walker<ROT, FREE, BG>(P, w, W);
+    if (valid) load_walker<ROT, FREE, BG>(P, seg * P.n_walkers + w, W);
     // a walker outside its box prior is never evaluated by the reference (runner.py:303-306)
     const bool active = valid && (W.prior_ok || !P.apply_prior);
 
@@ -490,7 +512,7 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
         if (tid == 0 && k + 1 < n_my_tiles) issue(k + 1);
         mbar_wait(&bars[stage], (uint32_t)(k / kStages) & 1u);
         const long long first = (long long)(t_begin + k) * tile;
-        const int n = (int)min((long long)tile, P.n_stars - first);
+        const int n = (int)min((long long)tile, seg_stars - first);
         if (active) {
             const double *c = sd + (size_t)stage * NC * TS;
             const int32_t *ci = si + (size_t)stage * TS;
@@ -535,16 +557,16 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     if (valid && slice == 0) {
         double s = red[lane];
         for (int j = 1; j < P.slices; ++j) s += red[j * P.wl + lane];
-        P.partials[(size_t)chunk * P.n_walkers + w] = s;
+        P.partials[((size_t)seg * P.n_chunks + chunk) * P.n_walkers + w] = s;
     }
 
     // ---- chunks -> result, two levels, both in index order (independent of CTA scheduling) ------
     // level 1: the last CTA of a super-chunk (P.super consecutive chunks) adds their partials;
     // level 2: the last super-chunk to finish adds the super-chunk sums and writes the result.
-    unsigned int *cnt = P.counters + (size_t)group * (P.n_super + 1);
+    unsigned int *cnt = P.counters + ((size_t)seg * P.n_groups + group) * (P.n_super + 1);
     const int sup = chunk / P.super;
     const int c_begin = sup * P.super;
-    const int c_end = min(P.n_chunks, c_begin + P.super);
+    const int c_end = min(n_chunks, c_begin + P.super);
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -557,15 +579,16 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     if (valid && slice == 0) {
         double s = 0.0;
 #pragma unroll 4
-        for (int cidx = c_begin; cidx < c_end; ++cidx) s += __ldcg(&P.partials[(size_t)cidx * P.n_walkers + w]);
-        P.partials2[(size_t)sup * P.n_walkers + w] = s;
+        for (int cidx = c_begin; cidx < c_end; ++cidx)
+            s += __ldcg(&P.partials[((size_t)seg * P.n_chunks + cidx) * P.n_walkers + w]);
+        P.partials2[((size_t)seg * P.n_super + sup) * P.n_walkers + w] = s;
     }
     if (tid == 0) cnt[sup] = 0u;
     __threadfence();
     __syncthreads();
     if (tid == 0) {
         const unsigned int ticket = atomicAdd(&cnt[P.n_super], 1u);
-        s_last = (ticket == (unsigned int)P.n_super - 1u);
+        s_last = (ticket == (unsigned int)n_super - 1u);
     }
     __syncthreads();
     if (!s_last) return;
@@ -573,10 +596,10 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     if (valid && slice == 0) {
         double s = 0.0;
 #pragma unroll 4
-        for (int k = 0; k < P.n_super; ++k) s += __ldcg(&P.partials2[(size_t)k * P.n_walkers + w]);
-        if (MATH == MCD_MATH_FAST) s = fma((double)P.n_stars, -0.5 * kLn2Pi, s);
+        for (int k = 0; k < n_super; ++k) s += __ldcg(&P.partials2[((size_t)seg * P.n_super + k) * P.n_walkers + w]);
+        if (MATH == MCD_MATH_FAST) s = fma((double)seg_stars, -0.5 * kLn2Pi, s);
         const bool rejected = P.apply_prior && !W.prior_ok;
-        P.out[w] = rejected ? __longlong_as_double(0xfff0000000000000LL) : s;
+        P.out[(size_t)seg * P.n_walkers + w] = rejected ? __longlong_as_double(0xfff0000000000000LL) : s;
     }
     if (tid == 0) cnt[P.n_super] = 0u;
 }
@@ -612,7 +635,7 @@ template <int ROT, int FREE, int BG, int MATH>
 static cudaError_t launch_one(const LaunchParams &p, cudaStream_t stream) {
     constexpr int NC = total_columns(ROT, FREE, BG);
     const size_t smem = (size_t)kStages * kMaxTile * (NC * 8 + (has_icol(BG, MATH) ? 4 : 0));
-    dim3 grid((unsigned)p.n_chunks, (unsigned)p.n_groups);
+    dim3 grid((unsigned)p.n_chunks, (unsigned)p.n_groups, (unsigned)std::max(1, p.n_segments));
     lnlike_kernel<ROT, FREE, BG, MATH><<<grid, kBlock, smem, stream>>>(p);
     return cudaGetLastError();
 }

@@ -45,27 +45,31 @@ __device__ __forceinline__ void uniforms(uint64_t seed, uint32_t step, uint32_t 
 }
 
 struct Ensemble {
-    int n_walkers, n_theta, n0, n1;     // n0 = first ("red") half, n1 = second
+    int n_segments;                     // independent ensembles advanced together (radial bins)
+    int n_walkers, n_theta, n0, n1;     // per segment; n0 = first ("red") half, n1 = second
     uint64_t seed;
     double a;
-    double *pos;          // [W][P]
-    double *lnp;          // [W]
-    double *q;            // [n0][P] proposals of the current half
-    double *lnp_q;        // [n0]
-    double *logz;         // [n0]
-    int *perm;            // [W]: perm[0:n0] = red walkers, perm[n0:W] = blue
-    long long *n_accepted;   // [W]
+    double *pos;          // [S][W][P]
+    double *lnp;          // [S][W]
+    double *q;            // [S][n0][P] proposals of the current half
+    double *lnp_q;        // [S][n0]
+    double *logz;         // [S][n0]
+    int *perm;            // [S][W]: perm[s][0:n0] = red walkers of segment s, perm[s][n0:W] = blue
+    long long *n_accepted;   // [S][W]
     unsigned int *step;      // [2]: global step counter, step inside the current run() chunk
-    double *chain;        // [chunk][W][P] or nullptr
-    double *chain_lnp;    // [chunk][W]
+    double *chain;        // [chunk][S][W][P] or nullptr
+    double *chain_lnp;    // [chunk][S][W]
 };
 
-// random red/blue partition: rank of a random key (emcee: inds = arange(W) % 2; shuffle(inds))
+// random red/blue partition: rank of a random key (emcee: inds = arange(W) % 2; shuffle(inds));
+// one CTA per segment
 __global__ void split_kernel(Ensemble E) {
     extern __shared__ unsigned long long keys[];
     const uint32_t step = E.step[0];
+    const int seg = blockIdx.x;
     for (int w = threadIdx.x; w < E.n_walkers; w += blockDim.x) {
-        const uint4 r = philox4x32_10(make_uint4(step, 2u, (uint32_t)w, 7u), make_uint2((uint32_t)E.seed, (uint32_t)(E.seed >> 32)));
+        const uint4 r = philox4x32_10(make_uint4(step, 2u, (uint32_t)(seg * E.n_walkers + w), 7u),
+                                      make_uint2((uint32_t)E.seed, (uint32_t)(E.seed >> 32)));
         keys[w] = (((unsigned long long)r.x << 32) | r.y);
     }
     __syncthreads();
@@ -76,41 +80,45 @@ __global__ void split_kernel(Ensemble E) {
             const unsigned long long other = keys[o];
             rank += (other < mine) || (other == mine && o < w);
         }
-        E.perm[rank] = w;
+        E.perm[(size_t)seg * E.n_walkers + rank] = w;
     }
 }
 
 __global__ void propose_kernel(Ensemble E, int half) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int ns = half == 0 ? E.n0 : E.n1;
     const int nc = E.n_walkers - ns;
-    if (k >= ns) return;
-    const int *active = E.perm + (half == 0 ? 0 : E.n0);
-    const int *other = E.perm + (half == 0 ? E.n0 : 0);
+    if (idx >= ns * E.n_segments) return;
+    const int seg = idx / ns, k = idx % ns;
+    const int *perm = E.perm + (size_t)seg * E.n_walkers;
+    const int *active = perm + (half == 0 ? 0 : E.n0);
+    const int *other = perm + (half == 0 ? E.n0 : 0);
     double u0, u1;
-    uniforms(E.seed, E.step[0], (uint32_t)half, (uint32_t)k, 0u, u0, u1);
+    uniforms(E.seed, E.step[0], (uint32_t)half, (uint32_t)(seg * E.n_walkers + k), 0u, u0, u1);
     const double t = (E.a - 1.0) * u0 + 1.0;
     const double z = t * t / E.a;
     int j = (int)(u1 * nc);
     j = j >= nc ? nc - 1 : j;
-    const double *s = E.pos + (size_t)active[k] * E.n_theta;
-    const double *c = E.pos + (size_t)other[j] * E.n_theta;
-    double *q = E.q + (size_t)k * E.n_theta;
+    const double *base = E.pos + (size_t)seg * E.n_walkers * E.n_theta;
+    const double *s = base + (size_t)active[k] * E.n_theta;
+    const double *c = base + (size_t)other[j] * E.n_theta;
+    double *q = E.q + ((size_t)seg * ns + k) * E.n_theta;
     for (int p = 0; p < E.n_theta; ++p) q[p] = c[p] - (c[p] - s[p]) * z;
-    E.logz[k] = (E.n_theta - 1.0) * log(z);
+    E.logz[(size_t)seg * ns + k] = (E.n_theta - 1.0) * log(z);
 }
 
 __global__ void accept_kernel(Ensemble E, int half) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int ns = half == 0 ? E.n0 : E.n1;
-    if (k >= ns) return;
-    const int w = E.perm[(half == 0 ? 0 : E.n0) + k];
+    if (idx >= ns * E.n_segments) return;
+    const int seg = idx / ns, k = idx % ns;
+    const int w = seg * E.n_walkers + E.perm[(size_t)seg * E.n_walkers + (half == 0 ? 0 : E.n0) + k];
     double u0, u1;
-    uniforms(E.seed, E.step[0], (uint32_t)half, (uint32_t)k, 1u, u0, u1);
-    const double new_lp = E.lnp_q[k];
-    const double diff = E.logz[k] + new_lp - E.lnp[w];
+    uniforms(E.seed, E.step[0], (uint32_t)half, (uint32_t)(seg * E.n_walkers + k), 1u, u0, u1);
+    const double new_lp = E.lnp_q[(size_t)seg * ns + k];
+    const double diff = E.logz[(size_t)seg * ns + k] + new_lp - E.lnp[w];
     if (diff > log(u0)) {     // NaN never accepts
-        const double *q = E.q + (size_t)k * E.n_theta;
+        const double *q = E.q + ((size_t)seg * ns + k) * E.n_theta;
         double *s = E.pos + (size_t)w * E.n_theta;
         for (int p = 0; p < E.n_theta; ++p) s[p] = q[p];
         E.lnp[w] = new_lp;
@@ -121,10 +129,11 @@ __global__ void accept_kernel(Ensemble E, int half) {
 __global__ void store_kernel(Ensemble E) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int local = E.step[1];
-    const int total = E.n_walkers * E.n_theta;
+    const int rows = E.n_walkers * E.n_segments;
+    const int total = rows * E.n_theta;
     if (E.chain) {
         if (i < total) E.chain[(size_t)local * total + i] = E.pos[i];
-        if (i < E.n_walkers) E.chain_lnp[(size_t)local * E.n_walkers + i] = E.lnp[i];
+        if (i < rows) E.chain_lnp[(size_t)local * rows + i] = E.lnp[i];
     }
 }
 
@@ -185,6 +194,7 @@ extern "C" int mcd_ensemble_create(mcd_handle *h, int32_t n_walkers, uint64_t se
     e->h = h;
     e->device = handle_device(h);
     Ensemble &E = e->E;
+    E.n_segments = std::max(1, (int)info.n_segments);
     E.n_walkers = n_walkers;
     E.n_theta = info.n_theta;
     E.n0 = (n_walkers + 1) / 2;
@@ -192,17 +202,18 @@ extern "C" int mcd_ensemble_create(mcd_handle *h, int32_t n_walkers, uint64_t se
     E.seed = seed;
     E.a = stretch_a;
     const size_t P = (size_t)std::max(1, E.n_theta);
+    const size_t S = (size_t)E.n_segments;
     bool ok = cudaSetDevice(e->device) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaMalloc(&E.pos, sizeof(double) * n_walkers * P) == cudaSuccess;
-    ok = ok && cudaMalloc(&E.lnp, sizeof(double) * n_walkers) == cudaSuccess;
-    ok = ok && cudaMalloc(&E.q, sizeof(double) * E.n0 * P) == cudaSuccess;
-    ok = ok && cudaMalloc(&E.lnp_q, sizeof(double) * E.n0) == cudaSuccess;
-    ok = ok && cudaMalloc(&E.logz, sizeof(double) * E.n0) == cudaSuccess;
-    ok = ok && cudaMalloc(&E.perm, sizeof(int) * n_walkers) == cudaSuccess;
-    ok = ok && cudaMalloc(&E.n_accepted, sizeof(long long) * n_walkers) == cudaSuccess;
+    ok = ok && cudaMalloc(&E.pos, sizeof(double) * S * n_walkers * P) == cudaSuccess;
+    ok = ok && cudaMalloc(&E.lnp, sizeof(double) * S * n_walkers) == cudaSuccess;
+    ok = ok && cudaMalloc(&E.q, sizeof(double) * S * E.n0 * P) == cudaSuccess;
+    ok = ok && cudaMalloc(&E.lnp_q, sizeof(double) * S * E.n0) == cudaSuccess;
+    ok = ok && cudaMalloc(&E.logz, sizeof(double) * S * E.n0) == cudaSuccess;
+    ok = ok && cudaMalloc(&E.perm, sizeof(int) * S * n_walkers) == cudaSuccess;
+    ok = ok && cudaMalloc(&E.n_accepted, sizeof(long long) * S * n_walkers) == cudaSuccess;
     ok = ok && cudaMalloc(&E.step, sizeof(unsigned int) * 2) == cudaSuccess;
-    ok = ok && cudaMemset(E.n_accepted, 0, sizeof(long long) * n_walkers) == cudaSuccess;
+    ok = ok && cudaMemset(E.n_accepted, 0, sizeof(long long) * S * n_walkers) == cudaSuccess;
     ok = ok && cudaMemset(E.step, 0, sizeof(unsigned int) * 2) == cudaSuccess;
     if (!ok) {
         free_ensemble(e);
@@ -216,7 +227,8 @@ extern "C" int mcd_ensemble_set_state(mcd_ensemble *e, const double *pos_host) {
     if (!e || !pos_host) return -1;
     ENS_CUDA(cudaSetDevice(e->device));
     Ensemble &E = e->E;
-    ENS_CUDA(cudaMemcpyAsync(E.pos, pos_host, sizeof(double) * E.n_walkers * E.n_theta, cudaMemcpyHostToDevice, e->stream));
+    ENS_CUDA(cudaMemcpyAsync(E.pos, pos_host, sizeof(double) * E.n_segments * E.n_walkers * E.n_theta, cudaMemcpyHostToDevice,
+                             e->stream));
     if (int rc = launch_ensemble(e->h, E.pos, E.n_walkers, E.lnp, 1, e->stream)) return rc;
     ENS_CUDA(cudaStreamSynchronize(e->stream));
     e->have_state = true;
@@ -227,15 +239,16 @@ static int enqueue_step(mcd_ensemble *e) {
     Ensemble &E = e->E;
     const int threads = 128;
     const int split_threads = std::min(1024, ((E.n_walkers + 31) / 32) * 32);
-    split_kernel<<<1, split_threads, sizeof(unsigned long long) * E.n_walkers, e->stream>>>(E);
+    split_kernel<<<E.n_segments, split_threads, sizeof(unsigned long long) * E.n_walkers, e->stream>>>(E);
     for (int half = 0; half < 2; ++half) {
         const int ns = half == 0 ? E.n0 : E.n1;
         if (ns == 0) continue;
-        propose_kernel<<<(ns + threads - 1) / threads, threads, 0, e->stream>>>(E, half);
+        const int all = ns * E.n_segments;
+        propose_kernel<<<(all + threads - 1) / threads, threads, 0, e->stream>>>(E, half);
         if (int rc = launch_ensemble(e->h, E.q, ns, E.lnp_q, 1, e->stream)) return rc;
-        accept_kernel<<<(ns + threads - 1) / threads, threads, 0, e->stream>>>(E, half);
+        accept_kernel<<<(all + threads - 1) / threads, threads, 0, e->stream>>>(E, half);
     }
-    const int total = E.n_walkers * std::max(1, E.n_theta);
+    const int total = E.n_segments * E.n_walkers * std::max(1, E.n_theta);
     store_kernel<<<(total + 255) / 256, 256, 0, e->stream>>>(E);
     advance_kernel<<<1, 1, 0, e->stream>>>(E);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
@@ -276,7 +289,8 @@ extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_
     ENS_CUDA(cudaSetDevice(e->device));
     Ensemble &E = e->E;
     const size_t P = (size_t)std::max(1, E.n_theta);
-    const size_t per_step = (size_t)E.n_walkers * P;
+    const size_t rows = (size_t)E.n_walkers * E.n_segments;
+    const size_t per_step = rows * P;
     const bool store = chain_host != nullptr || lnprob_host != nullptr;
     // chain chunks of at most 256 MiB on the device
     size_t chunk = std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, n_steps), ((size_t)256 << 20) / (per_step * 8)));
@@ -286,7 +300,7 @@ extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_
         E.chain = E.chain_lnp = nullptr;
         e->chain_cap_steps = 0;
         ENS_CUDA(cudaMalloc(&E.chain, sizeof(double) * chunk * per_step));
-        ENS_CUDA(cudaMalloc(&E.chain_lnp, sizeof(double) * chunk * E.n_walkers));
+        ENS_CUDA(cudaMalloc(&E.chain_lnp, sizeof(double) * chunk * rows));
         e->chain_cap_steps = chunk;
         if (e->exec) {   // pointers baked into the graph changed
             cudaGraphExecDestroy(e->exec);
@@ -315,15 +329,15 @@ extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_
         if (rc) break;
         if (chain_host && cudaMemcpyAsync(chain_host + (size_t)done * per_step, E.chain, sizeof(double) * todo * per_step,
                                           cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) rc = -2;
-        if (lnprob_host && cudaMemcpyAsync(lnprob_host + (size_t)done * E.n_walkers, E.chain_lnp,
-                                           sizeof(double) * todo * E.n_walkers, cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) rc = -2;
+        if (lnprob_host && cudaMemcpyAsync(lnprob_host + (size_t)done * rows, E.chain_lnp, sizeof(double) * todo * rows,
+                                           cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) rc = -2;
         if (cudaStreamSynchronize(e->stream) != cudaSuccess) rc = -2;
         done += todo;
     }
     E.chain = saved_chain;
     E.chain_lnp = saved_lnp;
     if (rc == 0 && n_accepted_host) {
-        if (cudaMemcpy(n_accepted_host, E.n_accepted, sizeof(long long) * E.n_walkers, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -2;
+        if (cudaMemcpy(n_accepted_host, E.n_accepted, sizeof(long long) * rows, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -2;
     }
     if (rc == 0 && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = -2;
     return rc;
@@ -333,7 +347,8 @@ extern "C" int mcd_ensemble_get_state(mcd_ensemble *e, double *pos_host, double 
     if (!e) return -1;
     ENS_CUDA(cudaSetDevice(e->device));
     ENS_CUDA(cudaStreamSynchronize(e->stream));
-    if (pos_host) ENS_CUDA(cudaMemcpy(pos_host, e->E.pos, sizeof(double) * e->E.n_walkers * e->E.n_theta, cudaMemcpyDeviceToHost));
-    if (lnprob_host) ENS_CUDA(cudaMemcpy(lnprob_host, e->E.lnp, sizeof(double) * e->E.n_walkers, cudaMemcpyDeviceToHost));
+    const size_t rows = (size_t)e->E.n_walkers * e->E.n_segments;
+    if (pos_host) ENS_CUDA(cudaMemcpy(pos_host, e->E.pos, sizeof(double) * rows * e->E.n_theta, cudaMemcpyDeviceToHost));
+    if (lnprob_host) ENS_CUDA(cudaMemcpy(lnprob_host, e->E.lnp, sizeof(double) * rows, cudaMemcpyDeviceToHost));
     return 0;
 }

@@ -37,11 +37,14 @@ at::Tensor run(ensemble_fn fn, int64_t handle, const at::Tensor &theta) {
     TORCH_CHECK(mcd_get_info(as_handle(handle), &info) == 0, mcd_last_error());
     TORCH_CHECK(theta.size(1) == info.n_theta, "mcd_b200: theta has ", theta.size(1), " columns, the model has ",
                 info.n_theta, " free parameters");
+    // segmented handles take theta as [segments * walkers, parameters]; the C ABI wants walkers per segment
+    const int64_t segments = info.n_segments > 1 ? info.n_segments : 1;
+    TORCH_CHECK(theta.size(0) % segments == 0, "mcd_b200: theta rows must be a multiple of the ", segments, " segments");
     c10::cuda::CUDAGuard guard(theta.device());
     at::Tensor out = at::empty({theta.size(0)}, theta.options());
     auto stream = c10::cuda::getCurrentCUDAStream(theta.get_device());
-    const int rc = fn(as_handle(handle), theta.data_ptr<double>(), (int32_t)theta.size(0), out.data_ptr<double>(),
-                      stream.stream());
+    const int rc = fn(as_handle(handle), theta.data_ptr<double>(), (int32_t)(theta.size(0) / segments),
+                      out.data_ptr<double>(), stream.stream());
     TORCH_CHECK(rc == 0, "mcd_b200: ", mcd_last_error());
     return out;
 }

@@ -52,7 +52,7 @@ def routing_signature(parameters, model_parameters):
 
 
 def build_descriptor(parameters, model_parameters, rotation, background, columns, math_mode=_native.MATH_FAST,
-                     device=0, n_stars_total=0):
+                     device=0, n_stars_total=0, segment_offsets=None):
     """Fill a ``PackDesc`` from a ``Parameters`` object.
 
     Parameters
@@ -124,6 +124,11 @@ def build_descriptor(parameters, model_parameters, rotation, background, columns
         keep.append(arr)
         setattr(desc, name, _native.as_double_ptr(arr))
     desc.n_stars = 0 if n is None else n
+    if segment_offsets is not None:
+        offsets = np.ascontiguousarray(segment_offsets, dtype=np.int64)
+        keep.append(offsets)
+        desc.n_segments = offsets.size - 1
+        desc.segment_offsets = offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
     return desc, keep
 
 
@@ -137,6 +142,7 @@ class PackedModel(object):
         self._handle = handle
         self.n_theta = int(desc.n_theta)
         self.n_stars = int(desc.n_stars)
+        self.n_segments = max(1, int(desc.n_segments))
         self.device = int(desc.device)
         del keep
 
@@ -156,23 +162,29 @@ class PackedModel(object):
         return {name: getattr(info, name) for name, _ in _native.Info._fields_}
 
     def _theta(self, theta):
+        """[n_walkers, n_theta], or [n_segments, n_walkers, n_theta] for a segmented handle."""
         theta = np.ascontiguousarray(theta, dtype=np.float64)
+        if self.n_segments > 1:
+            if theta.ndim != 3 or theta.shape[0] != self.n_segments or theta.shape[2] != self.n_theta:
+                raise ValueError('theta must have shape ({0}, n_walkers, {1}), got {2}'.format(
+                    self.n_segments, self.n_theta, theta.shape))
+            return theta, theta.shape[1], theta.shape[:2]
         if theta.ndim != 2 or theta.shape[1] != self.n_theta:
             raise ValueError('theta must have shape (n_walkers, {0}), got {1}'.format(self.n_theta, theta.shape))
-        return theta
+        return theta, theta.shape[0], theta.shape[:1]
 
     def lnprob(self, theta):
         """Host buffers in, host buffer out: copy, one kernel launch, copy, synchronise."""
-        theta = self._theta(theta)
-        out = np.empty(theta.shape[0], dtype=np.float64)
-        _native.check(self._lib.mcd_lnprob(self.handle, _native.as_double_ptr(theta), theta.shape[0],
+        theta, n_walkers, shape = self._theta(theta)
+        out = np.empty(shape, dtype=np.float64)
+        _native.check(self._lib.mcd_lnprob(self.handle, _native.as_double_ptr(theta), n_walkers,
                                            _native.as_double_ptr(out)))
         return out
 
     def lnlike(self, theta):
-        theta = self._theta(theta)
-        out = np.empty(theta.shape[0], dtype=np.float64)
-        _native.check(self._lib.mcd_lnlike(self.handle, _native.as_double_ptr(theta), theta.shape[0],
+        theta, n_walkers, shape = self._theta(theta)
+        out = np.empty(shape, dtype=np.float64)
+        _native.check(self._lib.mcd_lnlike(self.handle, _native.as_double_ptr(theta), n_walkers,
                                            _native.as_double_ptr(out)))
         return out
 

@@ -151,6 +151,9 @@ class DeviceEnsembleSampler(object):
             raise ValueError('ndim does not match the packed model')
         self.nwalkers = int(nwalkers)
         self.ndim = int(ndim)
+        #: independent ensembles advanced together (one per segment of a segmented handle); state
+        #: arrays then carry a leading segment axis
+        self.nsegments = int(getattr(packed, 'n_segments', 1))
         self._packed = packed          # keeps the handle alive
         self._lib = _native.load_library()
         if seed is None:
@@ -164,23 +167,30 @@ class DeviceEnsembleSampler(object):
         self.iteration = 0
         self._chain = []
         self._lnprob = []
-        self.naccepted = np.zeros(self.nwalkers, dtype=np.int64)
+        self.naccepted = np.zeros(self._rows_shape, dtype=np.int64)
         self._have_state = False
 
     @property
+    def _rows_shape(self):
+        return (self.nsegments, self.nwalkers) if self.nsegments > 1 else (self.nwalkers,)
+
+    @property
     def chain(self):
+        """[nwalkers, nsteps, ndim] like emcee's; [nsegments, nwalkers, nsteps, ndim] when segmented."""
         if not self._chain:
-            return np.empty((self.nwalkers, 0, self.ndim))
-        return np.swapaxes(np.concatenate(self._chain, axis=0), 0, 1)
+            return np.empty(self._rows_shape + (0, self.ndim))
+        steps_first = np.concatenate(self._chain, axis=0)              # [steps, (S,) W, P]
+        return np.moveaxis(steps_first, 0, -2)
 
     @property
     def lnprobability(self):
         if not self._lnprob:
-            return np.empty((self.nwalkers, 0))
-        return np.concatenate(self._lnprob, axis=0).T
+            return np.empty(self._rows_shape + (0,))
+        return np.moveaxis(np.concatenate(self._lnprob, axis=0), 0, -1)
 
     def get_chain(self, discard=0, flat=False):
-        chain = np.concatenate(self._chain, axis=0)[discard:] if self._chain else np.empty((0, self.nwalkers, self.ndim))
+        chain = np.concatenate(self._chain, axis=0)[discard:] if self._chain else np.empty(
+            (0,) + self._rows_shape + (self.ndim,))
         return chain.reshape((-1, self.ndim)) if flat else chain
 
     @property
@@ -191,15 +201,15 @@ class DeviceEnsembleSampler(object):
         nsteps = int(nsteps)
         if initial_state is not None and (not self._have_state or not np.array_equal(initial_state, self._last_pos)):
             pos = _native.contiguous(initial_state)
-            if pos.shape != (self.nwalkers, self.ndim):
+            if pos.shape != self._rows_shape + (self.ndim,):
                 raise ValueError("incompatible input dimensions {0}".format(pos.shape))
             rc = self._lib.mcd_ensemble_set_state(self._handle, _native.as_double_ptr(pos))
             if rc != 0:
                 raise _native.NativeError('mcd_ensemble_set_state failed with code {0}'.format(rc))
             self._have_state = True
-        chain = np.empty((nsteps, self.nwalkers, self.ndim), dtype=np.float64) if store else None
-        lnp = np.empty((nsteps, self.nwalkers), dtype=np.float64) if store else None
-        nacc = np.zeros(self.nwalkers, dtype=np.int64)
+        chain = np.empty((nsteps,) + self._rows_shape + (self.ndim,), dtype=np.float64) if store else None
+        lnp = np.empty((nsteps,) + self._rows_shape, dtype=np.float64) if store else None
+        nacc = np.zeros(self._rows_shape, dtype=np.int64)
         rc = self._lib.mcd_ensemble_run(
             self._handle, nsteps, _native.as_double_ptr(chain) if store else None,
             _native.as_double_ptr(lnp) if store else None, nacc.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
@@ -210,8 +220,8 @@ class DeviceEnsembleSampler(object):
         if store:
             self._chain.append(chain)
             self._lnprob.append(lnp)
-        pos = np.empty((self.nwalkers, self.ndim), dtype=np.float64)
-        last = np.empty(self.nwalkers, dtype=np.float64)
+        pos = np.empty(self._rows_shape + (self.ndim,), dtype=np.float64)
+        last = np.empty(self._rows_shape, dtype=np.float64)
         rc = self._lib.mcd_ensemble_get_state(self._handle, _native.as_double_ptr(pos), _native.as_double_ptr(last))
         if rc != 0:
             raise _native.NativeError('mcd_ensemble_get_state failed with code {0}'.format(rc))

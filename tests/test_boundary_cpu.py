@@ -36,10 +36,10 @@ def test_struct_layout_matches_header():
     header = open(os.path.join(ROOT, 'include', 'mcd_b200.h')).read()
     body = header[header.index('typedef struct mcd_pack_desc {'):header.index('} mcd_pack_desc;')]
     body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
-    fields = re.findall(r'\b(?:int32_t|int64_t|double|const double \*)\s*\*?(\w+)(?:\[\w+\])?;', body)
+    fields = re.findall(r'\b(?:int32_t|int64_t|double|const double \*|const int64_t \*)\s*\*?(\w+)(?:\[\w+\])?;', body)
     assert fields == [name for name, _ in _native.PackDesc._fields_]
     import ctypes
-    assert ctypes.sizeof(_native.PackDesc) == 16 + 8 + 7 * 8 + 11 * 4 + 4 + 2 * 11 * 8 + 2 * 16 * 8 + 8 + 8
+    assert ctypes.sizeof(_native.PackDesc) == 16 + 8 + 7 * 8 + 11 * 4 + 4 + 2 * 11 * 8 + 2 * 16 * 8 + 8 + 8 + 8 + 8
 
 
 @pytest.mark.skipif(__import__('torch').cuda.is_available(), reason='checks the no-GPU failure mode')

@@ -1,0 +1,77 @@
+"""Batched per-radial-bin fits: one segmented launch against one model object per bin
+(bin/run_tests.py:81-97, bin/run.py:179-190)."""
+import numpy as np
+import pytest
+
+from mcmc_dynamics_b200 import synthetic
+from mcmc_dynamics_b200.analysis import ConstantFit, ModelFit, RadialBinsFit
+from oracle import harness
+
+pytestmark = pytest.mark.gpu
+
+
+def _binned(n_stars=2500, seed=4, cls=ConstantFit):
+    data, truth = synthetic.mock_cluster(n_stars, seed=seed)
+    data.make_radial_bins(truth['ra_center'], truth['dec_center'], nstars=50, dlogr=0.1)
+    fit = RadialBinsFit(data, model_class=cls)
+    fit.parameters['ra_center'].set(value=truth['ra_center'], fixed=True)
+    fit.parameters['dec_center'].set(value=truth['dec_center'], fixed=True)
+    return fit, truth
+
+
+@pytest.mark.parametrize('cls', [ConstantFit, ModelFit])
+def test_segmented_lnprob_equals_per_bin_models_and_oracle(cls):
+    fit, truth = _binned(cls=cls)
+    assert fit.n_bins >= 5 and fit.bin_sizes.sum() == 2500
+    n_walkers = 24
+    theta = np.stack([synthetic.initial_ball(truth, fit.fitted_parameters, n_walkers, seed=10 + b, scale=0.3)
+                      for b in range(fit.n_bins)])
+    theta[2, 5, fit.fitted_parameters.index('sigma_max')] = -1.0       # one rejected walker in one bin
+    got = fit.lnprob(theta)
+    assert got.shape == (fit.n_bins, n_walkers)
+    assert got[2, 5] == -np.inf
+    for b in range(fit.n_bins):
+        single = fit.bin_model(b)
+        assert single.n_data == fit.bin_sizes[b]
+        alone = single.lnprob(theta[b])
+        assert harness.relative_error(got[b], alone) < 1e-13          # same kernel, same arithmetic per star
+        want = harness.oracle_for(single).lnprob_many(theta[b])
+        assert harness.relative_error(got[b], want) < 1e-9
+    ll = fit.lnlike(theta)
+    assert np.isfinite(ll[2, 5]) and np.allclose(np.delete(ll.ravel(), 2 * n_walkers + 5),
+                                                 np.delete(got.ravel(), 2 * n_walkers + 5))
+
+
+def test_binned_device_sampler_matches_independent_runs_statistically():
+    fit, truth = _binned(n_stars=1500, seed=9)
+    fit.parameters['sigma_max'].set(initials='rng.lognormal(mean=2.3, sigma=0.3, size=n)')
+    fit.parameters['v_maxx'].set(initials='rng.normal(loc=0, scale=3, size=n)')
+    fit.parameters['v_maxy'].set(initials='rng.normal(loc=0, scale=3, size=n)')
+    n_walkers, n_steps, n_burn = 32, 400, 150
+    engine = fit(n_walkers=n_walkers, n_steps=n_steps, seed=5)
+    chain = engine.chain
+    assert chain.shape == (fit.n_bins, n_walkers, n_steps, fit.n_fitted_parameters)
+    lnp = engine.lnprobability
+    assert lnp.shape == (fit.n_bins, n_walkers, n_steps) and np.all(np.isfinite(lnp))
+    # stored lnprob belongs to the stored positions, bin by bin
+    again = fit.lnprob(np.ascontiguousarray(chain[:, :, -1, :]))
+    assert np.allclose(again, lnp[:, :, -1], rtol=1e-12, atol=0)
+    # each bin's posterior agrees with a stand-alone device run of that bin
+    j = fit.fitted_parameters.index('sigma_max')
+    for b in (0, fit.n_bins - 1):
+        single = fit.bin_model(b)
+        pos = chain[b, :, 0, :]
+        alone = single(n_walkers=n_walkers, n_steps=n_steps, pos=np.ascontiguousarray(pos), sampler='device', seed=77,
+                       prefix=None)
+        a = chain[b, :, n_burn:, j].ravel()
+        c = alone.chain[:, n_burn:, j].ravel()
+        assert abs(np.median(a) - np.median(c)) < 0.5 * 0.5 * (a.std() + c.std())
+        assert 0.6 < a.std() / c.std() < 1.6
+    frac = engine.naccepted / float(n_steps)
+    assert frac.shape == (fit.n_bins, n_walkers) and 0.15 < frac.mean() < 0.9
+
+
+def test_bins_need_labels_and_plain_models():
+    data, truth = synthetic.mock_cluster(100, seed=1)
+    with pytest.raises(IOError):
+        RadialBinsFit(data)

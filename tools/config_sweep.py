@@ -143,6 +143,42 @@ def run(name, model, truth, n_walkers, quick):
         n_walkers * n / cpu_terms))
 
 
+def bins_workflow(n_stars=3000, n_walkers=100, n_steps=100):
+    """The per-radial-bin workflow of bin/run_tests.py:81-97 (100 walkers x 100 steps per bin):
+    all bins in one segmented launch vs one device-sampler run per bin vs the host stretch move."""
+    from mcmc_dynamics_b200.analysis import RadialBinsFit
+    data, truth = synthetic.mock_cluster(n_stars, seed=6)
+    data.make_radial_bins(truth['ra_center'], truth['dec_center'], nstars=50, dlogr=0.1)
+    fit = RadialBinsFit(data, model_class=ConstantFit)
+    fix_centre(fit, truth)
+    for name, expr in (('sigma_max', 'rng.lognormal(mean=2.3, sigma=0.5, size=n)'),
+                       ('v_maxx', 'rng.normal(loc=0, scale=3, size=n)'), ('v_maxy', 'rng.normal(loc=0, scale=3, size=n)')):
+        fit.parameters[name].set(initials=expr)
+    pos = fit.get_initials(n_walkers)
+    fit(n_walkers=n_walkers, n_steps=5, pos=pos, seed=1)                 # warm-up: pack, graph
+    t0 = time.perf_counter()
+    fit(n_walkers=n_walkers, n_steps=n_steps, pos=pos, seed=1)
+    batched = time.perf_counter() - t0
+    models = [fit.bin_model(b) for b in range(fit.n_bins)]
+    for m in models:
+        m.pack()
+    t0 = time.perf_counter()
+    for b, m in enumerate(models):
+        m(n_walkers=n_walkers, n_steps=n_steps, pos=pos[b], sampler='device', seed=1, prefix=None)
+    per_bin_device = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for b, m in enumerate(models[:4]):
+        m(n_walkers=n_walkers, n_steps=n_steps, pos=pos[b], sampler='host', seed=1, prefix=None)
+    per_bin_host = (time.perf_counter() - t0) * fit.n_bins / 4.0
+    oracle = harness.oracle_for(models[0])
+    t0 = time.perf_counter()
+    oracle.lnprob_many(pos[0])
+    cpu = (time.perf_counter() - t0) * n_steps * fit.n_bins          # W lnprob calls per step, per bin
+    return ('radial bins: %d stars in %d bins, %d walkers x %d steps per bin | batched device %.3f s | '
+            'one device sampler per bin %.3f s | host stretch move per bin %.3f s | CPU oracle (1 process, '
+            'extrapolated) %.1f s' % (n_stars, fit.n_bins, n_walkers, n_steps, batched, per_bin_device, per_bin_host, cpu))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default=None)
@@ -164,6 +200,9 @@ def main():
         lines.append(line)
         model.pack().close()
         del model
+    line = bins_workflow()
+    print(line, flush=True)
+    lines += ['', line]
     text = '\n'.join(lines) + '\n'
     if args.out:
         with open(args.out, 'w') as f:
