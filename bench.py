@@ -196,6 +196,10 @@ class ClockSampler(object):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+def half_guess(args):
+    return args.walkers // 2
+
+
 def gpu_run(args):
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -231,7 +235,9 @@ def gpu_run(args):
         model.parameters['ra_center'].set(value=truth['ra_center'])
         model.parameters['dec_center'].set(value=truth['dec_center'])
     packed = model.pack()
-    like = sharded.ShardedLikelihood(model)
+    # MCD_COLLECTIVE=nccl forces kernel + NCCL all_reduce; default: the reduction fused into the kernel
+    like = sharded.ShardedLikelihood(model, fused=os.environ.get('MCD_COLLECTIVE', 'fused') != 'nccl',
+                                     max_walkers=max(1024, half_guess(args)))
     info = packed.info()
 
     half = args.walkers // 2
@@ -296,7 +302,7 @@ def gpu_run(args):
         if flush:
             flush_buf.fill_(k & 0xff)
         k_starts[k].record()
-        packed.lnprob_partial_tensor(halves_dev[k & 1])
+        like.lnprob_tensor(halves_dev[k & 1]) if like.fused else packed.lnprob_partial_tensor(halves_dev[k & 1])
         k_stops[k].record()
     torch.cuda.synchronize(device)
     kernel_ms = float(np.mean([s.elapsed_time(e) for s, e in zip(k_starts, k_stops)]))
@@ -354,8 +360,9 @@ def gpu_run(args):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': dict(workload_config(args), stars_per_gpu=n_shard, collective='nccl all_reduce(sum) of %d f64 per call'
-                       % half if world > 1 else 'none',
+        'config': dict(workload_config(args), stars_per_gpu=n_shard, collective=('in-kernel one-shot all-reduce of %d f64 per call over NVLink peer memory '
+                                   '(symmetric memory), fused into the likelihood kernel' % half if like.fused else
+                                   'nccl all_reduce(sum) of %d f64 per call' % half) if world > 1 else 'none',
                        l2='flushed between steps (512 MiB write)' if flush else 'inputs larger than L2 (%.0f MB per GPU)'
                        % (bytes_resident / 1e6)),
         'steps_per_s': 1e3 / ms_per_step,
@@ -363,7 +370,8 @@ def gpu_run(args):
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(2 * half * info['n_theta'] * 8),
                 'd2h_bytes_per_step': int(2 * half * 8), 'ms_per_step': 1e3 * e2e_s / args.steps,
                 'api': 'ModelFit.lnprob(theta ndarray) -> C ABI mcd_lnprob (host buffers)' if world == 1 else
-                       'ShardedLikelihood.lnprob(theta ndarray): pinned H2D, shard kernel, NCCL all_reduce, D2H'},
+                       'ShardedLikelihood.lnprob(theta ndarray): pinned H2D, shard kernel with %s, D2H' % (
+                           'fused cross-GPU reduction' if like.fused else 'NCCL all_reduce')},
         'gpu_launches': int(launches),
         'clocks': clock_summary,
         'roofline': {

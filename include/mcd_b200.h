@@ -144,6 +144,17 @@ int mcd_lnprob_device(mcd_handle *h, const double *theta_dev, int32_t n_walkers,
 int mcd_lnprob_partial_device(mcd_handle *h, const double *theta_dev, int32_t n_walkers, double *out_dev,
                               void *stream);
 
+/* Fused compute + collective for star-sharded catalogues: the likelihood kernel itself exchanges the
+ * per-walker shard sums over NVLink peer mappings (symmetric memory) and adds them in rank order, so
+ * no separate all-reduce is launched and every GPU returns bit-identical values.
+ *   mcd_exchange_bytes : size of the per-rank exchange buffer (zero-filled by the caller)
+ *   mcd_exchange_attach: peer_buffers[r] = address, valid in THIS process, of rank r's buffer
+ *   mcd_lnprob_allreduce_device: lnprob of the whole catalogue on every rank; a collective call --
+ *       every rank must make the same sequence of calls with the same theta and n_walkers. */
+int mcd_exchange_bytes(int32_t world, int32_t max_walkers, int64_t *bytes_out);
+int mcd_exchange_attach(mcd_handle *h, int32_t rank, int32_t world, const uint64_t *peer_buffers, int32_t max_walkers);
+int mcd_lnprob_allreduce_device(mcd_handle *h, const double *theta_dev, int32_t n_walkers, double *out_dev, void *stream);
+
 /* Per-star log-likelihood of ONE parameter vector (`no_sum=True`, model.py:565,620-621). */
 int mcd_lnlike_per_star(mcd_handle *h, const double *theta_host, double *out_host /* [N] */);
 int mcd_lnlike_per_star_device(mcd_handle *h, const double *theta_dev, double *out_dev, void *stream);

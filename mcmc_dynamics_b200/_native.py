@@ -70,6 +70,10 @@ SYMBOLS = {
     'mcd_lnprob': (ctypes.c_int, [_vp, _c_double_p, ctypes.c_int32, _c_double_p]),
     'mcd_lnprob_device': (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, _vp]),
     'mcd_lnprob_partial_device': (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, _vp]),
+    'mcd_exchange_bytes': (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, _c_int64_p]),
+    'mcd_exchange_attach': (ctypes.c_int, [_vp, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint64),
+                                           ctypes.c_int32]),
+    'mcd_lnprob_allreduce_device': (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, _vp]),
     'mcd_lnlike_per_star': (ctypes.c_int, [_vp, _c_double_p, _c_double_p]),
     'mcd_lnlike_per_star_device': (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     'mcd_membership_per_star': (ctypes.c_int, [_vp, _c_double_p, _c_double_p]),

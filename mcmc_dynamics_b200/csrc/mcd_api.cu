@@ -58,6 +58,11 @@ struct mcd_handle {
     double *star_dev = nullptr;    // [n] scratch of the per-star entry point
     cudaStream_t stream = nullptr;
     int sm_count = 0, blocks_per_sm = 1;
+    // fused cross-GPU reduction (mcd_exchange_attach)
+    int xchg_world = 0, xchg_rank = 0, xchg_capacity = 0;
+    unsigned long long xchg_epoch = 0;
+    double *xchg_data[kMaxRanks] = {};
+    unsigned long long *xchg_flags[kMaxRanks] = {};
     mcd_info info{};
 };
 
@@ -379,7 +384,7 @@ static void fill_params(const mcd_handle *h, LaunchParams &p) {
 }
 
 static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double *out_dev, int apply_prior,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, bool exchange = false) {
     if (!h) return fail(-1, "null handle");
     if (n_walkers < 0) return fail(-1, "n_walkers < 0");
     if (n_walkers == 0) return 0;
@@ -397,6 +402,20 @@ static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double 
     p.partials = h->partials;
     p.partials2 = h->partials2;
     p.counters = h->counters;
+    if (exchange) {
+        if (h->xchg_world < 2) return fail(-1, "mcd_exchange_attach has not been called on this handle");
+        if (h->n_segments > 1) return fail(-1, "the fused cross-GPU reduction does not support segmented handles");
+        if (n_walkers > h->xchg_capacity) return fail(-1, "n_walkers %d exceeds the exchange capacity %d", n_walkers, h->xchg_capacity);
+        if (p.n_groups > kMaxXchgGroups) return fail(-1, "too many walker groups for the exchange buffer");
+        p.xchg_world = h->xchg_world;
+        p.xchg_rank = h->xchg_rank;
+        p.xchg_capacity = h->xchg_capacity;
+        p.xchg_epoch = ++h->xchg_epoch;
+        for (int r = 0; r < h->xchg_world; ++r) {
+            p.xchg_data[r] = h->xchg_data[r];
+            p.xchg_flags[r] = h->xchg_flags[r];
+        }
+    }
     MCD_CUDA(launch_lnlike(h->var, p, stream));
     h->info.last_grid_x = p.n_chunks;
     h->info.last_grid_y = p.n_groups;
@@ -472,6 +491,40 @@ extern "C" int mcd_lnprob_partial_device(mcd_handle *h, const double *theta_dev,
                                          void *stream) {
     // a shard's lnprob kernel already returns (sum over its stars) or -inf: additive across shards
     return launch(h, theta_dev, n_walkers, out_dev, 1, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------
+// fused cross-GPU reduction over symmetric (peer-mapped) memory
+// ------------------------------------------------------------------------------------------
+static size_t exchange_flag_bytes(int world) { return sizeof(unsigned long long) * 2 * world * kMaxXchgGroups; }
+
+extern "C" int mcd_exchange_bytes(int32_t world, int32_t max_walkers, int64_t *bytes_out) {
+    if (world < 2 || world > kMaxRanks || max_walkers < 1 || !bytes_out) return fail(-1, "bad exchange geometry");
+    *bytes_out = (int64_t)(exchange_flag_bytes(world) + sizeof(double) * 2 * world * (size_t)max_walkers);
+    return 0;
+}
+
+extern "C" int mcd_exchange_attach(mcd_handle *h, int32_t rank, int32_t world, const uint64_t *peer_buffers,
+                                   int32_t max_walkers) {
+    if (!h || !peer_buffers) return fail(-1, "null argument");
+    if (world < 2 || world > kMaxRanks || rank < 0 || rank >= world || max_walkers < 1)
+        return fail(-1, "bad exchange geometry (world %d, rank %d)", world, rank);
+    h->xchg_world = world;
+    h->xchg_rank = rank;
+    h->xchg_capacity = max_walkers;
+    h->xchg_epoch = 0;
+    for (int r = 0; r < world; ++r) {
+        if (!peer_buffers[r]) return fail(-1, "null peer buffer");
+        char *base = reinterpret_cast<char *>(static_cast<uintptr_t>(peer_buffers[r]));
+        h->xchg_flags[r] = reinterpret_cast<unsigned long long *>(base);
+        h->xchg_data[r] = reinterpret_cast<double *>(base + exchange_flag_bytes(world));
+    }
+    return 0;
+}
+
+extern "C" int mcd_lnprob_allreduce_device(mcd_handle *h, const double *theta_dev, int32_t n_walkers, double *out_dev,
+                                           void *stream) {
+    return launch(h, theta_dev, n_walkers, out_dev, 1, static_cast<cudaStream_t>(stream), true);
 }
 
 // ------------------------------------------------------------------------------------------

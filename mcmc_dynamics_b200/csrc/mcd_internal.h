@@ -12,6 +12,8 @@ constexpr int kBlock = 256;        // threads per CTA of the lnlike kernel
 constexpr int kMaxCols = 8;        // packed float64 columns per star
 constexpr int kMaxTile = 256;      // stars per shared-memory stage
 constexpr int kStages = 2;         // TMA bulk-copy stages in flight per CTA
+constexpr int kMaxRanks = 8;        // GPUs of one box that can share a star-sharded catalogue
+constexpr int kMaxXchgGroups = 64;  // walker groups per call of the fused cross-GPU reduction
 constexpr int kSuper = 32;         // chunks per super-chunk of the two-level cross-CTA reduction
 constexpr int kWaves = 8;          // CTA waves a large catalogue is cut into (tail balance)
 constexpr double kDeg2Rad = 0.017453292519943295769236907684886;
@@ -69,6 +71,13 @@ struct LaunchParams {
     double scale[MCD_NPARAM];
     double lower[MCD_MAX_THETA], upper[MCD_MAX_THETA];
     double ra0_deg;
+    // fused cross-GPU reduction (star-sharded catalogues): the CTA that finishes a walker group
+    // publishes this shard's sums into every rank's exchange buffer over NVLink peer mappings, waits
+    // for the other shards' sums and adds them in rank order.  xchg_world <= 1: disabled.
+    int xchg_world, xchg_rank, xchg_capacity;
+    unsigned long long xchg_epoch;                 // call counter, identical on all ranks, starts at 1
+    double *xchg_data[kMaxRanks];                  // rank p's data region  [2][world][capacity]
+    unsigned long long *xchg_flags[kMaxRanks];     // rank p's flag region  [2][world][kMaxXchgGroups]
 };
 
 struct Variant {

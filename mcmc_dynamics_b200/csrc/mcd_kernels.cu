@@ -593,14 +593,54 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    double total = 0.0;
     if (valid && slice == 0) {
         double s = 0.0;
 #pragma unroll 4
         for (int k = 0; k < n_super; ++k) s += __ldcg(&P.partials2[((size_t)seg * P.n_super + k) * P.n_walkers + w]);
         if (MATH == MCD_MATH_FAST) s = fma((double)seg_stars, -0.5 * kLn2Pi, s);
         const bool rejected = P.apply_prior && !W.prior_ok;
-        P.out[(size_t)seg * P.n_walkers + w] = rejected ? __longlong_as_double(0xfff0000000000000LL) : s;
+        total = rejected ? __longlong_as_double(0xfff0000000000000LL) : s;
     }
+    if (P.xchg_world > 1) {
+        // ---- shards -> catalogue: one-shot all-reduce over NVLink peer memory, fused here ------------
+        // Every rank runs this kernel on its shard with the same theta.  data/flags live in symmetric
+        // memory; parity double-buffers consecutive calls (a rank can be at most one call ahead,
+        // because it cannot finish call k+1 before every peer has published call k+1).
+        const int par = (int)(P.xchg_epoch & 1ull);
+        const size_t slot = ((size_t)par * P.xchg_world + P.xchg_rank) * P.xchg_capacity + w;
+        if (valid && slice == 0) {
+            for (int peer = 0; peer < P.xchg_world; ++peer) P.xchg_data[peer][slot] = total;   // st over NVLink
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (tid < P.xchg_world) {
+            // publish: flag[par][my rank][group] on rank `tid` <- epoch (release, system scope)
+            unsigned long long *dst = P.xchg_flags[tid] + ((size_t)par * P.xchg_world + P.xchg_rank) * kMaxXchgGroups + group;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(P.xchg_epoch) : "memory");
+            // wait: flag[par][rank tid][group] in MY buffer == epoch (acquire, system scope)
+            const unsigned long long *src =
+                P.xchg_flags[P.xchg_rank] + ((size_t)par * P.xchg_world + tid) * kMaxXchgGroups + group;
+            unsigned long long seen;
+            const long long t0 = clock64();
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
+                // a peer that never arrives (crashed rank) must not hang the GPU: give up after ~10 s
+                if (clock64() - t0 > 20000000000LL) {
+                    s_last = -1;
+                    break;
+                }
+            } while (seen != P.xchg_epoch);
+        }
+        __syncthreads();
+        if (valid && slice == 0) {
+            double s = s_last == -1 ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
+            for (int r = 0; r < P.xchg_world; ++r)
+                s += __ldcg(&P.xchg_data[P.xchg_rank][((size_t)par * P.xchg_world + r) * P.xchg_capacity + w]);
+            total = s;      // same order on every rank: bit-identical results across the box
+        }
+    }
+    if (valid && slice == 0) P.out[(size_t)seg * P.n_walkers + w] = total;
     if (tid == 0) cnt[P.n_super] = 0u;
 }
 

@@ -7,6 +7,7 @@
 //   torch.ops.mcd_b200.lnprob(handle, theta[W,P] f64 cuda)         -> [W]  Runner.lnprob   (runner.py:288-306)
 //   torch.ops.mcd_b200.lnlike(handle, theta)                       -> [W]  <Model>.lnlike  (constant.py:113-154, model.py:182-223, ...)
 //   torch.ops.mcd_b200.lnprob_partial(handle, theta)               -> [W]  this GPU's star shard; allreduce(sum) gives lnprob
+//   torch.ops.mcd_b200.lnprob_allreduce(handle, theta)             -> [W]  all shards, exchanged inside the kernel over NVLink
 //   torch.ops.mcd_b200.lnlike_per_star(handle, theta[P], n_stars)  -> [N]  lnlike(no_sum=True) (model.py:620-621)
 #include <ATen/ATen.h>
 #include <c10/cuda/CUDAGuard.h>
@@ -55,6 +56,10 @@ at::Tensor lnprob_partial(int64_t handle, const at::Tensor &theta) {
     return run(mcd_lnprob_partial_device, handle, theta);
 }
 
+at::Tensor lnprob_allreduce(int64_t handle, const at::Tensor &theta) {
+    return run(mcd_lnprob_allreduce_device, handle, theta);
+}
+
 at::Tensor lnlike_per_star(int64_t handle, const at::Tensor &theta) {
     check_theta(theta, 1);
     mcd_info info;
@@ -75,6 +80,7 @@ TORCH_LIBRARY(mcd_b200, m) {
     m.def("lnprob(int handle, Tensor theta) -> Tensor");
     m.def("lnlike(int handle, Tensor theta) -> Tensor");
     m.def("lnprob_partial(int handle, Tensor theta) -> Tensor");
+    m.def("lnprob_allreduce(int handle, Tensor theta) -> Tensor");
     m.def("lnlike_per_star(int handle, Tensor theta) -> Tensor");
 }
 
@@ -82,5 +88,6 @@ TORCH_LIBRARY_IMPL(mcd_b200, CUDA, m) {
     m.impl("lnprob", lnprob);
     m.impl("lnlike", lnlike);
     m.impl("lnprob_partial", lnprob_partial);
+    m.impl("lnprob_allreduce", lnprob_allreduce);
     m.impl("lnlike_per_star", lnlike_per_star);
 }

@@ -9,8 +9,20 @@ float64 values, 4 KiB for 512 walkers -- are combined with one ``all_reduce(SUM)
 (``analysis/runner.py:398-403``) at multi-GPU scale.
 
 ``torch.distributed`` is plumbing: process group, NCCL communicator, device tensors.
+
+With ``fused=True`` (default on CUDA) the collective is not a separate launch at all: the last CTA of
+the likelihood kernel publishes the shard's sums into every rank's exchange buffer through NVLink
+peer mappings (torch symmetric memory supplies the mappings), waits for the other shards and adds
+them in rank order (``mcd_lnprob_allreduce_device``).  Every GPU then holds bit-identical values.
 """
+import ctypes
+import logging
+
 import numpy as np
+
+from . import _native
+
+logger = logging.getLogger(__name__)
 
 
 def shard_range(n_stars, rank, world_size):
@@ -36,7 +48,7 @@ class ShardedLikelihood(object):
         collective is issued.
     """
 
-    def __init__(self, model, group=None, device=None):
+    def __init__(self, model, group=None, device=None, fused=True, max_walkers=4096):
         import torch
         import torch.distributed as dist
         self._torch = torch
@@ -48,11 +60,45 @@ class ShardedLikelihood(object):
         self.device = torch.device('cuda', model.device) if device is None else torch.device(device)
         self._pinned_in = None
         self._pinned_out = None
+        self.max_walkers = int(max_walkers)
+        self.fused = False
+        self._exchange = None
+        if fused and self.world_size > 1 and self.device.type == 'cuda':
+            self.fused = self._attach_exchange()
+
+    def _attach_exchange(self):
+        """Allocate the exchange buffer in symmetric memory, map the peers and hand the addresses to
+        the handle.  Any failure (no peer access, old torch) falls back to the NCCL all-reduce."""
+        torch, dist = self._torch, self._dist
+        ok = True
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            lib = _native.load_library()
+            nbytes = ctypes.c_int64()
+            _native.check(lib.mcd_exchange_bytes(self.world_size, self.max_walkers, ctypes.byref(nbytes)))
+            buf = symm_mem.empty((int(nbytes.value) // 8,), dtype=torch.float64, device=self.device)
+            hdl = symm_mem.rendezvous(buf, group=self.group if self.group is not None else dist.group.WORLD)
+            buf.zero_()
+            torch.cuda.synchronize(self.device)
+            ptrs = (ctypes.c_uint64 * self.world_size)(*[int(p) for p in hdl.buffer_ptrs])
+            _native.check(lib.mcd_exchange_attach(self.model.pack().handle, int(hdl.rank), self.world_size, ptrs,
+                                                  self.max_walkers))
+            self._exchange = (buf, hdl)
+        except Exception as exc:                      # noqa: BLE001 -- any failure means "use NCCL"
+            logger.warning('fused cross-GPU reduction unavailable (%s); using the NCCL all-reduce', exc)
+            ok = False
+        # all ranks must agree, and nobody may publish before every buffer is zeroed
+        flag = torch.tensor([1 if ok else 0], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(flag.item())
 
     def lnprob_tensor(self, theta):
         """theta: [n_walkers, n_free] float64 CUDA tensor, identical on every rank.  Returns the
         full-catalogue lnprob on every rank (asynchronous on the current stream)."""
-        partial = self.model.pack().lnprob_partial_tensor(theta)
+        packed = self.model.pack()
+        if self.fused and theta.shape[0] <= self.max_walkers:
+            return _native.load_torch_ops().lnprob_allreduce(packed.handle.value, theta)
+        partial = packed.lnprob_partial_tensor(theta)
         if self.world_size > 1:
             self._dist.all_reduce(partial, op=self._dist.ReduceOp.SUM, group=self.group)
         return partial

@@ -91,3 +91,16 @@ def test_two_rank_gloo_allreduce_matches_whole_catalogue():
     assert sorted(r[0] for r in results) == [0, 1]
     assert all(r[1] for r in results)
     assert sorted(r[2] for r in results) == [500, 501]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs (fused cross-GPU reduction)')
+@pytest.mark.timeout(300)
+def test_fused_in_kernel_allreduce_two_gpus():
+    """tools/check_fused_allreduce.py under torchrun on two GPUs: fused == NCCL == whole catalogue,
+    bit-identical across ranks."""
+    import subprocess
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+           '127.0.0.1', '--master-port', str(_free_port()), os.path.join(ROOT, 'tools', 'check_fused_allreduce.py')]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=280, env=dict(os.environ, N_STARS='100000'))
+    assert res.returncode == 0 and 'RESULT PASS' in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
