@@ -13,7 +13,10 @@
  *     message (thread-local).  No C++ exception crosses the ABI.
  *   - a handle owns all of its device memory.  Host columns passed to
  *     mcd_pack_create() are copied; the caller keeps ownership.
- *   - a handle is thread-compatible: use it from one host thread at a time.
+ *   - a handle is thread-compatible: use it from one host thread at a time.  All launches through
+ *     one handle share its reduction scratch, so they must be ordered: issue them on one stream, or
+ *     synchronise between streams (the host-buffer entry points run on the handle's own stream and
+ *     return synchronised).
  *   - *_device entry points are asynchronous on the given CUDA stream
  *     (a cudaStream_t passed as void*; NULL = the legacy default stream); results
  *     are valid after that stream is synchronised.  Entry points without the
