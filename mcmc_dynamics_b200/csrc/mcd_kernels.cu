@@ -37,6 +37,12 @@
 #ifndef MCD_PAIRS
 #define MCD_PAIRS 2           // star pairs per inner-loop iteration (1 or 2), no-background variants
 #endif
+#ifndef MCD_BG_MIN_BLOCKS
+#define MCD_BG_MIN_BLOCKS 2   // the same two knobs for the background-mixture variants
+#endif
+#ifndef MCD_BG_PAIRS
+#define MCD_BG_PAIRS 1
+#endif
 
 namespace mcd {
 
@@ -230,15 +236,13 @@ struct Accum<MCD_BG_NONE, MCD_MATH_FAST> {
 template <int BG>
 struct Accum<BG, MCD_MATH_FAST> {
     LogProduct num, den;
-    int invalid;
-    __device__ __forceinline__ void reset() { num.reset(); den.reset(); invalid = 0; }
+    __device__ __forceinline__ void reset() { num.reset(); den.reset(); }
     __device__ __forceinline__ void end_group() {
-        num.renormalise();
-        if (BG != MCD_BG_FIXED_PMEMBER) den.renormalise_checked();
+        if (BG != MCD_BG_FIXED_PMEMBER) den.renormalise_checked();     // raw factors: fold every pair
     }
-    __device__ __forceinline__ void end_tile() {}
+    // mul_ext() keeps the factors' mantissas in [1, 2): the product of a tile (<= 256) cannot overflow
+    __device__ __forceinline__ void end_tile() { num.renormalise(); }
     __device__ __forceinline__ double value() {
-        num.bad |= invalid;
         const double n = num.ln();
         return BG == MCD_BG_FIXED_PMEMBER ? n : n - den.ln();
     }
@@ -316,7 +320,7 @@ __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(R
             const double y = ROT == MCD_ROT_RADIAL ? yq * D1 : yq;
             double em;
             int ee;
-            exp_split(-0.5 * (z * z), em, ee, A.invalid);
+            exp_neg_half(z * z, em, ee);
             const double wm = S.c[NB];
             double bm;
             int be;
@@ -332,7 +336,7 @@ __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(R
                 const double yb = fast_rsqrt(nb);
                 const double zb = (v - W.vb) * yb;
                 double ebm;
-                exp_split(-0.5 * (zb * zb), ebm, be, A.invalid);
+                exp_neg_half(zb * zb, ebm, be);
                 bm = W.fb * yb * ebm;
                 A.den.mul_raw(wm + W.fb);
             }
@@ -443,7 +447,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // the lnlike / lnprob kernel
 // ------------------------------------------------------------------------------------------
 template <int ROT, int FREE, int BG, int MATH>
-__global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 2)) lnlike_kernel(const __grid_constant__ LaunchParams P) {
+__global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : MCD_BG_MIN_BLOCKS)) lnlike_kernel(const __grid_constant__ LaunchParams P) {
     constexpr int NC = total_columns(ROT, FREE, BG);
     constexpr bool ICOL = has_icol(BG, MATH);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -520,9 +524,8 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
             // pairs of adjacent stars: (2 slice, 2 slice + 1), then stride 2 slices
             const int n2 = n & ~1;
             int i = 2 * slice;
-            // two pairs per iteration (no-background variants only: the mixtures need the
-            // registers): four independent dependency chains per thread
-            if constexpr (MCD_PAIRS == 2 && BG == MCD_BG_NONE) for (; i + step < n2; i += 2 * step) {
+            // two pairs per iteration: four independent dependency chains per thread
+            if constexpr ((BG == MCD_BG_NONE ? MCD_PAIRS : MCD_BG_PAIRS) == 2) for (; i + step < n2; i += 2 * step) {
                 Star<NC> s0, s1, s2, s3;
                 load_pair<NC, ICOL>(c, ci, TS, i, s0, s1);
                 load_pair<NC, ICOL>(c, ci, TS, i + step, s2, s3);

@@ -100,14 +100,16 @@ struct LogProduct {
         mant *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
     }
 
-    // multiply by m * 2^e with m >= 0; m == 0 marks the whole product as zero
+    // multiply by m * 2^e with m >= 0; m == 0 marks the whole product as zero (lnlike = -inf);
+    // anything else outside the normal positive range (negative, denormal, inf, NaN) marks it bad
     __device__ __forceinline__ void mul_ext(double m, int e) {
         const int hi = __double2hiint(m);
         const bool is_zero = (hi | __double2loint(m)) == 0;
+        const bool out_of_range = (unsigned)(hi - 0x00100000) >= 0x7fe00000u;
         zero |= is_zero;
-        bad |= (!is_zero && (unsigned)(hi - 0x00100000) >= 0x7fe00000u);
-        expo += is_zero ? 0 : (long long)((hi >> 20) - 1023 + e);
-        mant *= is_zero ? 1.0 : __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(m));
+        bad |= (out_of_range && !is_zero);
+        expo += out_of_range ? 0 : (long long)((hi >> 20) - 1023 + e);
+        mant *= out_of_range ? 1.0 : __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(m));
     }
 
     // multiply by x without touching the exponent: the caller renormalises after a small group of
@@ -140,26 +142,29 @@ struct LogProduct {
     }
 };
 
+// Taylor coefficients of 2^f = exp(f ln 2): ln2^k / k!, k = 1..12.  In constant memory so that the
+// FMAs of the polynomial take them as constant-bank operands (no register, no move per use).
+__constant__ double kExp2Coef[12] = {
+    6.93147180559945286e-01, 2.40226506959100694e-01, 5.55041086648215762e-02, 9.61812910762847687e-03,
+    1.33335581464284411e-03, 1.54035303933816099e-04, 1.52527338040598403e-05, 1.32154867901443095e-06,
+    1.01780860092396998e-07, 7.05491162080112333e-09, 4.44553827187081150e-10, 2.56784359934882051e-11};
+
 // 2^f for |f| <= 0.5 (Taylor in f*ln2, degree 12: truncation 2e-16 relative).  Even and odd
 // coefficients are two independent Horner chains in f^2 (depth 8 instead of 12 for one more
 // instruction): the mixture kernels run at low occupancy and are latency-, not issue-bound.
 __device__ __forceinline__ double exp2_frac(double f) {
-    const double c1 = 6.93147180559945286e-01, c2 = 2.40226506959100694e-01, c3 = 5.55041086648215762e-02,
-                 c4 = 9.61812910762847687e-03, c5 = 1.33335581464284411e-03, c6 = 1.54035303933816099e-04,
-                 c7 = 1.52527338040598403e-05, c8 = 1.32154867901443095e-06, c9 = 1.01780860092396998e-07,
-                 c10 = 7.05491162080112333e-09, c11 = 4.44553827187081150e-10, c12 = 2.56784359934882051e-11;
     const double g = f * f;
-    double even = c12, odd = c11;
-    even = fma(even, g, c10);
-    odd = fma(odd, g, c9);
-    even = fma(even, g, c8);
-    odd = fma(odd, g, c7);
-    even = fma(even, g, c6);
-    odd = fma(odd, g, c5);
-    even = fma(even, g, c4);
-    odd = fma(odd, g, c3);
-    even = fma(even, g, c2);
-    odd = fma(odd, g, c1);
+    double even = kExp2Coef[11], odd = kExp2Coef[10];
+    even = fma(even, g, kExp2Coef[9]);
+    odd = fma(odd, g, kExp2Coef[8]);
+    even = fma(even, g, kExp2Coef[7]);
+    odd = fma(odd, g, kExp2Coef[6]);
+    even = fma(even, g, kExp2Coef[5]);
+    odd = fma(odd, g, kExp2Coef[4]);
+    even = fma(even, g, kExp2Coef[3]);
+    odd = fma(odd, g, kExp2Coef[2]);
+    even = fma(even, g, kExp2Coef[1]);
+    odd = fma(odd, g, kExp2Coef[0]);
     even = fma(even, g, 1.0);
     return fma(odd, f, even);
 }
@@ -186,26 +191,35 @@ __device__ __forceinline__ void exp_split(double x, double &mant, int &expo, int
     invalid |= (huge && (thi >= 0 || isnan)) ? 1 : 0;
 }
 
-// a_m*2^a_e + b_m*2^b_e as (mantissa, exponent); both mantissas >= 0.
-// The component with the smaller exponent is scaled down and flushed to zero beyond 2^-1022 --
-// the analogue of exp() underflowing in the reference's max-shifted form (analysis/runner.py:280-286).
-// If the component with the larger exponent has zero weight the other one is returned exactly
-// as long as the reference's exp(l_small - l_big) would not have underflowed (|d| <= 1074).
+// exp(-w/2) = mant * 2^expo for w >= 0 (w = z^2 of a Gaussian), the hot-loop variant of exp_split:
+// no range checks at all.  w is clamped to 2^31 so that the exponent always fits an int32 (a star
+// 46 000 sigma away contributes exp(-1e9), i.e. nothing, either way); NaN propagates into the
+// mantissa and is caught where the mantissa enters the running product.
+__device__ __forceinline__ void exp_neg_half(double w, double &mant, int &expo) {
+    const double kMagic = 6755399441055744.0;            // 1.5 * 2^52
+    const double kC = -0.5 * kLog2e;
+    const double wc = fmin(w, 2147483648.0);
+    const double shifted = fma(wc, kC, kMagic);
+    expo = __double2loint(shifted);
+    const double nf = shifted - kMagic;
+    const double f = fma(wc, kC, -nf);                  // exact product minus the integer part
+    mant = exp2_frac(f);
+}
+
+// 2^d for d <= 0, exactly zero below 2^-960 (integer pipe only)
+__device__ __forceinline__ double pow2_flush(int d) {
+    const int hi = (d + 1023) << 20;
+    return __hiloint2double(d < -960 ? 0 : hi, 0);
+}
+
+// a_m*2^a_e + b_m*2^b_e as (mantissa, exponent); both mantissas >= 0 and O(1).
+// Both terms are scaled to the larger exponent; the smaller one is flushed to zero beyond 2^-960 --
+// the analogue of exp() underflowing in the reference's max-shifted form (analysis/runner.py:280-286:
+// a component more than ~745 nats below the other contributes exactly nothing, and if the other one
+// has zero weight the star's likelihood is 0, i.e. lnlike = -inf).  Branch- and select-free.
 __device__ __forceinline__ void ext_add(double a_m, int a_e, double b_m, int b_e, double &m, int &e) {
-    const int d = a_e - b_e;
-    const bool a_big = d >= 0;
-    const double big = a_big ? a_m : b_m;
-    const double small = a_big ? b_m : a_m;
-    const int k = a_big ? a_e : b_e;
-    const int ks = a_big ? b_e : a_e;
-    const int ad = abs(d);
-    const double sum = fma(small, pow2_nonpos(-ad), big);
-    const bool big_zero = (__double2hiint(big) | __double2loint(big)) == 0;
-    // both components saturated (exp of something below -2^29 ln2): the sum is zero for every purpose
-    const bool vanished = k < -(1 << 29);
-    const bool keep_small = big_zero && ad <= 1074 && ks >= -(1 << 29);
-    e = vanished ? 0 : (keep_small ? ks : k);
-    m = vanished ? 0.0 : (keep_small ? small : sum);
+    e = max(a_e, b_e);
+    m = fma(a_m, pow2_flush(a_e - e), b_m * pow2_flush(b_e - e));
 }
 
 }  // namespace mcd
