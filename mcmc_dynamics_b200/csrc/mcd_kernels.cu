@@ -579,31 +579,38 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    double level1 = 0.0;
     if (valid && slice == 0) {
-        double s = 0.0;
 #pragma unroll 4
         for (int cidx = c_begin; cidx < c_end; ++cidx)
-            s += __ldcg(&P.partials[((size_t)seg * P.n_chunks + cidx) * P.n_walkers + w]);
-        P.partials2[((size_t)seg * P.n_super + sup) * P.n_walkers + w] = s;
+            level1 += __ldcg(&P.partials[((size_t)seg * P.n_chunks + cidx) * P.n_walkers + w]);
     }
     if (tid == 0) cnt[sup] = 0u;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned int ticket = atomicAdd(&cnt[P.n_super], 1u);
-        s_last = (ticket == (unsigned int)n_super - 1u);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
     double total = 0.0;
-    if (valid && slice == 0) {
-        double s = 0.0;
+    if (n_super > 1) {
+        if (valid && slice == 0) P.partials2[((size_t)seg * P.n_super + sup) * P.n_walkers + w] = level1;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int ticket = atomicAdd(&cnt[P.n_super], 1u);
+            s_last = (ticket == (unsigned int)n_super - 1u);
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        if (valid && slice == 0) {
 #pragma unroll 4
-        for (int k = 0; k < n_super; ++k) s += __ldcg(&P.partials2[((size_t)seg * P.n_super + k) * P.n_walkers + w]);
-        if (MATH == MCD_MATH_FAST) s = fma((double)seg_stars, -0.5 * kLn2Pi, s);
+            for (int k = 0; k < n_super; ++k)
+                total += __ldcg(&P.partials2[((size_t)seg * P.n_super + k) * P.n_walkers + w]);
+        }
+        if (tid == 0) cnt[P.n_super] = 0u;
+    } else {
+        total = level1;            // at most P.super chunks: one level is the whole reduction
+    }
+    if (valid && slice == 0) {
+        if (MATH == MCD_MATH_FAST) total = fma((double)seg_stars, -0.5 * kLn2Pi, total);
         const bool rejected = P.apply_prior && !W.prior_ok;
-        total = rejected ? __longlong_as_double(0xfff0000000000000LL) : s;
+        total = rejected ? __longlong_as_double(0xfff0000000000000LL) : total;
     }
     if (P.xchg_world > 1) {
         // ---- shards -> catalogue: one-shot all-reduce over NVLink peer memory, fused here ------------
@@ -644,7 +651,6 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
         }
     }
     if (valid && slice == 0) P.out[(size_t)seg * P.n_walkers + w] = total;
-    if (tid == 0) cnt[P.n_super] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------
