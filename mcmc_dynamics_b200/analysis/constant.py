@@ -35,24 +35,6 @@ class ConstantFit(Runner):
             parameters = Parameters().load(self.parameters_file)
         super(ConstantFit, self).__init__(data=data, parameters=parameters, **kwargs)
 
-    def compute_theta_vmax(self, chain, n_burn, return_samples=False):
-        """(v_max, theta_0) from the (v_maxx, v_maxy) samples (``constant.py:156-214``,
-        ``utils/coordinates/get_amplitude_and_angle.py:10-51``): medians and 16/84 percentiles."""
-        names = self.fitted_parameters
-        samples = np.asarray(chain)[:, n_burn:, :].reshape((-1, len(names)))
-        vx = samples[:, names.index('v_maxx')] if 'v_maxx' in names else np.full(
-            len(samples), self.parameters['v_maxx'].value)
-        vy = samples[:, names.index('v_maxy')] if 'v_maxy' in names else np.full(
-            len(samples), self.parameters['v_maxy'].value)
-        v_max = np.hypot(vx, vy)
-        theta = np.arctan2(vy, vx)
-        # centre the angle distribution on its circular mean before taking percentiles
-        mean = np.arctan2(np.sin(theta).mean(), np.cos(theta).mean())
-        theta = mean + np.angle(np.exp(1j * (theta - mean)))
-        if return_samples:
-            return v_max, theta
-        return {'v_max': np.percentile(v_max, [16, 50, 84]), 'theta_0': np.percentile(theta, [16, 50, 84])}
-
 
 class ConstantFitGB(ConstantFit):
     """Constant fit plus a Gaussian background population (``constant.py:250-374``)."""

@@ -37,6 +37,54 @@ class ModelFit(Runner):
             parameters = Parameters().load(self.parameters_file)
         super(ModelFit, self).__init__(data=data, parameters=parameters, **kwargs)
 
+    def create_profiles(self, chains, n_burn, radii=None, filename=None):
+        """Radial profiles of the rotation amplitude and the velocity dispersion implied by the
+        post-burn-in samples (``model.py:225-317``): median, 1-sigma (16/84 %) and 3-sigma
+        (0.15/99.85 %) limits at every radius.  Host-side post-processing, O(radii x samples).
+
+        `radii` without unit are taken to be in the unit of ``r_peak``; default
+        ``logspace(-1, 2.5, 50)`` arcsec.  Returns a :class:`~mcmc_dynamics_b200.data_reader.Table`.
+        """
+        from ..data_reader import Table
+        chains = np.asarray(chains)
+        samples = {}
+        i = 0
+        for name, parameter in self.parameters.items():
+            if parameter.fixed:
+                samples[name] = np.asarray(parameter.value, dtype=np.float64)
+            else:
+                samples[name] = chains[:, n_burn:, i].flatten()
+                i += 1
+        unit_rp = self.parameters['r_peak'].unit or u.arcsec
+        unit_a = self.parameters['a'].unit or u.arcsec
+        if radii is None:
+            radii = u.Quantity(np.logspace(-1, 2.5, 50), u.arcsec)
+        elif not u.is_quantity(radii) or u.as_quantity(radii).unit.is_unity():
+            radii = u.Quantity(np.asarray(getattr(radii, 'value', radii), dtype=np.float64), unit_rp)
+        radii = u.as_quantity(radii)
+        r_in_rp = radii.to(unit_rp).value[:, np.newaxis]
+        r_in_a = radii.to(unit_a).value[:, np.newaxis]
+        to_kms = (self.parameters['v_maxx'].unit or u.km_s).to(u.km_s)
+        v_max = np.sqrt(samples['v_maxx'] ** 2 + samples['v_maxy'] ** 2) * to_kms
+        v_rot = 2. * (v_max / samples['r_peak']) * r_in_rp / (1. + (r_in_rp / samples['r_peak']) ** 2)
+        sigma_max = samples['sigma_max'] * (self.parameters['sigma_max'].unit or u.km_s).to(u.km_s)
+        sigma = sigma_max / (1. + r_in_a ** 2 / samples['a'] ** 2) ** 0.25
+        if v_rot.ndim == 1:                     # every parameter fixed: one "sample"
+            v_rot, sigma = v_rot[:, np.newaxis], sigma[:, np.newaxis]
+        pct = [50, 16, 84, 0.15, 99.85]
+        pv_rot = np.percentile(v_rot, pct, axis=-1)
+        psigma = np.percentile(sigma, pct, axis=-1)
+        profile = Table()
+        profile['r'] = radii
+        for stem, values in (('v_rot', pv_rot), ('sigma', psigma)):
+            for suffix, row in zip(('', '_lower_1s', '_upper_1s', '_lower_3s', '_upper_3s'), values):
+                profile[stem + suffix] = u.Quantity(row, u.km_s)
+        if filename is not None:
+            names = profile.colnames
+            np.savetxt(filename, np.column_stack([np.asarray(profile[n].value) for n in names]), delimiter=',',
+                       header=','.join(names))
+        return profile
+
 
 class ModelFitGB(ModelFit):
     """Radial-profile fit plus a Gaussian background population (``model.py:338-456``)."""

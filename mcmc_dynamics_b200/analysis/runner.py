@@ -367,6 +367,45 @@ class Runner(object):
         chain = Runner.read_chain(filename)
         return chain[:, -1, :]
 
+    def convert_to_parameters(self, chain, n_burn):
+        """``analysis/runner.py:521-564``: one array of post-burn-in samples per parameter -- sampled
+        ones from the chain, fixed ones repeated, ``expr``-constrained ones evaluated per sample."""
+        chain = np.asarray(chain)
+        pars = {}
+        n_samples = chain.shape[0] * (chain.shape[1] - n_burn)
+        for par in self.parameters:
+            if par in self.fitted_parameters:
+                i = self.fitted_parameters.index(par)
+                pars[par] = chain[:, n_burn:, i].flatten()
+        for fix_par in [p for p in self.parameters if p not in pars]:
+            if self.parameters[fix_par].expr is None:
+                pars[fix_par] = np.full(n_samples, self.parameters[fix_par].value)
+        for dep_par in [p for p in self.parameters if p not in pars]:
+            if self.parameters[dep_par].expr is not None:
+                values = np.zeros(n_samples, dtype=np.float64)
+                deps = [p for p in pars.keys() if p in self.parameters[dep_par]._expr_deps]
+                for n in range(n_samples):
+                    for par in deps:
+                        self.parameters[par].value = pars[par][n]
+                    values[n] = self.parameters[dep_par].value
+                pars[dep_par] = values
+        return pars
+
+    def compute_theta_vmax(self, chain, n_burn, return_samples=False):
+        """Position angle ``theta_0`` and amplitude ``v_max`` of the rotation field from the
+        ``(v_maxx, v_maxy)`` samples (``constant.py:156-214``, ``model.py:319-335``,
+        ``utils/coordinates/get_amplitude_and_angle.py:10-51``): median and 16/84 percentiles."""
+        pars = self.convert_to_parameters(chain=chain, n_burn=n_burn)
+        results, v_max, _theta = get_amplitude_and_angle(pars, return_samples=return_samples)
+        if results is None:
+            logger.error('Could not recover paramaters of rotation field in {}.compute_theta_vmax().'.format(
+                self.__class__.__name__))
+            return None
+        results.units['v_max'] = self.units['v_maxx']
+        if return_samples:
+            return results, v_max, _theta, pars['sigma_max']
+        return results
+
     def compute_percentiles(self, chain, n_burn, pct=None):
         """``analysis/runner.py:566-613``: the requested percentiles (default 16, 50, 84) of the
         post-burn-in samples of every fitted parameter, shape ``[len(pct), n_fitted]``."""
@@ -402,6 +441,40 @@ class Runner(object):
         median = self.compute_percentiles(chain, n_burn=n_burn, pct=[50])[0]
         self.compute_bestfit_values(chain, n_burn)          # the reference updates parameter values here
         return self.pack().membership_per_star(median)
+
+
+def get_amplitude_and_angle(pars, return_samples=False):
+    """``utils/coordinates/get_amplitude_and_angle.py:10-51``: complete the triple (theta_0, v_maxx,
+    v_maxy) from whichever two are given, measure angles relative to the direction of the median
+    velocity vector (so that the median sits in the middle of (-pi, pi]), and define ``v_max`` as the
+    component of (v_maxx, v_maxy) along that direction.  Returns ``(BestFit, v_max, theta)``."""
+    pars = dict(pars)
+    if 'theta_0' not in pars and 'v_maxx' in pars and 'v_maxy' in pars:
+        pars['theta_0'] = np.arctan2(pars['v_maxy'], pars['v_maxx'])
+    elif 'v_maxx' not in pars and 'theta_0' in pars and 'v_maxy' in pars:
+        pars['v_maxx'] = pars['v_maxy'] * np.tan(pars['theta_0'])
+    elif 'v_maxy' not in pars and 'theta_0' in pars and 'v_maxx' in pars:
+        pars['v_maxy'] = pars['v_maxx'] / np.tan(pars['theta_0'])
+    for par in ['theta_0', 'v_maxx', 'v_maxy']:
+        if par not in pars:
+            logger.error('Failed to recover parameter {}.'.format(par))
+            return None, None, None
+
+    median_theta = np.arctan2(np.median(pars['v_maxy']), np.median(pars['v_maxx']))
+    _theta = pars['theta_0'] - median_theta
+    _theta = np.where(_theta < -np.pi, _theta + 2 * np.pi, _theta)
+    _theta = np.where(_theta > np.pi, _theta - 2 * np.pi, _theta)
+    v_max = pars['v_maxx'] * np.cos(-median_theta) - pars['v_maxy'] * np.sin(-median_theta)
+
+    columns = {}
+    for name, values in (('v_max', v_max), ('theta_0', _theta)):
+        p = np.percentile(values, [16, 50, 84])
+        columns[name] = [p[1], p[2] - p[1], p[1] - p[0]]
+    columns['theta_0'][0] += median_theta
+    results = BestFit({k: tuple(v) for k, v in columns.items()}, {'v_max': None, 'theta_0': u.rad})
+    if return_samples:
+        return results, v_max, _theta
+    return results, None, None
 
 
 class BestFit(object):

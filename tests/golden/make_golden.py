@@ -241,6 +241,55 @@ def main():
     g = R.Gaussian(5.0 * u.km / u.s, 55.0 * u.km / u.s)
     extras['gaussian'] = {'mean': 5.0, 'sigma': 55.0, 'lnlike': [float(x) for x in np.asarray(g(v, verr).value)]}
 
+    # ---- the callers either side of the path: radial binning and chain post-processing -------------
+    post = {}
+    binning = []
+    for nstars, dlogr in ((50, 0.1), (30, 0.2), (200, 0.05)):
+        cb, tb, _ = catalogue(700, seed=41)
+        rd = reader(cb)
+        rd.make_radial_bins(tb['ra_center'] * u.deg, tb['dec_center'] * u.deg, nstars=nstars, dlogr=dlogr)
+        binning.append({'n_stars': 700, 'seed': 41, 'nstars': nstars, 'dlogr': dlogr,
+                        'labels': [int(x) for x in np.asarray(rd.data['bin'])]})
+    post['make_radial_bins'] = binning
+    # a synthetic "chain" [walkers, steps, parameters] for a ConstantFit with v_sys fixed
+    rng = np.random.default_rng(77)
+    cb, tb, _ = catalogue(60, seed=42)
+    cf = R.ConstantFit(reader(cb))
+    cf.parameters['ra_center'].set(value=u.Quantity(tb['ra_center'], u.deg), fixed=True)
+    cf.parameters['dec_center'].set(value=u.Quantity(tb['dec_center'], u.deg), fixed=True)
+    cf.parameters['v_sys'].set(value=u.Quantity(1.5, u.km / u.s), fixed=True)
+    names = cf.fitted_parameters                         # sigma_max, v_maxx, v_maxy
+    chain = np.stack([8.0 + rng.normal(0, 0.7, (12, 40)), -3.0 + rng.normal(0, 1.2, (12, 40)),
+                      -0.4 + rng.normal(0, 1.0, (12, 40))], axis=2)
+    pct = cf.compute_percentiles(chain, n_burn=10)
+    best = cf.compute_bestfit_values(chain, n_burn=10)
+    conv = cf.convert_to_parameters(chain, n_burn=10)
+    res = cf.compute_theta_vmax(chain, n_burn=10)
+
+    def _val(x):
+        return float(getattr(x, 'value', x))
+    post['chain_case'] = {
+        'fitted_parameters': names, 'chain': chain.tolist(), 'n_burn': 10,
+        'percentiles': np.asarray(pct).tolist(),
+        'bestfit': {n_: [_val(best.loc[row][n_]) for row in ('median', 'uperr', 'loerr')] for n_ in names},
+        'convert_to_parameters': {k: [float(x) for x in np.asarray(getattr(v_, 'value', v_))[:5]] for k, v_ in conv.items()},
+        'convert_sizes': {k: int(np.size(v_)) for k, v_ in conv.items()},
+        'theta_vmax': {n_: [_val(res.loc[row][n_]) for row in ('median', 'uperr', 'loerr')] for n_ in ('v_max', 'theta_0')},
+    }
+
+    # ModelFit.create_profiles on a synthetic chain (model.py:225-317)
+    mfp = R.ModelFit(reader(cb))
+    mfp.parameters['ra_center'].set(value=u.Quantity(tb['ra_center'], u.deg), fixed=True)
+    mfp.parameters['dec_center'].set(value=u.Quantity(tb['dec_center'], u.deg), fixed=True)
+    mnames = mfp.fitted_parameters              # v_sys, sigma_max, a, v_maxx, v_maxy, r_peak
+    centre = {'v_sys': 0.2, 'sigma_max': 9.0, 'a': 35.0, 'v_maxx': 2.5, 'v_maxy': -3.0, 'r_peak': 70.0}
+    mchain = np.stack([centre[n_] * (1.0 + 0.05 * rng.standard_normal((10, 30))) for n_ in mnames], axis=2)
+    prof = mfp.create_profiles(mchain, n_burn=5, radii=u.Quantity([1.0, 10.0, 60.0, 200.0], u.arcsec))
+    post['create_profiles'] = {
+        'fitted_parameters': mnames, 'chain': mchain.tolist(), 'n_burn': 5, 'radii_arcsec': [1.0, 10.0, 60.0, 200.0],
+        'columns': {name: [float(x) for x in np.asarray(getattr(col, 'value', col))] for name, col in prof.columns.items()},
+    }
+
     # default parameter tables as the reference's Parameters class loads them
     tables = {}
     for cls_name in ('ConstantFit', 'ConstantFitGB', 'ModelFit', 'ModelFitGB', 'ModelFitConstantBackground'):
@@ -248,7 +297,7 @@ def main():
         tables[cls_name] = [[name, float(p.value), None if p.unit is None else str(p.unit), bool(p.fixed),
                              float(p.min), float(p.max), p.initials] for name, p in pars.items()]
     doc = {'generator': 'tests/golden/make_golden.py', 'reference': 'skamann/mcmc-dynamics (files listed in the generator)',
-           'cases': cases, 'extras': extras, 'default_parameters': tables}
+           'cases': cases, 'extras': extras, 'default_parameters': tables, 'post': post}
     with open(OUT, 'w') as f:
         json.dump(doc, f)
     print('wrote', OUT, os.path.getsize(OUT), 'bytes')

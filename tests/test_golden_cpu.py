@@ -80,3 +80,69 @@ def test_default_parameter_tables_as_loaded_by_the_reference():
             assert o.min == lo == p.min and o.max == hi == p.max
             assert (unit or '').replace(' ', '') == (o.unit or '') == ('' if p.unit is None else str(p.unit).replace(' ', ''))
             assert p.initials == initials
+
+
+# ---------------------------------------------------------------------------------------------
+# the callers either side of the path: radial binning and chain post-processing
+# ---------------------------------------------------------------------------------------------
+def test_make_radial_bins_matches_reference():
+    from mcmc_dynamics_b200 import synthetic
+    for case in GOLDEN['post']['make_radial_bins']:
+        data, truth = synthetic.mock_cluster(case['n_stars'], seed=case['seed'])
+        data.make_radial_bins(truth['ra_center'], truth['dec_center'], nstars=case['nstars'], dlogr=case['dlogr'])
+        got = np.asarray(getattr(data.data['bin'], 'value', data.data['bin'])).astype(int)
+        assert np.array_equal(got, case['labels']), (case['nstars'], case['dlogr'])
+        sub = data.fetch_radial_bin(0)
+        assert sub.sample_size == case['labels'].count(0)
+
+
+def test_chain_post_processing_matches_reference():
+    from mcmc_dynamics_b200 import synthetic
+    from mcmc_dynamics_b200.analysis import ConstantFit
+    c = GOLDEN['post']['chain_case']
+    data, truth = synthetic.mock_cluster(60, seed=42)
+    cf = ConstantFit(data)
+    cf.parameters['ra_center'].set(value=truth['ra_center'], fixed=True)
+    cf.parameters['dec_center'].set(value=truth['dec_center'], fixed=True)
+    cf.parameters['v_sys'].set(value=1.5, fixed=True)
+    assert cf.fitted_parameters == c['fitted_parameters']
+    chain = np.asarray(c['chain'])
+    assert np.allclose(cf.compute_percentiles(chain, n_burn=c['n_burn']), c['percentiles'], rtol=1e-14, atol=0)
+    best = cf.compute_bestfit_values(chain, n_burn=c['n_burn'])
+    for name, rows in c['bestfit'].items():
+        got = [float(getattr(best.loc[r][name], 'value', best.loc[r][name])) for r in ('median', 'uperr', 'loerr')]
+        assert np.allclose(got, rows, rtol=1e-13, atol=1e-15)
+        assert cf.parameters[name].value == pytest.approx(rows[0])      # medians become the current values
+    conv = cf.convert_to_parameters(chain, n_burn=c['n_burn'])
+    assert {k: int(np.size(v)) for k, v in conv.items()} == c['convert_sizes']
+    for name, head in c['convert_to_parameters'].items():
+        assert np.allclose(np.asarray(conv[name])[:5], head, rtol=1e-14, atol=0)
+    res = cf.compute_theta_vmax(chain, n_burn=c['n_burn'])
+    for name, rows in c['theta_vmax'].items():
+        got = [float(getattr(res.loc[r][name], 'value', res.loc[r][name])) for r in ('median', 'uperr', 'loerr')]
+        assert np.allclose(got, rows, rtol=1e-12, atol=1e-14), name
+    res2, v_max, theta, sig = cf.compute_theta_vmax(chain, n_burn=c['n_burn'], return_samples=True)
+    assert v_max.shape == theta.shape == sig.shape == (12 * 30,)
+
+
+def test_create_profiles_matches_reference(tmp_path):
+    from mcmc_dynamics_b200 import synthetic
+    from mcmc_dynamics_b200 import units as u
+    from mcmc_dynamics_b200.analysis import ModelFit
+    c = GOLDEN['post']['create_profiles']
+    data, truth = synthetic.mock_cluster(60, seed=42)
+    mf = ModelFit(data)
+    mf.parameters['ra_center'].set(value=truth['ra_center'], fixed=True)
+    mf.parameters['dec_center'].set(value=truth['dec_center'], fixed=True)
+    assert mf.fitted_parameters == c['fitted_parameters']
+    out = str(tmp_path / 'profile.csv')
+    prof = mf.create_profiles(np.asarray(c['chain']), n_burn=c['n_burn'], radii=u.Quantity(c['radii_arcsec'], u.arcsec),
+                              filename=out)
+    assert prof.colnames == list(c['columns'])
+    for name, want in c['columns'].items():
+        assert np.allclose(np.asarray(prof[name].value), want, rtol=1e-12, atol=0), name
+    # radii without unit are in the unit of r_peak (arcsec)
+    prof2 = mf.create_profiles(np.asarray(c['chain']), n_burn=c['n_burn'], radii=c['radii_arcsec'])
+    assert np.allclose(np.asarray(prof2['sigma'].value), c['columns']['sigma'], rtol=1e-12)
+    assert np.loadtxt(out, delimiter=',').shape == (4, 11)
+    assert len(mf.create_profiles(np.asarray(c['chain']), n_burn=c['n_burn'])) == 50
