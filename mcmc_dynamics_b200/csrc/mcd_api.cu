@@ -170,6 +170,8 @@ extern "C" void mcd_destroy(mcd_handle *h) {
 static int setup_segments(mcd_handle *h, const mcd_pack_desc *desc) {
     const int S = desc->n_segments;
     if (!desc->segment_offsets) return fail(-1, "n_segments > 1 needs segment_offsets");
+    if (desc->background != MCD_BG_NONE) return fail(-1, "segmented handles support the models without background component");
+    if (S > 65535) return fail(-1, "at most 65535 segments per handle");
     std::vector<long long> begin(S + 1), packed(S);
     long long pos = 0, longest = 0;
     for (int s = 0; s <= S; ++s) begin[s] = desc->segment_offsets[s];
@@ -177,6 +179,7 @@ static int setup_segments(mcd_handle *h, const mcd_pack_desc *desc) {
     for (int s = 0; s < S; ++s) {
         const long long count = begin[s + 1] - begin[s];
         if (count < 0) return fail(-1, "segment_offsets must be non-decreasing");
+        if (count > 2000000000LL) return fail(-1, "a segment holds at most 2e9 stars");
         packed[s] = pos;
         pos += ((count + 15) / 16) * 16;
         longest = std::max(longest, count);

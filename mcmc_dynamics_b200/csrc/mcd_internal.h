@@ -48,11 +48,11 @@ struct LaunchParams {
     int tile;                 // stars per stage (multiple of 16, <= kMaxTile)
     int n_tiles;              // of the largest segment
     int tiles_per_chunk;
-    int n_chunks;             // gridDim.x: chunks of the largest segment
-    int n_segments;           // gridDim.z: independent (star range, walker set) problems, >= 1
+    int n_chunks;             // chunks of the largest segment (gridDim.x = n_chunks * n_groups)
+    int n_segments;           // gridDim.y: independent (star range, walker set) problems, >= 1
     const long long *seg_begin;   // [n_segments + 1] star index boundaries, or nullptr for one segment
     const long long *seg_packed;  // [n_segments] 16-aligned position of each segment in the packed columns
-    int n_groups;             // gridDim.y
+    int n_groups;             // walker groups
     int n_walkers;
     int wl;                   // walkers per CTA
     int slices;               // star slices per CTA: kBlock / wl

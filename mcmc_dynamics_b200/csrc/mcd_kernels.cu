@@ -10,7 +10,7 @@
 // and the walker-parallel process pool around it (analysis/runner.py:398-403).
 //
 // Work decomposition
-//   grid  = (star chunks, walker groups, segments); a CTA owns `wl` walkers x `slices` star slices
+//   grid  = (star chunks x walker groups, segments); a CTA owns `wl` walkers x `slices` star slices
 //           (wl * slices <= 256 threads) and a contiguous run of star tiles.
 //   tile  = `tile` stars of every packed column, brought into shared memory by TMA bulk copies
 //           (cp.async.bulk, mbarrier completion), double buffered; every thread of the CTA then
@@ -444,9 +444,59 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 // ------------------------------------------------------------------------------------------
+// shards -> catalogue: one-shot all-reduce over NVLink peer memory, fused into the kernel tail
+// ------------------------------------------------------------------------------------------
+// Called by every thread of the CTA that finished a walker group.  Every rank runs the kernel on its
+// shard with the same theta; `owner` threads hold the shard's sum for walker `w`.  data/flags live in
+// symmetric memory; parity double-buffers consecutive calls (a rank can be at most one call ahead,
+// because it cannot finish call k+1 before every peer has published call k+1).  Kept out of line so
+// that this cold path does not take part in the register allocation of the star loop.
+__device__ __noinline__ double exchange_shard_sums(const LaunchParams &P, double total, int w, int group, bool owner,
+                                                   int *timed_out) {
+    const int tid = threadIdx.x;
+    const int par = (int)(P.xchg_epoch & 1ull);
+    const size_t slot = ((size_t)par * P.xchg_world + P.xchg_rank) * P.xchg_capacity + w;
+    if (tid == 0) *timed_out = 0;
+    if (owner) {
+        for (int peer = 0; peer < P.xchg_world; ++peer) P.xchg_data[peer][slot] = total;   // st over NVLink
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (tid < P.xchg_world) {
+        // publish: flag[par][my rank][group] on rank `tid` <- epoch (release, system scope)
+        unsigned long long *dst = P.xchg_flags[tid] + ((size_t)par * P.xchg_world + P.xchg_rank) * kMaxXchgGroups + group;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(P.xchg_epoch) : "memory");
+        // wait: flag[par][rank tid][group] in MY buffer == epoch (acquire, system scope)
+        const unsigned long long *src =
+            P.xchg_flags[P.xchg_rank] + ((size_t)par * P.xchg_world + tid) * kMaxXchgGroups + group;
+        unsigned long long seen;
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
+            // a peer that never arrives (crashed rank) must not hang the GPU: give up after ~10 s
+            if (clock64() - t0 > 20000000000LL) {
+                *timed_out = 1;
+                break;
+            }
+        } while (seen != P.xchg_epoch);
+    }
+    __syncthreads();
+    if (owner) {
+        double s = *timed_out ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
+        for (int r = 0; r < P.xchg_world; ++r)
+            s += __ldcg(&P.xchg_data[P.xchg_rank][((size_t)par * P.xchg_world + r) * P.xchg_capacity + w]);
+        total = s;      // same order on every rank: bit-identical results across the box
+    }
+    return total;
+}
+
+// ------------------------------------------------------------------------------------------
 // the lnlike / lnprob kernel
 // ------------------------------------------------------------------------------------------
-template <int ROT, int FREE, int BG, int MATH>
+// SEG: segmented launch (blockIdx.y = segment).  A separate instantiation so that the single-catalogue
+// kernel carries none of the segment bookkeeping (it changed the star loop's register allocation
+// and cost 2.8 % on the headline workload when it was a run-time branch).
+template <int ROT, int FREE, int BG, int MATH, bool SEG>
 __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : MCD_BG_MIN_BLOCKS)) lnlike_kernel(const __grid_constant__ LaunchParams P) {
     constexpr int NC = total_columns(ROT, FREE, BG);
     constexpr bool ICOL = has_icol(BG, MATH);
@@ -462,18 +512,24 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     int32_t *si = reinterpret_cast<int32_t *>(sd + (size_t)kStages * NC * TS);   // [kStages][TS]
 
     const int tid = threadIdx.x;
-    const int chunk = blockIdx.x, group = blockIdx.y, seg = blockIdx.z;
+    // walker groups of one star chunk are adjacent in launch order: the second group finds the chunk's
+    // tiles in L2 instead of re-reading them from HBM
+    const int chunk = blockIdx.x / P.n_groups, group = blockIdx.x % P.n_groups, seg = SEG ? blockIdx.y : 0;
     const int lane = tid % P.wl, slice = tid / P.wl;
     const int w = group * P.wl + lane;
     const bool valid = slice < P.slices && w < P.n_walkers;
 
-    // Segments (blockIdx.z): independent star ranges with their own walkers, e.g. the radial bins of
+    // Segments (blockIdx.y): independent star ranges with their own walkers, e.g. the radial bins of
     // bin/run.py:179-190 / bin/run_tests.py:81-97 fitted in one launch.  One segment = whole shard.
-    const long long seg_first = P.seg_begin ? P.seg_begin[seg] : 0;
-    const long long seg_stars = P.seg_begin ? P.seg_begin[seg + 1] - seg_first : P.n_stars;
-    const long long seg_offset = P.seg_begin ? P.seg_packed[seg] : 0;     // 16-star aligned position in the columns
-    const int n_tiles = (int)((seg_stars + tile - 1) / tile);
-    const int n_chunks = max(1, (n_tiles + P.tiles_per_chunk - 1) / P.tiles_per_chunk);
+    long long seg_stars = P.n_stars, seg_offset = 0;
+    int n_tiles = P.n_tiles, n_chunks = P.n_chunks;
+    if constexpr (SEG) {                                // segment sizes fit 32 bits (checked at pack time)
+        const int count = (int)(P.seg_begin[seg + 1] - P.seg_begin[seg]);
+        seg_stars = count;
+        seg_offset = P.seg_packed[seg];                 // 16-star aligned position in the packed columns
+        n_tiles = (count + tile - 1) / tile;
+        n_chunks = max(1, (n_tiles + P.tiles_per_chunk - 1) / P.tiles_per_chunk);
+    }
     const int n_super = (n_chunks + P.super - 1) / P.super;
     if (chunk >= n_chunks) return;          // the grid is sized for the largest segment
 
@@ -612,44 +668,7 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
         const bool rejected = P.apply_prior && !W.prior_ok;
         total = rejected ? __longlong_as_double(0xfff0000000000000LL) : total;
     }
-    if (P.xchg_world > 1) {
-        // ---- shards -> catalogue: one-shot all-reduce over NVLink peer memory, fused here ------------
-        // Every rank runs this kernel on its shard with the same theta.  data/flags live in symmetric
-        // memory; parity double-buffers consecutive calls (a rank can be at most one call ahead,
-        // because it cannot finish call k+1 before every peer has published call k+1).
-        const int par = (int)(P.xchg_epoch & 1ull);
-        const size_t slot = ((size_t)par * P.xchg_world + P.xchg_rank) * P.xchg_capacity + w;
-        if (valid && slice == 0) {
-            for (int peer = 0; peer < P.xchg_world; ++peer) P.xchg_data[peer][slot] = total;   // st over NVLink
-            __threadfence_system();
-        }
-        __syncthreads();
-        if (tid < P.xchg_world) {
-            // publish: flag[par][my rank][group] on rank `tid` <- epoch (release, system scope)
-            unsigned long long *dst = P.xchg_flags[tid] + ((size_t)par * P.xchg_world + P.xchg_rank) * kMaxXchgGroups + group;
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(P.xchg_epoch) : "memory");
-            // wait: flag[par][rank tid][group] in MY buffer == epoch (acquire, system scope)
-            const unsigned long long *src =
-                P.xchg_flags[P.xchg_rank] + ((size_t)par * P.xchg_world + tid) * kMaxXchgGroups + group;
-            unsigned long long seen;
-            const long long t0 = clock64();
-            do {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
-                // a peer that never arrives (crashed rank) must not hang the GPU: give up after ~10 s
-                if (clock64() - t0 > 20000000000LL) {
-                    s_last = -1;
-                    break;
-                }
-            } while (seen != P.xchg_epoch);
-        }
-        __syncthreads();
-        if (valid && slice == 0) {
-            double s = s_last == -1 ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
-            for (int r = 0; r < P.xchg_world; ++r)
-                s += __ldcg(&P.xchg_data[P.xchg_rank][((size_t)par * P.xchg_world + r) * P.xchg_capacity + w]);
-            total = s;      // same order on every rank: bit-identical results across the box
-        }
-    }
+    if (P.xchg_world > 1) total = exchange_shard_sums(P, total, w, group, valid && slice == 0, &s_last);
     if (valid && slice == 0) P.out[(size_t)seg * P.n_walkers + w] = total;
 }
 
@@ -684,8 +703,14 @@ template <int ROT, int FREE, int BG, int MATH>
 static cudaError_t launch_one(const LaunchParams &p, cudaStream_t stream) {
     constexpr int NC = total_columns(ROT, FREE, BG);
     const size_t smem = (size_t)kStages * kMaxTile * (NC * 8 + (has_icol(BG, MATH) ? 4 : 0));
-    dim3 grid((unsigned)p.n_chunks, (unsigned)p.n_groups, (unsigned)std::max(1, p.n_segments));
-    lnlike_kernel<ROT, FREE, BG, MATH><<<grid, kBlock, smem, stream>>>(p);
+    dim3 grid((unsigned)p.n_chunks * (unsigned)p.n_groups, (unsigned)std::max(1, p.n_segments));
+    if (p.seg_begin) {
+        // segmented handles exist for the models without background component (RadialBinsFit)
+        if constexpr (BG == MCD_BG_NONE) lnlike_kernel<ROT, FREE, BG, MATH, true><<<grid, kBlock, smem, stream>>>(p);
+        else return cudaErrorInvalidValue;
+    } else {
+        lnlike_kernel<ROT, FREE, BG, MATH, false><<<grid, kBlock, smem, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 
@@ -694,7 +719,7 @@ static int occupancy_one() {
     constexpr int NC = total_columns(ROT, FREE, BG);
     const size_t smem = (size_t)kStages * kMaxTile * (NC * 8 + (has_icol(BG, MATH) ? 4 : 0));
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lnlike_kernel<ROT, FREE, BG, MATH>, kBlock, smem) !=
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lnlike_kernel<ROT, FREE, BG, MATH, false>, kBlock, smem) !=
         cudaSuccess)
         return 1;
     return n > 0 ? n : 1;
