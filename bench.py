@@ -115,12 +115,30 @@ def cpu_reference_run(args, steps, warmup):
             pool.map(_cpu_one, list(theta))
         elapsed = time.perf_counter() - t0
     value = steps * per_step * n_sample / elapsed
+    # the same sample through the compiled C restatement (oracle/oracle_c.c, OpenMP over walkers):
+    # what the reference's arithmetic costs without NumPy temporaries and the Python interpreter
+    c_port = None
+    try:
+        from oracle import c_port as cport
+        if cport.available():
+            co = cport.COracle(_CPU_ORACLE)
+            co.lnprob_many(theta[:cores])
+            t0 = time.perf_counter()
+            co.lnprob_many(theta)
+            c_all = per_step * n_sample / (time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            co.lnprob_many(theta[:1])
+            c_port = {'value': c_all, 'unit': UNIT, 'threads': cores,
+                      'one_walker_call_value': n_sample / (time.perf_counter() - t0),
+                      'what': 'oracle/oracle_c.c (gcc -O2 -fopenmp), literal C restatement incl. per-call geometry'}
+    except Exception as exc:                                # the C port is optional
+        c_port = {'error': str(exc)}
     return {
         'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
         'sample': '{0} lnprob calls (one walker each, process pool of {1}) over a {2}-star catalogue from the workload generator, '
                   'x{3} steps; NumPy oracle = literal restatement of the reference'.format(per_step, cores, n_sample,
                                                                                            steps),
-        'single_process_value': single, 'ms_per_step': 1e3 * elapsed / steps,
+        'single_process_value': single, 'ms_per_step': 1e3 * elapsed / steps, 'c_port': c_port,
     }
 
 
@@ -412,7 +430,8 @@ def reference_run(args):
         'n_gpus': int(os.environ.get('WORLD_SIZE', str(args.gpus))), 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': res['ms_per_step'], 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args),
-        'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample', 'single_process_value')},
+        'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample', 'single_process_value',
+                                             'c_port')},
         'e2e': {'value': res['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)

@@ -26,6 +26,14 @@ static int fail(int code, const char *fmt, ...) {
     return code;
 }
 
+int mcd::set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
 #define MCD_CUDA(call)                                                                              \
     do {                                                                                            \
         cudaError_t err__ = (call);                                                                 \

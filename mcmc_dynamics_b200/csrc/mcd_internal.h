@@ -101,5 +101,7 @@ int lnlike_blocks_per_sm(const Variant &v);
 int launch_ensemble(mcd_handle *h, const double *theta_dev, int n_walkers, double *out_dev, int apply_prior,
                     cudaStream_t stream);
 int handle_device(const mcd_handle *h);
+// record the thread-local message returned by mcd_last_error() and hand back `code`
+int set_error(int code, const char *fmt, ...);
 
 }  // namespace mcd

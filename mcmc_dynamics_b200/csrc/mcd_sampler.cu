@@ -177,20 +177,23 @@ static void free_ensemble(mcd_ensemble *e) {
 
 extern "C" void mcd_ensemble_destroy(mcd_ensemble *e) { free_ensemble(e); }
 
-#define ENS_CUDA(call)                        \
-    do {                                      \
-        if ((call) != cudaSuccess) return -2; \
+#define ENS_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t err__ = (call);                                                                      \
+        if (err__ != cudaSuccess) return set_error(-2, "%s failed: %s", #call, cudaGetErrorString(err__)); \
     } while (0)
 
 extern "C" int mcd_ensemble_create(mcd_handle *h, int32_t n_walkers, uint64_t seed, double stretch_a, mcd_ensemble **out) {
-    if (!h || !out) return -1;
+    if (!h || !out) return set_error(-1, "null argument");
     *out = nullptr;
     mcd_info info;
     if (mcd_get_info(h, &info) != 0) return -1;
     // emcee: "nwalkers >= 2 * ndim" (RuntimeError otherwise)
-    if (n_walkers < 2 || n_walkers > kMaxWalkers || n_walkers < 2 * info.n_theta || !(stretch_a > 1.0)) return -1;
+    if (n_walkers < 2 || n_walkers > kMaxWalkers || n_walkers < 2 * info.n_theta)
+        return set_error(-1, "n_walkers = %d must be in [max(2, 2 * n_theta = %d), %d]", n_walkers, 2 * info.n_theta, kMaxWalkers);
+    if (!(stretch_a > 1.0)) return set_error(-1, "the stretch scale a must exceed 1");
     mcd_ensemble *e = new (std::nothrow) mcd_ensemble();
-    if (!e) return -4;
+    if (!e) return set_error(-4, "out of host memory");
     e->h = h;
     e->device = handle_device(h);
     Ensemble &E = e->E;
@@ -217,14 +220,14 @@ extern "C" int mcd_ensemble_create(mcd_handle *h, int32_t n_walkers, uint64_t se
     ok = ok && cudaMemset(E.step, 0, sizeof(unsigned int) * 2) == cudaSuccess;
     if (!ok) {
         free_ensemble(e);
-        return -2;
+        return set_error(-2, "allocating the ensemble state failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     *out = e;
     return 0;
 }
 
 extern "C" int mcd_ensemble_set_state(mcd_ensemble *e, const double *pos_host) {
-    if (!e || !pos_host) return -1;
+    if (!e || !pos_host) return set_error(-1, "null argument");
     ENS_CUDA(cudaSetDevice(e->device));
     Ensemble &E = e->E;
     ENS_CUDA(cudaMemcpyAsync(E.pos, pos_host, sizeof(double) * E.n_segments * E.n_walkers * E.n_theta, cudaMemcpyHostToDevice,
@@ -251,7 +254,8 @@ static int enqueue_step(mcd_ensemble *e) {
     const int total = E.n_segments * E.n_walkers * std::max(1, E.n_theta);
     store_kernel<<<(total + 255) / 256, 256, 0, e->stream>>>(E);
     advance_kernel<<<1, 1, 0, e->stream>>>(E);
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    const cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? 0 : set_error(-2, "launching the ensemble step failed: %s", cudaGetErrorString(err));
 }
 
 static int build_graph(mcd_ensemble *e) {
@@ -284,8 +288,8 @@ static int build_graph(mcd_ensemble *e) {
 
 extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_host, double *lnprob_host,
                                 int64_t *n_accepted_host) {
-    if (!e || n_steps < 0) return -1;
-    if (!e->have_state) return -1;
+    if (!e || n_steps < 0) return set_error(-1, "bad argument");
+    if (!e->have_state) return set_error(-1, "mcd_ensemble_set_state has not been called");
     ENS_CUDA(cudaSetDevice(e->device));
     Ensemble &E = e->E;
     const size_t P = (size_t)std::max(1, E.n_theta);

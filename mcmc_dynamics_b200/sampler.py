@@ -162,7 +162,7 @@ class DeviceEnsembleSampler(object):
         rc = self._lib.mcd_ensemble_create(packed.handle, self.nwalkers, ctypes.c_uint64(int(seed)), float(a),
                                            ctypes.byref(handle))
         if rc != 0:
-            raise _native.NativeError('mcd_ensemble_create failed with code {0}'.format(rc))
+            _native.check(rc)
         self._handle = handle
         self.iteration = 0
         self._chain = []
@@ -205,7 +205,7 @@ class DeviceEnsembleSampler(object):
                 raise ValueError("incompatible input dimensions {0}".format(pos.shape))
             rc = self._lib.mcd_ensemble_set_state(self._handle, _native.as_double_ptr(pos))
             if rc != 0:
-                raise _native.NativeError('mcd_ensemble_set_state failed with code {0}'.format(rc))
+                _native.check(rc)
             self._have_state = True
         chain = np.empty((nsteps,) + self._rows_shape + (self.ndim,), dtype=np.float64) if store else None
         lnp = np.empty((nsteps,) + self._rows_shape, dtype=np.float64) if store else None
@@ -214,7 +214,7 @@ class DeviceEnsembleSampler(object):
             self._handle, nsteps, _native.as_double_ptr(chain) if store else None,
             _native.as_double_ptr(lnp) if store else None, nacc.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
         if rc != 0:
-            raise _native.NativeError('mcd_ensemble_run failed with code {0}'.format(rc))
+            _native.check(rc)
         self.naccepted = nacc
         self.iteration += nsteps
         if store:
@@ -224,7 +224,7 @@ class DeviceEnsembleSampler(object):
         last = np.empty(self._rows_shape, dtype=np.float64)
         rc = self._lib.mcd_ensemble_get_state(self._handle, _native.as_double_ptr(pos), _native.as_double_ptr(last))
         if rc != 0:
-            raise _native.NativeError('mcd_ensemble_get_state failed with code {0}'.format(rc))
+            _native.check(rc)
         if np.any(np.isnan(last)):
             raise ValueError("Probability function returned NaN")
         self._last_pos = pos.copy()
