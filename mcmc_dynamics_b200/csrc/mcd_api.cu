@@ -395,12 +395,14 @@ static void fill_params(const mcd_handle *h, LaunchParams &p) {
 }
 
 static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double *out_dev, int apply_prior,
-                  cudaStream_t stream, bool exchange = false) {
+                  cudaStream_t stream, bool exchange = false, const FuseParams *fuse = nullptr) {
     if (!h) return fail(-1, "null handle");
     if (n_walkers < 0) return fail(-1, "n_walkers < 0");
     if (n_walkers == 0) return 0;
-    if (!theta_dev && h->desc.n_theta > 0) return fail(-1, "null theta");
-    if (!out_dev) return fail(-1, "null out");
+    if (!fuse) {
+        if (!theta_dev && h->desc.n_theta > 0) return fail(-1, "null theta");
+        if (!out_dev) return fail(-1, "null out");
+    }
     MCD_CUDA(cudaSetDevice(h->device));
     LaunchParams p{};
     fill_params(h, p);
@@ -413,6 +415,10 @@ static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double 
     p.partials = h->partials;
     p.partials2 = h->partials2;
     p.counters = h->counters;
+    if (fuse) {
+        p.fuse = *fuse;
+        p.fuse.enabled = 1;
+    }
     if (exchange) {
         if (h->xchg_world < 2) return fail(-1, "mcd_exchange_attach has not been called on this handle");
         if (h->n_segments > 1) return fail(-1, "the fused cross-GPU reduction does not support segmented handles");
@@ -483,6 +489,9 @@ static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, dou
 int mcd::launch_ensemble(mcd_handle *h, const double *theta_dev, int n_walkers, double *out_dev, int apply_prior,
                          cudaStream_t stream) {
     return launch(h, theta_dev, n_walkers, out_dev, apply_prior, stream);
+}
+int mcd::launch_ensemble_fused(mcd_handle *h, int n_walkers, const FuseParams &fuse, cudaStream_t stream) {
+    return launch(h, nullptr, n_walkers, nullptr, 1, stream, false, &fuse);
 }
 int mcd::handle_device(const mcd_handle *h) { return h->device; }
 

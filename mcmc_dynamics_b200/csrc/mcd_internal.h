@@ -40,6 +40,23 @@ struct PackParams {
     double ra0_deg;                 // reference right ascension of the free-centre expansion
 };
 
+// Fused ensemble half-step (device-resident sampler): the likelihood kernel draws the stretch-move
+// proposals of the active half itself and its finishing CTA accepts or rejects them in place, so a
+// half-step is ONE launch instead of propose -> lnprob -> accept.
+struct FuseParams {
+    int enabled;
+    int half;                     // 0: red walkers move, 1: blue
+    int n0;                       // size of the red half; LaunchParams::n_walkers is the active half's size
+    int walkers_total;            // W per segment
+    double a;                     // stretch scale
+    unsigned long long seed;
+    double *pos;                  // [S][W][P] current positions, updated in place on acceptance
+    double *lnp;                  // [S][W]
+    const int *perm;              // [S][W] red/blue partition of this step
+    long long *n_accepted;        // [S][W]
+    const unsigned int *step;     // [0]: global step counter (Philox counter word)
+};
+
 // Kernel argument block of one lnlike / lnprob launch (passed by value, __grid_constant__).
 struct LaunchParams {
     const double *cols[kMaxCols];
@@ -78,6 +95,7 @@ struct LaunchParams {
     unsigned long long xchg_epoch;                 // call counter, identical on all ranks, starts at 1
     double *xchg_data[kMaxRanks];                  // rank p's data region  [2][world][capacity]
     unsigned long long *xchg_flags[kMaxRanks];     // rank p's flag region  [2][world][kMaxXchgGroups]
+    FuseParams fuse;
 };
 
 struct Variant {
@@ -100,6 +118,9 @@ int lnlike_blocks_per_sm(const Variant &v);
 // one lnlike (apply_prior = 0) / lnprob (1) launch on `stream`, device pointers (mcd_api.cu)
 int launch_ensemble(mcd_handle *h, const double *theta_dev, int n_walkers, double *out_dev, int apply_prior,
                     cudaStream_t stream);
+// the same with the proposal and the acceptance of an ensemble half-step fused in (theta is drawn in
+// the kernel; n_walkers = size of the active half)
+int launch_ensemble_fused(mcd_handle *h, int n_walkers, const FuseParams &fuse, cudaStream_t stream);
 int handle_device(const mcd_handle *h);
 // record the thread-local message returned by mcd_last_error() and hand back `code`
 int set_error(int code, const char *fmt, ...);

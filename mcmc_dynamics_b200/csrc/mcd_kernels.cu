@@ -26,6 +26,7 @@
 
 #include "mcd_internal.h"
 #include "mcd_math.cuh"
+#include "mcd_rng.cuh"
 
 // tuning knobs (overridable at compile time for A/B runs: -DMCD_MIN_BLOCKS=.. -DMCD_PAIRS=..)
 // Measured on the headline workload (gpurun_out/ab*.log): 6.27e11 terms/s with
@@ -171,10 +172,32 @@ struct Walker {
     int prior_ok;
 };
 
+// stretch-move proposal of active walker k of segment `seg` (emcee RedBlueMove/StretchMove):
+// z = ((a-1) u + 1)^2 / a, q = c_j - (c_j - s) z with c_j drawn uniformly from the other half.
+// Pure function of (seed, step, half, walker): every CTA of the walker and the accepting CTA
+// recompute the same q.  Returns the global walker index (row of pos / lnp) through `row_index`.
+__device__ __forceinline__ double draw_proposal(const LaunchParams &P, int seg, int k, double *q, int &row_index) {
+    const FuseParams &F = P.fuse;
+    const int ns = P.n_walkers, nc = F.walkers_total - ns;
+    const int *perm = F.perm + (size_t)seg * F.walkers_total;
+    const int *active = perm + (F.half == 0 ? 0 : F.n0);
+    const int *other = perm + (F.half == 0 ? F.n0 : 0);
+    double u0, u1;
+    uniforms(F.seed, F.step[0], (uint32_t)F.half, (uint32_t)(seg * F.walkers_total + k), 0u, u0, u1);
+    const double t = (F.a - 1.0) * u0 + 1.0;
+    const double z = t * t / F.a;
+    int j = (int)(u1 * nc);
+    j = j >= nc ? nc - 1 : j;
+    row_index = seg * F.walkers_total + active[k];
+    const double *s = F.pos + (size_t)row_index * P.n_theta;
+    const double *c = F.pos + ((size_t)seg * F.walkers_total + other[j]) * P.n_theta;
+    for (int p = 0; p < P.n_theta; ++p) q[p] = c[p] - (c[p] - s[p]) * z;
+    return z;
+}
+
 template <int ROT, int FREE, int BG>
-__device__ __forceinline__ void load_walker(const LaunchParams &P, int w, Walker &W) {
+__device__ __forceinline__ void load_walker(const LaunchParams &P, const double *row, Walker &W) {
     double par[MCD_NPARAM];
-    const double *row = P.theta + (size_t)w * P.n_theta;
 #pragma unroll
     for (int k = 0; k < MCD_NPARAM; ++k) {
         const int s = P.slot[k];
@@ -443,6 +466,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
+// Ticket of the cross-CTA reductions: one acq_rel read-modify-write at GPU scope.  Together with the
+// bar.sync before (all partials of this CTA are written) and after (the ticket is known) it orders
+// "every earlier CTA's partials" before "the last CTA's reads" -- release/acquire cumulativity --
+// without the sequentially consistent fence + L1 invalidation that __threadfence() costs (about a
+// microsecond each, which is what small catalogues spend most of their kernel time on).  The
+// partials are read with ld.cg (L2), so no L1 line can be stale.
+__device__ __forceinline__ unsigned int take_ticket(unsigned int *counter) {
+    unsigned int ticket;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(counter) : "memory");
+    return ticket;
+}
+
 // ------------------------------------------------------------------------------------------
 // shards -> catalogue: one-shot all-reduce over NVLink peer memory, fused into the kernel tail
 // ------------------------------------------------------------------------------------------
@@ -490,13 +525,31 @@ __device__ __noinline__ double exchange_shard_sums(const LaunchParams &P, double
     return total;
 }
 
+// acceptance of the fused half-step: (P-1) ln z + lnp(q) - lnp(s) > ln u'; NaN never accepts
+__device__ __noinline__ void accept_proposal(const LaunchParams &P, int seg, int k, double lnp_new) {
+    const FuseParams &F = P.fuse;
+    double q[MCD_MAX_THETA];
+    int row;
+    const double z = draw_proposal(P, seg, k, q, row);
+    double u0, u1;
+    uniforms(F.seed, F.step[0], (uint32_t)F.half, (uint32_t)(seg * F.walkers_total + k), 1u, u0, u1);
+    const double diff = (P.n_theta - 1.0) * log(z) + lnp_new - F.lnp[row];
+    if (diff > log(u0)) {
+        double *s = F.pos + (size_t)row * P.n_theta;
+        for (int p = 0; p < P.n_theta; ++p) s[p] = q[p];
+        F.lnp[row] = lnp_new;
+        F.n_accepted[row] += 1;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // the lnlike / lnprob kernel
 // ------------------------------------------------------------------------------------------
 // SEG: segmented launch (blockIdx.y = segment).  A separate instantiation so that the single-catalogue
 // kernel carries none of the segment bookkeeping (it changed the star loop's register allocation
 // and cost 2.8 % on the headline workload when it was a run-time branch).
-template <int ROT, int FREE, int BG, int MATH, bool SEG>
+// FUSE: ensemble half-step fused in (proposal drawn in the prologue, acceptance in the finishing CTA).
+template <int ROT, int FREE, int BG, int MATH, bool SEG, bool FUSE>
 __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : MCD_BG_MIN_BLOCKS)) lnlike_kernel(const __grid_constant__ LaunchParams P) {
     constexpr int NC = total_columns(ROT, FREE, BG);
     constexpr bool ICOL = has_icol(BG, MATH);
@@ -560,7 +613,16 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
 
     Walker W;
     W.prior_ok = 0;
-    if (valid) load_walker<ROT, FREE, BG>(P, seg * P.n_walkers + w, W);
+    if constexpr (FUSE) {
+        if (valid) {
+            double q[MCD_MAX_THETA];
+            int row_index;
+            draw_proposal(P, seg, w, q, row_index);
+            load_walker<ROT, FREE, BG>(P, q, W);
+        }
+    } else {
+        if (valid) load_walker<ROT, FREE, BG>(P, P.theta + (size_t)(seg * P.n_walkers + w) * P.n_theta, W);
+    }
     // a walker outside its box prior is never evaluated by the reference (runner.py:303-306)
     const bool active = valid && (W.prior_ok || !P.apply_prior);
 
@@ -626,15 +688,10 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     const int sup = chunk / P.super;
     const int c_begin = sup * P.super;
     const int c_end = min(n_chunks, c_begin + P.super);
-    __threadfence();
     __syncthreads();
-    if (tid == 0) {
-        const unsigned int ticket = atomicAdd(&cnt[sup], 1u);
-        s_last = (ticket == (unsigned int)(c_end - c_begin) - 1u);
-    }
+    if (tid == 0) s_last = (take_ticket(&cnt[sup]) == (unsigned int)(c_end - c_begin) - 1u);
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
     double level1 = 0.0;
     if (valid && slice == 0) {
 #pragma unroll 4
@@ -645,15 +702,10 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     double total = 0.0;
     if (n_super > 1) {
         if (valid && slice == 0) P.partials2[((size_t)seg * P.n_super + sup) * P.n_walkers + w] = level1;
-        __threadfence();
         __syncthreads();
-        if (tid == 0) {
-            const unsigned int ticket = atomicAdd(&cnt[P.n_super], 1u);
-            s_last = (ticket == (unsigned int)n_super - 1u);
-        }
+        if (tid == 0) s_last = (take_ticket(&cnt[P.n_super]) == (unsigned int)n_super - 1u);
         __syncthreads();
         if (!s_last) return;
-        __threadfence();
         if (valid && slice == 0) {
 #pragma unroll 4
             for (int k = 0; k < n_super; ++k)
@@ -669,7 +721,14 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
         total = rejected ? __longlong_as_double(0xfff0000000000000LL) : total;
     }
     if (P.xchg_world > 1) total = exchange_shard_sums(P, total, w, group, valid && slice == 0, &s_last);
-    if (valid && slice == 0) P.out[(size_t)seg * P.n_walkers + w] = total;
+    if constexpr (FUSE) {
+        // accept or reject in place.  Safe without further synchronisation: the positions of the active
+        // half are read only by the CTAs of their own walker group, all of which have finished (ticket),
+        // and the other half is read-only during this half-step.
+        if (valid && slice == 0) accept_proposal(P, seg, w, total);
+    } else {
+        if (valid && slice == 0) P.out[(size_t)seg * P.n_walkers + w] = total;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -681,7 +740,7 @@ template <int ROT, int FREE, int BG>
 __global__ void per_star_kernel(const __grid_constant__ LaunchParams P, double *__restrict__ out, int membership) {
     constexpr int NC = total_columns(ROT, FREE, BG);
     __shared__ Walker Ws;
-    if (threadIdx.x == 0) load_walker<ROT, FREE, BG>(P, 0, Ws);
+    if (threadIdx.x == 0) load_walker<ROT, FREE, BG>(P, P.theta, Ws);
     __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_stars) return;
@@ -706,10 +765,16 @@ static cudaError_t launch_one(const LaunchParams &p, cudaStream_t stream) {
     dim3 grid((unsigned)p.n_chunks * (unsigned)p.n_groups, (unsigned)std::max(1, p.n_segments));
     if (p.seg_begin) {
         // segmented handles exist for the models without background component (RadialBinsFit)
-        if constexpr (BG == MCD_BG_NONE) lnlike_kernel<ROT, FREE, BG, MATH, true><<<grid, kBlock, smem, stream>>>(p);
-        else return cudaErrorInvalidValue;
+        if constexpr (BG == MCD_BG_NONE) {
+            if (p.fuse.enabled) lnlike_kernel<ROT, FREE, BG, MATH, true, true><<<grid, kBlock, smem, stream>>>(p);
+            else lnlike_kernel<ROT, FREE, BG, MATH, true, false><<<grid, kBlock, smem, stream>>>(p);
+        } else {
+            return cudaErrorInvalidValue;
+        }
+    } else if (p.fuse.enabled) {
+        lnlike_kernel<ROT, FREE, BG, MATH, false, true><<<grid, kBlock, smem, stream>>>(p);
     } else {
-        lnlike_kernel<ROT, FREE, BG, MATH, false><<<grid, kBlock, smem, stream>>>(p);
+        lnlike_kernel<ROT, FREE, BG, MATH, false, false><<<grid, kBlock, smem, stream>>>(p);
     }
     return cudaGetLastError();
 }
@@ -719,7 +784,7 @@ static int occupancy_one() {
     constexpr int NC = total_columns(ROT, FREE, BG);
     const size_t smem = (size_t)kStages * kMaxTile * (NC * 8 + (has_icol(BG, MATH) ? 4 : 0));
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lnlike_kernel<ROT, FREE, BG, MATH, false>, kBlock, smem) !=
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lnlike_kernel<ROT, FREE, BG, MATH, false, false>, kBlock, smem) !=
         cudaSuccess)
         return 1;
     return n > 0 ? n : 1;

@@ -1,8 +1,10 @@
 // Device-resident affine-invariant ensemble sampler: emcee's default red/blue StretchMove(a = 2)
 // as the reference drives it (analysis/runner.py:403,416-419), with positions, log-probabilities,
 // random numbers, proposals and accept/reject all on the GPU.  One emcee iteration is
-//     split (random red/blue partition) -> [propose -> lnprob kernel -> accept] x 2 -> store
-// captured once as a CUDA graph and replayed per step: no host round trip inside a chain.
+//     split (random red/blue partition) -> lnprob kernel with fused propose/accept x 2 -> store
+// (the likelihood kernel draws the proposals of the active half in its prologue and its finishing
+// CTAs accept or reject in place: csrc/mcd_kernels.cu, FUSE) captured once as a CUDA graph and
+// replayed per step: no host round trip inside a chain.
 //
 // emcee is a third-party dependency of the reference (unpinned, not vendored); the algorithm
 // restated here is its published one (Goodman & Weare 2010; emcee 3 `RedBlueMove.propose`):
@@ -15,34 +17,13 @@
 #include <new>
 
 #include "mcd_internal.h"
+#include "mcd_rng.cuh"
 
 using namespace mcd;
 
 namespace {
 
 constexpr int kMaxWalkers = 4096;   // split_kernel keeps one 64-bit key per walker in 32 KiB of shared memory
-
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-        const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += W0;
-        k.y += W1;
-    }
-    return c;
-}
-
-// two uniforms in [0, 1) with 53 random bits each
-__device__ __forceinline__ void uniforms(uint64_t seed, uint32_t step, uint32_t half, uint32_t walker, uint32_t purpose,
-                                         double &u0, double &u1) {
-    const uint4 r = philox4x32_10(make_uint4(step, half, walker, purpose), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    const uint64_t a = ((uint64_t)r.x << 32) | r.y, b = ((uint64_t)r.z << 32) | r.w;
-    u0 = (double)(a >> 11) * (1.0 / 9007199254740992.0);
-    u1 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
-}
 
 struct Ensemble {
     int n_segments;                     // independent ensembles advanced together (radial bins)
@@ -51,9 +32,7 @@ struct Ensemble {
     double a;
     double *pos;          // [S][W][P]
     double *lnp;          // [S][W]
-    double *q;            // [S][n0][P] proposals of the current half
-    double *lnp_q;        // [S][n0]
-    double *logz;         // [S][n0]
+    double *lnp_q;        // [S][n0] scratch of the geometry dry run
     int *perm;            // [S][W]: perm[s][0:n0] = red walkers of segment s, perm[s][n0:W] = blue
     long long *n_accepted;   // [S][W]
     unsigned int *step;      // [2]: global step counter, step inside the current run() chunk
@@ -84,62 +63,21 @@ __global__ void split_kernel(Ensemble E) {
     }
 }
 
-__global__ void propose_kernel(Ensemble E, int half) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ns = half == 0 ? E.n0 : E.n1;
-    const int nc = E.n_walkers - ns;
-    if (idx >= ns * E.n_segments) return;
-    const int seg = idx / ns, k = idx % ns;
-    const int *perm = E.perm + (size_t)seg * E.n_walkers;
-    const int *active = perm + (half == 0 ? 0 : E.n0);
-    const int *other = perm + (half == 0 ? E.n0 : 0);
-    double u0, u1;
-    uniforms(E.seed, E.step[0], (uint32_t)half, (uint32_t)(seg * E.n_walkers + k), 0u, u0, u1);
-    const double t = (E.a - 1.0) * u0 + 1.0;
-    const double z = t * t / E.a;
-    int j = (int)(u1 * nc);
-    j = j >= nc ? nc - 1 : j;
-    const double *base = E.pos + (size_t)seg * E.n_walkers * E.n_theta;
-    const double *s = base + (size_t)active[k] * E.n_theta;
-    const double *c = base + (size_t)other[j] * E.n_theta;
-    double *q = E.q + ((size_t)seg * ns + k) * E.n_theta;
-    for (int p = 0; p < E.n_theta; ++p) q[p] = c[p] - (c[p] - s[p]) * z;
-    E.logz[(size_t)seg * ns + k] = (E.n_theta - 1.0) * log(z);
-}
-
-__global__ void accept_kernel(Ensemble E, int half) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ns = half == 0 ? E.n0 : E.n1;
-    if (idx >= ns * E.n_segments) return;
-    const int seg = idx / ns, k = idx % ns;
-    const int w = seg * E.n_walkers + E.perm[(size_t)seg * E.n_walkers + (half == 0 ? 0 : E.n0) + k];
-    double u0, u1;
-    uniforms(E.seed, E.step[0], (uint32_t)half, (uint32_t)(seg * E.n_walkers + k), 1u, u0, u1);
-    const double new_lp = E.lnp_q[(size_t)seg * ns + k];
-    const double diff = E.logz[(size_t)seg * ns + k] + new_lp - E.lnp[w];
-    if (diff > log(u0)) {     // NaN never accepts
-        const double *q = E.q + ((size_t)seg * ns + k) * E.n_theta;
-        double *s = E.pos + (size_t)w * E.n_theta;
-        for (int p = 0; p < E.n_theta; ++p) s[p] = q[p];
-        E.lnp[w] = new_lp;
-        E.n_accepted[w] += 1;
-    }
-}
-
-__global__ void store_kernel(Ensemble E) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// end of a step: append the state to the chain (if one is kept) and advance the step counters.
+// One CTA, so that the counters can be advanced after every thread has read them.
+__global__ void __launch_bounds__(1024) store_advance_kernel(Ensemble E) {
     const unsigned int local = E.step[1];
     const int rows = E.n_walkers * E.n_segments;
     const int total = rows * E.n_theta;
     if (E.chain) {
-        if (i < total) E.chain[(size_t)local * total + i] = E.pos[i];
-        if (i < rows) E.chain_lnp[(size_t)local * rows + i] = E.lnp[i];
+        for (int i = threadIdx.x; i < total; i += blockDim.x) E.chain[(size_t)local * total + i] = E.pos[i];
+        for (int i = threadIdx.x; i < rows; i += blockDim.x) E.chain_lnp[(size_t)local * rows + i] = E.lnp[i];
     }
-}
-
-__global__ void advance_kernel(Ensemble E) {
-    E.step[0] += 1u;
-    E.step[1] += 1u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        E.step[0] += 1u;
+        E.step[1] = local + 1u;
+    }
 }
 
 }  // namespace
@@ -163,9 +101,7 @@ static void free_ensemble(mcd_ensemble *e) {
     if (e->graph) cudaGraphDestroy(e->graph);
     cudaFree(e->E.pos);
     cudaFree(e->E.lnp);
-    cudaFree(e->E.q);
     cudaFree(e->E.lnp_q);
-    cudaFree(e->E.logz);
     cudaFree(e->E.perm);
     cudaFree(e->E.n_accepted);
     cudaFree(e->E.step);
@@ -210,9 +146,7 @@ extern "C" int mcd_ensemble_create(mcd_handle *h, int32_t n_walkers, uint64_t se
     ok = ok && cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMalloc(&E.pos, sizeof(double) * S * n_walkers * P) == cudaSuccess;
     ok = ok && cudaMalloc(&E.lnp, sizeof(double) * S * n_walkers) == cudaSuccess;
-    ok = ok && cudaMalloc(&E.q, sizeof(double) * S * E.n0 * P) == cudaSuccess;
     ok = ok && cudaMalloc(&E.lnp_q, sizeof(double) * S * E.n0) == cudaSuccess;
-    ok = ok && cudaMalloc(&E.logz, sizeof(double) * S * E.n0) == cudaSuccess;
     ok = ok && cudaMalloc(&E.perm, sizeof(int) * S * n_walkers) == cudaSuccess;
     ok = ok && cudaMalloc(&E.n_accepted, sizeof(long long) * S * n_walkers) == cudaSuccess;
     ok = ok && cudaMalloc(&E.step, sizeof(unsigned int) * 2) == cudaSuccess;
@@ -240,20 +174,28 @@ extern "C" int mcd_ensemble_set_state(mcd_ensemble *e, const double *pos_host) {
 
 static int enqueue_step(mcd_ensemble *e) {
     Ensemble &E = e->E;
-    const int threads = 128;
     const int split_threads = std::min(1024, ((E.n_walkers + 31) / 32) * 32);
     split_kernel<<<E.n_segments, split_threads, sizeof(unsigned long long) * E.n_walkers, e->stream>>>(E);
     for (int half = 0; half < 2; ++half) {
         const int ns = half == 0 ? E.n0 : E.n1;
         if (ns == 0) continue;
-        const int all = ns * E.n_segments;
-        propose_kernel<<<(all + threads - 1) / threads, threads, 0, e->stream>>>(E, half);
-        if (int rc = launch_ensemble(e->h, E.q, ns, E.lnp_q, 1, e->stream)) return rc;
-        accept_kernel<<<(all + threads - 1) / threads, threads, 0, e->stream>>>(E, half);
+        // one launch per half-step: the likelihood kernel draws the proposals of the active half and
+        // its finishing CTAs accept or reject them in place
+        FuseParams f{};
+        f.half = half;
+        f.n0 = E.n0;
+        f.walkers_total = E.n_walkers;
+        f.a = E.a;
+        f.seed = E.seed;
+        f.pos = E.pos;
+        f.lnp = E.lnp;
+        f.perm = E.perm;
+        f.n_accepted = E.n_accepted;
+        f.step = E.step;
+        if (int rc = launch_ensemble_fused(e->h, ns, f, e->stream)) return rc;
     }
     const int total = E.n_segments * E.n_walkers * std::max(1, E.n_theta);
-    store_kernel<<<(total + 255) / 256, 256, 0, e->stream>>>(E);
-    advance_kernel<<<1, 1, 0, e->stream>>>(E);
+    store_advance_kernel<<<1, std::min(1024, ((total + 31) / 32) * 32), 0, e->stream>>>(E);
     const cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? 0 : set_error(-2, "launching the ensemble step failed: %s", cudaGetErrorString(err));
 }
