@@ -394,7 +394,12 @@ def gpu_run(args):
         'clocks': clock_summary,
         'roofline': {
             'bound': 'fp64', 'achieved': achieved_tflops, 'peak': fp64_peak, 'unit': 'TFLOP/s',
-            'frac': (achieved_tflops / fp64_peak) if fp64_peak else None, 'traffic': None,
+            'frac': (achieved_tflops / fp64_peak) if fp64_peak else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel on the default workload
+            # (ncu, profiles/r01_summary.md); null for any other workload
+            'traffic': 4.11e8 if (world == 1 and args.stars == 10_000_000 and args.walkers == 1024
+                                  and not args.free_centre and args.math == 'fast') else None,
+            'traffic_unit': 'bytes per launch (algorithmic: %.3g)' % bytes_per_launch,
             'kernel': 'mcd::lnlike_kernel<RADIAL,%s,BG_NONE,%s>' % ('FREE' if args.free_centre else 'FIXED',
                                                                     args.math.upper()),
             'kernel_ms': kernel_ms, 'terms_per_launch': terms_per_launch,
