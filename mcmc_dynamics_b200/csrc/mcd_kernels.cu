@@ -543,6 +543,67 @@ __device__ __noinline__ void accept_proposal(const LaunchParams &P, int seg, int
 }
 
 // ------------------------------------------------------------------------------------------
+// chunks -> result
+// ------------------------------------------------------------------------------------------
+// Called by every thread of every CTA after its chunk partial is stored.  Two ticketed levels, both
+// adding in index order (independent of CTA scheduling): the last CTA of a super-chunk (P.super
+// consecutive chunks) adds their partials, the last super-chunk to finish adds the super-chunk sums,
+// applies the prior mask and hands the result on (output vector, cross-GPU exchange or the fused
+// acceptance).  `owner` threads (slice 0 of a valid walker) carry walker `w`.  Out of line on
+// purpose: the register allocation of the star loop must not depend on this cold code.
+template <int MATH, bool FUSE>
+__device__ __noinline__ void finish_walker_group(const LaunchParams &P, int seg, int chunk, int group, int w, int n_chunks,
+                                                 long long seg_stars, bool owner, int prior_ok, int *s_last) {
+    const int tid = threadIdx.x;
+    const int n_super = (n_chunks + P.super - 1) / P.super;
+    unsigned int *cnt = P.counters + ((size_t)seg * P.n_groups + group) * (P.n_super + 1);
+    const int sup = chunk / P.super;
+    const int c_begin = sup * P.super;
+    const int c_end = min(n_chunks, c_begin + P.super);
+    __syncthreads();
+    if (tid == 0) *s_last = (take_ticket(&cnt[sup]) == (unsigned int)(c_end - c_begin) - 1u);
+    __syncthreads();
+    if (!*s_last) return;
+    double level1 = 0.0;
+    if (owner) {
+#pragma unroll 4
+        for (int cidx = c_begin; cidx < c_end; ++cidx)
+            level1 += __ldcg(&P.partials[((size_t)seg * P.n_chunks + cidx) * P.n_walkers + w]);
+    }
+    if (tid == 0) cnt[sup] = 0u;
+    double total = 0.0;
+    if (n_super > 1) {
+        if (owner) P.partials2[((size_t)seg * P.n_super + sup) * P.n_walkers + w] = level1;
+        __syncthreads();
+        if (tid == 0) *s_last = (take_ticket(&cnt[P.n_super]) == (unsigned int)n_super - 1u);
+        __syncthreads();
+        if (!*s_last) return;
+        if (owner) {
+#pragma unroll 4
+            for (int k = 0; k < n_super; ++k)
+                total += __ldcg(&P.partials2[((size_t)seg * P.n_super + k) * P.n_walkers + w]);
+        }
+        if (tid == 0) cnt[P.n_super] = 0u;
+    } else {
+        total = level1;            // at most P.super chunks: one level is the whole reduction
+    }
+    if (owner) {
+        if (MATH == MCD_MATH_FAST) total = fma((double)seg_stars, -0.5 * kLn2Pi, total);
+        const bool rejected = P.apply_prior && !prior_ok;
+        total = rejected ? __longlong_as_double(0xfff0000000000000LL) : total;
+    }
+    if (P.xchg_world > 1) total = exchange_shard_sums(P, total, w, group, owner, s_last);
+    if constexpr (FUSE) {
+        // accept or reject in place.  Safe without further synchronisation: the positions of the active
+        // half are read only by the CTAs of their own walker group, all of which have finished (ticket),
+        // and the other half is read-only during this half-step.
+        if (owner) accept_proposal(P, seg, w, total);
+    } else {
+        if (owner) P.out[(size_t)seg * P.n_walkers + w] = total;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // the lnlike / lnprob kernel
 // ------------------------------------------------------------------------------------------
 // SEG: segmented launch (blockIdx.y = segment).  A separate instantiation so that the single-catalogue
@@ -583,7 +644,6 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
         n_tiles = (count + tile - 1) / tile;
         n_chunks = max(1, (n_tiles + P.tiles_per_chunk - 1) / P.tiles_per_chunk);
     }
-    const int n_super = (n_chunks + P.super - 1) / P.super;
     if (chunk >= n_chunks) return;          // the grid is sized for the largest segment
 
     const int t_begin = chunk * P.tiles_per_chunk;
@@ -681,54 +741,9 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
         P.partials[((size_t)seg * P.n_chunks + chunk) * P.n_walkers + w] = s;
     }
 
-    // ---- chunks -> result, two levels, both in index order (independent of CTA scheduling) ------
-    // level 1: the last CTA of a super-chunk (P.super consecutive chunks) adds their partials;
-    // level 2: the last super-chunk to finish adds the super-chunk sums and writes the result.
-    unsigned int *cnt = P.counters + ((size_t)seg * P.n_groups + group) * (P.n_super + 1);
-    const int sup = chunk / P.super;
-    const int c_begin = sup * P.super;
-    const int c_end = min(n_chunks, c_begin + P.super);
-    __syncthreads();
-    if (tid == 0) s_last = (take_ticket(&cnt[sup]) == (unsigned int)(c_end - c_begin) - 1u);
-    __syncthreads();
-    if (!s_last) return;
-    double level1 = 0.0;
-    if (valid && slice == 0) {
-#pragma unroll 4
-        for (int cidx = c_begin; cidx < c_end; ++cidx)
-            level1 += __ldcg(&P.partials[((size_t)seg * P.n_chunks + cidx) * P.n_walkers + w]);
-    }
-    if (tid == 0) cnt[sup] = 0u;
-    double total = 0.0;
-    if (n_super > 1) {
-        if (valid && slice == 0) P.partials2[((size_t)seg * P.n_super + sup) * P.n_walkers + w] = level1;
-        __syncthreads();
-        if (tid == 0) s_last = (take_ticket(&cnt[P.n_super]) == (unsigned int)n_super - 1u);
-        __syncthreads();
-        if (!s_last) return;
-        if (valid && slice == 0) {
-#pragma unroll 4
-            for (int k = 0; k < n_super; ++k)
-                total += __ldcg(&P.partials2[((size_t)seg * P.n_super + k) * P.n_walkers + w]);
-        }
-        if (tid == 0) cnt[P.n_super] = 0u;
-    } else {
-        total = level1;            // at most P.super chunks: one level is the whole reduction
-    }
-    if (valid && slice == 0) {
-        if (MATH == MCD_MATH_FAST) total = fma((double)seg_stars, -0.5 * kLn2Pi, total);
-        const bool rejected = P.apply_prior && !W.prior_ok;
-        total = rejected ? __longlong_as_double(0xfff0000000000000LL) : total;
-    }
-    if (P.xchg_world > 1) total = exchange_shard_sums(P, total, w, group, valid && slice == 0, &s_last);
-    if constexpr (FUSE) {
-        // accept or reject in place.  Safe without further synchronisation: the positions of the active
-        // half are read only by the CTAs of their own walker group, all of which have finished (ticket),
-        // and the other half is read-only during this half-step.
-        if (valid && slice == 0) accept_proposal(P, seg, w, total);
-    } else {
-        if (valid && slice == 0) P.out[(size_t)seg * P.n_walkers + w] = total;
-    }
+    // ---- chunks -> result (and shards -> catalogue, proposal acceptance): cold path, out of line ----
+    finish_walker_group<MATH, FUSE>(P, seg, chunk, group, w, n_chunks, seg_stars, valid && slice == 0, W.prior_ok,
+                                    &s_last);
 }
 
 // ------------------------------------------------------------------------------------------
