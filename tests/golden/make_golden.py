@@ -290,6 +290,31 @@ def main():
         'columns': {name: [float(x) for x in np.asarray(getattr(col, 'value', col))] for name, col in prof.columns.items()},
     }
 
+    # ---- config format, both directions -----------------------------------------------------------
+    # (i) a Parameters object edited and serialised by the REFERENCE; the product must load it
+    rp = R.ModelFit.default_parameters()
+    rp['ra_center'].set(value=u.Quantity(201.697, u.deg), fixed=True)
+    rp['a'].set(value=u.Quantity(0.5, u.arcmin), min=0.0, max=120.0)
+    rp['v_sys'].set(value=u.Quantity(232.5, u.km / u.s), fixed=True, lnprior='norm.logpdf(val, loc=232.5, scale=2)')
+    rp['sigma_max'].set(initials='rng.lognormal(mean=2.3, sigma=0.5, size=n)')
+    post['parameters_json_from_reference'] = rp.dumps()
+    post['parameters_expected'] = [[name, float(p.value), None if p.unit is None else str(p.unit), bool(p.fixed),
+                                    float(p.min), float(p.max), p.initials, p.lnprior] for name, p in rp.items()]
+    # (ii) a string serialised by the PRODUCT; the reference must load it (checked here, at generation time)
+    sys.path.insert(0, ROOT)
+    from mcmc_dynamics_b200.analysis import ModelFit as ProductModelFit
+    pp = ProductModelFit.default_parameters()
+    pp['dec_center'].set(value=-47.4799, fixed=True)
+    pp['r_peak'].set(value=90.0, min=0.0, max=500.0)
+    back = R.Parameters().loads(pp.dumps())
+    for name, p in pp.items():
+        q = back[name]
+        assert float(q.value) == float(p.value) and bool(q.fixed) == bool(p.fixed), name
+        assert float(q.min) == float(p.min) and float(q.max) == float(p.max), name
+        assert (q.unit is None and p.unit is None) or str(q.unit).replace(' ', '') == str(p.unit).replace(' ', ''), name
+        assert q.initials == p.initials, name
+    print('product -> reference Parameters JSON round trip ok')
+
     # default parameter tables as the reference's Parameters class loads them
     tables = {}
     for cls_name in ('ConstantFit', 'ConstantFitGB', 'ModelFit', 'ModelFitGB', 'ModelFitConstantBackground'):

@@ -146,3 +146,25 @@ def test_create_profiles_matches_reference(tmp_path):
     assert np.allclose(np.asarray(prof2['sigma'].value), c['columns']['sigma'], rtol=1e-12)
     assert np.loadtxt(out, delimiter=',').shape == (4, 11)
     assert len(mf.create_profiles(np.asarray(c['chain']), n_burn=c['n_burn'])) == 50
+
+
+def test_parameters_json_written_by_the_reference_loads_here():
+    """Config-format boundary: a Parameters object edited and serialised by the reference's own
+    ``Parameters.dumps`` (with a stored ``random_state``) is read back with identical content.  The
+    opposite direction (product ``dumps`` -> reference ``loads``) is asserted at generation time in
+    tests/golden/make_golden.py."""
+    from mcmc_dynamics_b200 import Parameters
+    text = GOLDEN['post']['parameters_json_from_reference']
+    pars = Parameters().loads(text)
+    want = GOLDEN['post']['parameters_expected']
+    assert list(pars) == [row[0] for row in want]
+    for name, value, unit, fixed, lo, hi, initials, lnprior in want:
+        p = pars[name]
+        assert p.value == pytest.approx(value, rel=1e-15) and p.fixed == fixed and p.min == lo and p.max == hi
+        assert (unit or '').replace(' ', '') == ('' if p.unit is None else str(p.unit).replace(' ', ''))
+        assert p.initials == initials and p.lnprior == lnprior
+    # the edited object behaves: unit conversion happened in the reference (0.5 arcmin -> 30 arcsec)
+    assert pars['a'].value == pytest.approx(30.0) and pars['a'].max == 120.0
+    assert pars['v_sys'].evaluate_lnprior(232.5) == pytest.approx(-np.log(2.0 * np.sqrt(2 * np.pi)))
+    draws = pars['sigma_max'].evaluate_initials(50)
+    assert draws.shape == (50,) and np.all(draws > 0)
