@@ -493,6 +493,34 @@ int mcd::launch_ensemble(mcd_handle *h, const double *theta_dev, int n_walkers, 
 int mcd::launch_ensemble_fused(mcd_handle *h, int n_walkers, const FuseParams &fuse, cudaStream_t stream) {
     return launch(h, nullptr, n_walkers, nullptr, 1, stream, false, &fuse);
 }
+int mcd::launch_resident_chain(mcd_handle *h, const ChainParams &chain, cudaStream_t stream) {
+    if (!h) return fail(-1, "null handle");
+    const size_t smem = chain_shared_bytes(h->var, h->max_segment, chain.n_walkers, h->desc.n_theta);
+    if (smem == 0) return 1;                 // does not fit one SM's shared memory: not eligible
+    // One SM per segment against the whole machine per launch: take the resident kernel only where its
+    // half-step is estimated to be shorter than a launch (~14 us of fixed latency + the same arithmetic
+    // spread over all SMs).  Cycle model: FP64-pipe instructions ~ nominal flops per term, 64 lanes per
+    // SM, 60 % pipe efficiency, 1.9 GHz.  MCD_FORCE_RESIDENT_CHAIN=1 overrides (tests).
+    {
+        const char *force = getenv("MCD_FORCE_RESIDENT_CHAIN");
+        const double flops = (double)variant_flops_per_term(h->var);
+        const double ns = 0.5 * chain.n_walkers;
+        const double per_sm = 64.0 * 1.9e9 * 0.6;
+        const double waves = std::ceil((double)h->n_segments / std::max(1, h->sm_count));
+        const double resident = waves * (2e-6 + ns * (double)h->max_segment * flops / per_sm);
+        const double launched = 14e-6 + ns * (double)h->n * flops / (per_sm * std::max(1, h->sm_count));
+        if (!(force && force[0] == '1') && resident > launched) return 1;
+    }
+    MCD_CUDA(cudaSetDevice(h->device));
+    LaunchParams p{};
+    fill_params(h, p);
+    p.apply_prior = 1;
+    ChainParams c = chain;
+    c.max_segment_padded = (int)(((h->max_segment + 15) / 16) * 16);
+    MCD_CUDA(launch_chain(h->var, p, c, smem, stream));
+    h->info.launches += 1;
+    return 0;
+}
 int mcd::handle_device(const mcd_handle *h) { return h->device; }
 
 extern "C" int mcd_lnlike(mcd_handle *h, const double *theta_host, int32_t n_walkers, double *out_host) {

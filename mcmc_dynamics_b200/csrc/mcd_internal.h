@@ -57,6 +57,26 @@ struct FuseParams {
     const unsigned int *step;     // [0]: global step counter (Philox counter word)
 };
 
+// Whole chains inside one kernel (small catalogues): one CTA per segment keeps the segment's packed
+// columns and the ensemble state in shared memory and runs `n_steps` stretch-move iterations without
+// leaving the SM.
+constexpr int kChainBlock = 512;      // threads per CTA of the resident-chain kernel
+constexpr int kChainMaxWalkers = 1024;
+struct ChainParams {
+    int n_steps;
+    int n_walkers;                // W per segment
+    int n0;                       // red half
+    int max_segment_padded;       // column stride in shared memory (stars, multiple of 16)
+    unsigned int step0;           // global step counter at entry
+    double a;
+    unsigned long long seed;
+    double *pos;                  // [S][W][P] in/out
+    double *lnp;                  // [S][W] in/out
+    long long *n_accepted;        // [S][W] accumulated
+    double *chain;                // [n_steps][S][W][P] or nullptr
+    double *chain_lnp;            // [n_steps][S][W] or nullptr
+};
+
 // Kernel argument block of one lnlike / lnprob launch (passed by value, __grid_constant__).
 struct LaunchParams {
     const double *cols[kMaxCols];
@@ -112,6 +132,9 @@ cudaError_t launch_lnlike(const Variant &v, const LaunchParams &p, cudaStream_t 
 // per-star lnlike (membership = 0) or membership probability (1) of walker 0 of p.theta into out[N]
 // (always PLAIN arithmetic)
 cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out, int membership, cudaStream_t stream);
+// resident-chain kernel: shared memory it needs for this problem, or 0 if the problem does not fit
+size_t chain_shared_bytes(const Variant &v, long long max_segment, int n_walkers, int n_theta);
+cudaError_t launch_chain(const Variant &v, const LaunchParams &p, const ChainParams &c, size_t smem, cudaStream_t stream);
 // resident CTAs per SM of the lnlike kernel of this variant (occupancy API)
 int lnlike_blocks_per_sm(const Variant &v);
 
@@ -121,6 +144,8 @@ int launch_ensemble(mcd_handle *h, const double *theta_dev, int n_walkers, doubl
 // the same with the proposal and the acceptance of an ensemble half-step fused in (theta is drawn in
 // the kernel; n_walkers = size of the active half)
 int launch_ensemble_fused(mcd_handle *h, int n_walkers, const FuseParams &fuse, cudaStream_t stream);
+// whole chains in one launch when the catalogue fits shared memory; returns 1 if not eligible
+int launch_resident_chain(mcd_handle *h, const ChainParams &chain, cudaStream_t stream);
 int handle_device(const mcd_handle *h);
 // record the thread-local message returned by mcd_last_error() and hand back `code`
 int set_error(int code, const char *fmt, ...);

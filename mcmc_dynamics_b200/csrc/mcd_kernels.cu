@@ -45,6 +45,13 @@
 #define MCD_BG_PAIRS 1
 #endif
 
+// This file is compiled three times (see __graft_entry__.py), so that the template instantiations
+// build in parallel:  MCD_TU_PART 0 = pack kernel, variant tables and the dispatch front ends,
+// 1 = every FAST-arithmetic kernel, 2 = every PLAIN-arithmetic kernel (+ the per-star kernel).
+#ifndef MCD_TU_PART
+#error "compile with -DMCD_TU_PART=0|1|2"
+#endif
+
 namespace mcd {
 
 // ------------------------------------------------------------------------------------------
@@ -69,6 +76,7 @@ __host__ __device__ constexpr bool has_icol(int bg, int math) {
     return math == MCD_MATH_FAST && (bg == MCD_BG_FIXED_PMEMBER || bg == MCD_BG_FIXED_DENSITY);
 }
 
+#if MCD_TU_PART == 0
 int variant_columns(const Variant &v) { return total_columns(v.rotation, v.free_centre, v.background); }
 bool variant_has_icol(const Variant &v) { return has_icol(v.background, v.math_mode); }
 
@@ -159,6 +167,9 @@ cudaError_t launch_pack(const PackParams &p, cudaStream_t stream) {
     pack_kernel<<<(unsigned)grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
+#endif  // MCD_TU_PART == 0
+
+#if MCD_TU_PART != 0
 
 // ------------------------------------------------------------------------------------------
 // per-walker derived constants
@@ -486,7 +497,7 @@ __device__ __forceinline__ unsigned int take_ticket(unsigned int *counter) {
 // symmetric memory; parity double-buffers consecutive calls (a rank can be at most one call ahead,
 // because it cannot finish call k+1 before every peer has published call k+1).  Kept out of line so
 // that this cold path does not take part in the register allocation of the star loop.
-__device__ __noinline__ double exchange_shard_sums(const LaunchParams &P, double total, int w, int group, bool owner,
+static __device__ __noinline__ double exchange_shard_sums(const LaunchParams &P, double total, int w, int group, bool owner,
                                                    int *timed_out) {
     const int tid = threadIdx.x;
     const int par = (int)(P.xchg_epoch & 1ull);
@@ -526,7 +537,7 @@ __device__ __noinline__ double exchange_shard_sums(const LaunchParams &P, double
 }
 
 // acceptance of the fused half-step: (P-1) ln z + lnp(q) - lnp(s) > ln u'; NaN never accepts
-__device__ __noinline__ void accept_proposal(const LaunchParams &P, int seg, int k, double lnp_new) {
+static __device__ __noinline__ void accept_proposal(const LaunchParams &P, int seg, int k, double lnp_new) {
     const FuseParams &F = P.fuse;
     double q[MCD_MAX_THETA];
     int row;
@@ -747,6 +758,157 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
 }
 
 // ------------------------------------------------------------------------------------------
+// resident chains: whole stretch-move runs of small catalogues inside one CTA per segment
+// ------------------------------------------------------------------------------------------
+// For catalogues of a few thousand stars (the per-radial-bin fits of bin/run.py:179-190 and
+// bin/run_tests.py:81-97, BASELINE config 1) a likelihood launch is < 1 us of arithmetic inside
+// ~13 us of launch, first-tile and cross-CTA reduction latency.  Here one CTA per segment loads the
+// segment's packed columns into shared memory ONCE, keeps positions and log-probabilities of its
+// ensemble in shared memory, and runs every emcee iteration (red/blue split, proposals, likelihood
+// over all stars, acceptance) with __syncthreads as the only synchronisation.  Same move, same
+// Philox counters and the same per-term arithmetic (`term<>`) as the launch-per-half-step sampler.
+template <int ROT, int FREE, int BG, int MATH>
+__global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constant__ LaunchParams P,
+                                                            const __grid_constant__ ChainParams C) {
+    constexpr int NC = total_columns(ROT, FREE, BG);
+    constexpr bool ICOL = has_icol(BG, MATH);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int seg = blockIdx.x;
+    const int W = C.n_walkers, NP = P.n_theta;
+    const int stride = C.max_segment_padded;
+
+    const long long seg_first = P.seg_begin ? P.seg_begin[seg] : 0;
+    const int n = (int)((P.seg_begin ? P.seg_begin[seg + 1] : P.n_stars) - seg_first);
+    const long long offset = P.seg_begin ? P.seg_packed[seg] : 0;
+
+    // shared-memory carve-up (every block is a multiple of 16 bytes)
+    double *cols = reinterpret_cast<double *>(smem_raw);                       // [NC][stride]
+    int32_t *icol = reinterpret_cast<int32_t *>(cols + (size_t)NC * stride);  // [stride]  (ICOL only)
+    double *red = reinterpret_cast<double *>(icol + (ICOL ? stride : 0));     // [kChainBlock]
+    double *pos = red + kChainBlock;                                          // [W][NP]
+    double *lnp = pos + (size_t)W * NP;                                       // [W]
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(lnp + W);   // [W]
+    int *perm = reinterpret_cast<int *>(keys + W);                            // [W]
+    int *nacc = perm + W;                                                     // [W]
+
+    const int padded = ((n + 15) / 16) * 16;
+    for (int c = 0; c < NC; ++c)
+        for (int i = tid; i < padded; i += kChainBlock) cols[(size_t)c * stride + i] = P.cols[c][offset + i];
+    if (ICOL)
+        for (int i = tid; i < padded; i += kChainBlock) icol[i] = P.icol[offset + i];
+    for (int i = tid; i < W * NP; i += kChainBlock) pos[i] = C.pos[(size_t)seg * W * NP + i];
+    for (int i = tid; i < W; i += kChainBlock) {
+        lnp[i] = C.lnp[(size_t)seg * W + i];
+        nacc[i] = 0;
+    }
+    __syncthreads();
+
+    for (int it = 0; it < C.n_steps; ++it) {
+        const unsigned int step = C.step0 + (unsigned int)it;
+        // ---- red/blue partition: rank of a random key ---------------------------------------------
+        for (int w = tid; w < W; w += kChainBlock) {
+            const uint4 r = philox4x32_10(make_uint4(step, 2u, (uint32_t)(seg * W + w), 7u),
+                                          make_uint2((uint32_t)C.seed, (uint32_t)(C.seed >> 32)));
+            keys[w] = (((unsigned long long)r.x << 32) | r.y);
+        }
+        __syncthreads();
+        for (int w = tid; w < W; w += kChainBlock) {
+            const unsigned long long mine = keys[w];
+            int rank = 0;
+            for (int o = 0; o < W; ++o) rank += (keys[o] < mine) || (keys[o] == mine && o < w);
+            perm[rank] = w;
+        }
+        __syncthreads();
+        for (int half = 0; half < 2; ++half) {
+            const int ns = half == 0 ? C.n0 : W - C.n0;
+            const int nc = W - ns;
+            const int *active = perm + (half == 0 ? 0 : C.n0);
+            const int *other = perm + (half == 0 ? C.n0 : 0);
+            // thread = (walker of the active half, star slice); the active half may exceed the CTA
+            for (int base = 0; base < ns; base += kChainBlock) {
+                const int wl = min(ns - base, kChainBlock);
+                const int slices = kChainBlock / wl;
+                const int lane = tid % wl, slice = tid / wl;
+                const int k = base + lane;
+                const bool valid = slice < slices;
+                double q[MCD_MAX_THETA];
+                double z = 1.0;
+                Walker Wk;
+                Wk.prior_ok = 0;
+                if (valid) {
+                    double u0, u1;
+                    uniforms(C.seed, step, (uint32_t)half, (uint32_t)(seg * W + k), 0u, u0, u1);
+                    const double t = (C.a - 1.0) * u0 + 1.0;
+                    z = t * t / C.a;
+                    int j = (int)(u1 * nc);
+                    j = j >= nc ? nc - 1 : j;
+                    const double *s = pos + (size_t)active[k] * NP;
+                    const double *c = pos + (size_t)other[j] * NP;
+                    for (int p = 0; p < NP; ++p) q[p] = c[p] - (c[p] - s[p]) * z;
+                    load_walker<ROT, FREE, BG>(P, q, Wk);
+                }
+                Accum<BG, MATH> A;
+                A.reset();
+                if (valid && Wk.prior_ok) {
+                    const int n2 = n & ~1;
+                    const int stepi = 2 * slices;
+                    int done = 0;
+                    for (int i = 2 * slice; i < n2; i += stepi) {
+                        Star<NC> s0, s1;
+                        load_pair<NC, ICOL>(cols, icol, stride, i, s0, s1);
+                        term<ROT, FREE, BG, MATH>(Wk, s0, A);
+                        term<ROT, FREE, BG, MATH>(Wk, s1, A);
+                        A.end_group();
+                        if (++done == 64) {     // fold the running products before they can overflow
+                            A.end_tile();
+                            done = 0;
+                        }
+                    }
+                    if ((n & 1) && (n2 / 2) % slices == slice) {
+                        Star<NC> s0;
+                        load_one<NC, ICOL>(cols, icol, stride, n2, s0);
+                        term<ROT, FREE, BG, MATH>(Wk, s0, A);
+                        A.end_group();
+                    }
+                    A.end_tile();
+                }
+                red[tid] = (valid && Wk.prior_ok) ? A.value() : 0.0;
+                __syncthreads();
+                if (valid && slice == 0) {
+                    double total = red[lane];
+                    for (int j = 1; j < slices; ++j) total += red[j * wl + lane];
+                    if (MATH == MCD_MATH_FAST) total = fma((double)n, -0.5 * kLn2Pi, total);
+                    if (!Wk.prior_ok) total = __longlong_as_double(0xfff0000000000000LL);
+                    double u0, u1;
+                    uniforms(C.seed, step, (uint32_t)half, (uint32_t)(seg * W + k), 1u, u0, u1);
+                    const int wa = active[k];
+                    const double diff = (NP - 1.0) * log(z) + total - lnp[wa];
+                    if (diff > log(u0)) {          // NaN never accepts
+                        for (int p = 0; p < NP; ++p) pos[(size_t)wa * NP + p] = q[p];
+                        lnp[wa] = total;
+                        nacc[wa] += 1;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (C.chain) {
+            const size_t rows = (size_t)gridDim.x * W;
+            double *dst = C.chain + ((size_t)it * rows + (size_t)seg * W) * NP;
+            for (int i = tid; i < W * NP; i += kChainBlock) dst[i] = pos[i];
+            double *dl = C.chain_lnp + (size_t)it * rows + (size_t)seg * W;
+            for (int i = tid; i < W; i += kChainBlock) dl[i] = lnp[i];
+        }
+    }
+    for (int i = tid; i < W * NP; i += kChainBlock) C.pos[(size_t)seg * W * NP + i] = pos[i];
+    for (int i = tid; i < W; i += kChainBlock) {
+        C.lnp[(size_t)seg * W + i] = lnp[i];
+        C.n_accepted[(size_t)seg * W + i] += nacc[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // per-star lnlike of one parameter vector (`no_sum=True`, model.py:565,620-621) or, with
 // `membership`, the a-posteriori membership probability of every star at that parameter vector
 // (constant.py:366-374, model.py:458-510,625-687)
@@ -773,6 +935,22 @@ __global__ void per_star_kernel(const __grid_constant__ LaunchParams P, double *
 // ------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------
+#define MCD_DISPATCH_BG(ROT, FREE, MATH, FN, ...)                                            \
+    switch (v.background) {                                                                   \
+        case MCD_BG_NONE: return FN<ROT, FREE, MCD_BG_NONE, MATH>(__VA_ARGS__);               \
+        case MCD_BG_FIXED_PMEMBER: return FN<ROT, FREE, MCD_BG_FIXED_PMEMBER, MATH>(__VA_ARGS__); \
+        case MCD_BG_FIXED_DENSITY: return FN<ROT, FREE, MCD_BG_FIXED_DENSITY, MATH>(__VA_ARGS__); \
+        default: return FN<ROT, FREE, MCD_BG_GAUSSIAN, MATH>(__VA_ARGS__);                    \
+    }
+#define MCD_DISPATCH_GEO(MATH, FN, ...)                                                       \
+    if (v.rotation == MCD_ROT_CONSTANT) {                                                     \
+        if (v.free_centre) { MCD_DISPATCH_BG(MCD_ROT_CONSTANT, 1, MATH, FN, __VA_ARGS__) }    \
+        else { MCD_DISPATCH_BG(MCD_ROT_CONSTANT, 0, MATH, FN, __VA_ARGS__) }                  \
+    } else {                                                                                  \
+        if (v.free_centre) { MCD_DISPATCH_BG(MCD_ROT_RADIAL, 1, MATH, FN, __VA_ARGS__) }      \
+        else { MCD_DISPATCH_BG(MCD_ROT_RADIAL, 0, MATH, FN, __VA_ARGS__) }                    \
+    }
+
 template <int ROT, int FREE, int BG, int MATH>
 static cudaError_t launch_one(const LaunchParams &p, cudaStream_t stream) {
     constexpr int NC = total_columns(ROT, FREE, BG);
@@ -805,30 +983,30 @@ static int occupancy_one() {
     return n > 0 ? n : 1;
 }
 
-#define MCD_DISPATCH_BG(ROT, FREE, MATH, FN, ...)                                            \
-    switch (v.background) {                                                                   \
-        case MCD_BG_NONE: return FN<ROT, FREE, MCD_BG_NONE, MATH>(__VA_ARGS__);               \
-        case MCD_BG_FIXED_PMEMBER: return FN<ROT, FREE, MCD_BG_FIXED_PMEMBER, MATH>(__VA_ARGS__); \
-        case MCD_BG_FIXED_DENSITY: return FN<ROT, FREE, MCD_BG_FIXED_DENSITY, MATH>(__VA_ARGS__); \
-        default: return FN<ROT, FREE, MCD_BG_GAUSSIAN, MATH>(__VA_ARGS__);                    \
-    }
-#define MCD_DISPATCH_GEO(MATH, FN, ...)                                                       \
-    if (v.rotation == MCD_ROT_CONSTANT) {                                                     \
-        if (v.free_centre) { MCD_DISPATCH_BG(MCD_ROT_CONSTANT, 1, MATH, FN, __VA_ARGS__) }    \
-        else { MCD_DISPATCH_BG(MCD_ROT_CONSTANT, 0, MATH, FN, __VA_ARGS__) }                  \
-    } else {                                                                                  \
-        if (v.free_centre) { MCD_DISPATCH_BG(MCD_ROT_RADIAL, 1, MATH, FN, __VA_ARGS__) }      \
-        else { MCD_DISPATCH_BG(MCD_ROT_RADIAL, 0, MATH, FN, __VA_ARGS__) }                    \
-    }
-
-cudaError_t launch_lnlike(const Variant &v, const LaunchParams &p, cudaStream_t stream) {
-    if (v.math_mode == MCD_MATH_PLAIN) { MCD_DISPATCH_GEO(MCD_MATH_PLAIN, launch_one, p, stream) }
-    else { MCD_DISPATCH_GEO(MCD_MATH_FAST, launch_one, p, stream) }
+template <int ROT, int FREE, int BG, int MATH>
+static cudaError_t chain_one(const LaunchParams &p, const ChainParams &c, size_t smem, cudaStream_t stream) {
+    cudaError_t err = cudaFuncSetAttribute(chain_kernel<ROT, FREE, BG, MATH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem);
+    if (err != cudaSuccess) return err;
+    chain_kernel<ROT, FREE, BG, MATH><<<(unsigned)std::max(1, p.n_segments), kChainBlock, smem, stream>>>(p, c);
+    return cudaGetLastError();
 }
 
-int lnlike_blocks_per_sm(const Variant &v) {
-    if (v.math_mode == MCD_MATH_PLAIN) { MCD_DISPATCH_GEO(MCD_MATH_PLAIN, occupancy_one) }
-    else { MCD_DISPATCH_GEO(MCD_MATH_FAST, occupancy_one) }
+#if MCD_TU_PART == 1
+cudaError_t launch_lnlike_fast(const Variant &v, const LaunchParams &p, cudaStream_t stream) {
+    MCD_DISPATCH_GEO(MCD_MATH_FAST, launch_one, p, stream)
+}
+int occupancy_fast(const Variant &v) { MCD_DISPATCH_GEO(MCD_MATH_FAST, occupancy_one) }
+cudaError_t launch_chain_fast(const Variant &v, const LaunchParams &p, const ChainParams &c, size_t smem, cudaStream_t stream) {
+    MCD_DISPATCH_GEO(MCD_MATH_FAST, chain_one, p, c, smem, stream)
+}
+#else
+cudaError_t launch_lnlike_plain(const Variant &v, const LaunchParams &p, cudaStream_t stream) {
+    MCD_DISPATCH_GEO(MCD_MATH_PLAIN, launch_one, p, stream)
+}
+int occupancy_plain(const Variant &v) { MCD_DISPATCH_GEO(MCD_MATH_PLAIN, occupancy_one) }
+cudaError_t launch_chain_plain(const Variant &v, const LaunchParams &p, const ChainParams &c, size_t smem, cudaStream_t stream) {
+    MCD_DISPATCH_GEO(MCD_MATH_PLAIN, chain_one, p, c, smem, stream)
 }
 
 template <int ROT, int FREE, int BG, int MATH_UNUSED>
@@ -843,5 +1021,44 @@ static cudaError_t per_star_one(const LaunchParams &p, double *out, int membersh
 cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out, int membership, cudaStream_t stream) {
     MCD_DISPATCH_GEO(MCD_MATH_PLAIN, per_star_one, p, out, membership, stream)
 }
+#endif
+#endif  // MCD_TU_PART != 0
+
+#if MCD_TU_PART == 0
+cudaError_t launch_lnlike_fast(const Variant &v, const LaunchParams &p, cudaStream_t stream);
+cudaError_t launch_lnlike_plain(const Variant &v, const LaunchParams &p, cudaStream_t stream);
+int occupancy_fast(const Variant &v);
+int occupancy_plain(const Variant &v);
+cudaError_t launch_chain_fast(const Variant &v, const LaunchParams &p, const ChainParams &c, size_t smem, cudaStream_t stream);
+cudaError_t launch_chain_plain(const Variant &v, const LaunchParams &p, const ChainParams &c, size_t smem, cudaStream_t stream);
+
+cudaError_t launch_lnlike(const Variant &v, const LaunchParams &p, cudaStream_t stream) {
+    return v.math_mode == MCD_MATH_PLAIN ? launch_lnlike_plain(v, p, stream) : launch_lnlike_fast(v, p, stream);
+}
+
+int lnlike_blocks_per_sm(const Variant &v) {
+    return v.math_mode == MCD_MATH_PLAIN ? occupancy_plain(v) : occupancy_fast(v);
+}
+
+static size_t chain_bytes(int nc, bool icol, long long stride, int n_walkers, int n_theta) {
+    size_t b = (size_t)nc * stride * 8 + (icol ? (size_t)stride * 4 : 0);
+    b += (size_t)kChainBlock * 8;                          // red
+    b += (size_t)n_walkers * n_theta * 8 + (size_t)n_walkers * 8;   // pos, lnp
+    b += (size_t)n_walkers * (8 + 4 + 4);                  // keys, perm, nacc
+    return (b + 15) & ~(size_t)15;
+}
+
+size_t chain_shared_bytes(const Variant &v, long long max_segment, int n_walkers, int n_theta) {
+    if (n_walkers > kChainMaxWalkers) return 0;
+    const long long stride = ((max_segment + 15) / 16) * 16;
+    const size_t b = chain_bytes(variant_columns(v), variant_has_icol(v), stride, n_walkers, n_theta);
+    return b <= (size_t)220 * 1024 ? b : 0;                // 227 KB per CTA on sm_100a, minus static use
+}
+
+cudaError_t launch_chain(const Variant &v, const LaunchParams &p, const ChainParams &c, size_t smem, cudaStream_t stream) {
+    return v.math_mode == MCD_MATH_PLAIN ? launch_chain_plain(v, p, c, smem, stream)
+                                         : launch_chain_fast(v, p, c, smem, stream);
+}
+#endif  // MCD_TU_PART == 0
 
 }  // namespace mcd

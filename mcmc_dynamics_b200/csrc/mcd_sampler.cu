@@ -13,6 +13,7 @@
 // Random numbers: Philox4x32-10, counter = (step, half, walker, stream id), key = seed.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -92,6 +93,8 @@ struct mcd_ensemble {
     bool graph_stores = false;
     size_t chain_cap_steps = 0;
     bool have_state = false;
+    unsigned int steps_done = 0;     // host mirror of E.step[0]
+    int last_path = 0;               // 1: resident-chain kernel, 2: CUDA graph of launches (diagnostics)
 };
 
 static void free_ensemble(mcd_ensemble *e) {
@@ -254,6 +257,47 @@ extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_
         }
     }
     if (store) chunk = std::min(chunk, e->chain_cap_steps);
+
+    // ---- small catalogues: whole chains inside one CTA per segment (csrc/mcd_kernels.cu) -----------
+    const char *no_resident = getenv("MCD_NO_RESIDENT_CHAIN");
+    if (!(no_resident && no_resident[0] == '1')) {
+        int rc = 0;
+        int done = 0;
+        while (done < n_steps) {
+            const int todo = (int)std::min<size_t>(chunk, (size_t)(n_steps - done));
+            ChainParams c{};
+            c.n_steps = todo;
+            c.n_walkers = E.n_walkers;
+            c.n0 = E.n0;
+            c.step0 = e->steps_done;
+            c.a = E.a;
+            c.seed = E.seed;
+            c.pos = E.pos;
+            c.lnp = E.lnp;
+            c.n_accepted = E.n_accepted;
+            c.chain = store ? E.chain : nullptr;
+            c.chain_lnp = store ? E.chain_lnp : nullptr;
+            rc = launch_resident_chain(e->h, c, e->stream);
+            if (rc != 0) break;              // 1: not eligible (nothing was launched), < 0: error
+            if (chain_host) ENS_CUDA(cudaMemcpyAsync(chain_host + (size_t)done * per_step, E.chain,
+                                                     sizeof(double) * todo * per_step, cudaMemcpyDeviceToHost, e->stream));
+            if (lnprob_host) ENS_CUDA(cudaMemcpyAsync(lnprob_host + (size_t)done * rows, E.chain_lnp,
+                                                      sizeof(double) * todo * rows, cudaMemcpyDeviceToHost, e->stream));
+            ENS_CUDA(cudaStreamSynchronize(e->stream));
+            e->steps_done += (unsigned int)todo;
+            done += todo;
+        }
+        if (rc < 0) return rc;
+        if (rc == 0) {
+            e->last_path = 1;
+            ENS_CUDA(cudaMemcpy(E.step, &e->steps_done, sizeof(unsigned int), cudaMemcpyHostToDevice));
+            if (n_accepted_host)
+                ENS_CUDA(cudaMemcpy(n_accepted_host, E.n_accepted, sizeof(long long) * rows, cudaMemcpyDeviceToHost));
+            return 0;
+        }
+        // rc == 1 on the first chunk: fall through to the graph of launches
+    }
+    e->last_path = 2;
     // the graph bakes in whether the chain is stored (E.chain pointer): rebuild when that changes
     double *saved_chain = E.chain, *saved_lnp = E.chain_lnp;
     if (!store) E.chain = E.chain_lnp = nullptr;
@@ -279,6 +323,7 @@ extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_
                                            cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) rc = -2;
         if (cudaStreamSynchronize(e->stream) != cudaSuccess) rc = -2;
         done += todo;
+        e->steps_done += (unsigned int)todo;
     }
     E.chain = saved_chain;
     E.chain_lnp = saved_lnp;

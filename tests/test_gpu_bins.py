@@ -42,7 +42,10 @@ def test_segmented_lnprob_equals_per_bin_models_and_oracle(cls):
                                                  np.delete(got.ravel(), 2 * n_walkers + 5))
 
 
-def test_binned_device_sampler_matches_independent_runs_statistically():
+@pytest.mark.parametrize('path', ['resident', 'graph'])
+def test_binned_device_sampler_matches_independent_runs_statistically(path, monkeypatch):
+    monkeypatch.setenv('MCD_NO_RESIDENT_CHAIN', '1' if path == 'graph' else '0')
+    monkeypatch.setenv('MCD_FORCE_RESIDENT_CHAIN', '1' if path == 'resident' else '0')
     fit, truth = _binned(n_stars=1500, seed=9)
     fit.parameters['sigma_max'].set(initials='rng.lognormal(mean=2.3, sigma=0.3, size=n)')
     fit.parameters['v_maxx'].set(initials='rng.normal(loc=0, scale=3, size=n)')

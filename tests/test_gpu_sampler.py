@@ -10,6 +10,15 @@ from mcmc_dynamics_b200.analysis import ConstantFit, ModelFit
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=['resident', 'graph'])
+def sampler_path(request, monkeypatch):
+    """Both device-sampler engines: whole chains inside one CTA per segment (small catalogues), and
+    the CUDA graph of fused likelihood launches (any size; forced with MCD_NO_RESIDENT_CHAIN=1)."""
+    monkeypatch.setenv('MCD_NO_RESIDENT_CHAIN', '1' if request.param == 'graph' else '0')
+    monkeypatch.setenv('MCD_FORCE_RESIDENT_CHAIN', '1' if request.param == 'resident' else '0')
+    return request.param
+
+
 def _mock_model(n_stars=1500, seed=21, cls=ModelFit):
     data, truth = synthetic.mock_cluster(n_stars, seed=seed)
     model = cls(data)
@@ -18,7 +27,7 @@ def _mock_model(n_stars=1500, seed=21, cls=ModelFit):
     return model, truth
 
 
-def test_device_chain_is_self_consistent_and_reproducible():
+def test_device_chain_is_self_consistent_and_reproducible(sampler_path):
     model, truth = _mock_model()
     pos = synthetic.initial_ball(truth, model.fitted_parameters, 32, seed=3)
     runs = []
@@ -42,7 +51,7 @@ def test_device_chain_is_self_consistent_and_reproducible():
     assert moved.sum() == nacc.sum() - np.any(chain[:, 0, :] != pos, axis=1).sum()
 
 
-def test_device_and_host_samplers_agree_and_recover_the_truth():
+def test_device_and_host_samplers_agree_and_recover_the_truth(sampler_path):
     """Mock recovery (bin/run_tests.py:36-41 scenario): posterior percentiles (runner.py:566-613) of
     the device sampler and of the host stretch move driving the same GPU lnprob agree within
     Monte-Carlo error, and bracket the truth."""
