@@ -66,6 +66,13 @@ struct mcd_handle {
     double *star_dev = nullptr;    // [n] scratch of the per-star entry point
     cudaStream_t stream = nullptr;
     int sm_count = 0, blocks_per_sm = 1;
+    // host-buffer calls replayed as CUDA graphs (H2D theta -> kernel -> D2H result), one per
+    // (walkers per call, prior on/off); dropped whenever a pointer or the routing baked into them changes
+    struct HostGraph {
+        int n_walkers = 0, apply_prior = 0, seen = 0;
+        cudaGraphExec_t exec = nullptr;
+    };
+    HostGraph host_graphs[8];
     // fused cross-GPU reduction (mcd_exchange_attach)
     int xchg_world = 0, xchg_rank = 0, xchg_capacity = 0;
     unsigned long long xchg_epoch = 0;
@@ -73,6 +80,8 @@ struct mcd_handle {
     unsigned long long *xchg_flags[kMaxRanks] = {};
     mcd_info info{};
 };
+
+static void drop_host_graphs(mcd_handle *h);
 
 extern "C" int mcd_abi_version(void) { return MCD_ABI_VERSION; }
 extern "C" const char *mcd_last_error(void) { return g_error; }
@@ -93,6 +102,7 @@ static int validate_routing(const mcd_pack_desc *d) {
 
 static int repack(mcd_handle *h) {
     const mcd_pack_desc &d = h->desc;
+    drop_host_graphs(h);
     h->var.rotation = d.rotation;
     h->var.background = d.background;
     h->var.math_mode = d.math_mode;
@@ -153,9 +163,17 @@ static int repack(mcd_handle *h) {
     return 0;
 }
 
+static void drop_host_graphs(mcd_handle *h) {
+    for (auto &g : h->host_graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g = mcd_handle::HostGraph();
+    }
+}
+
 extern "C" void mcd_destroy(mcd_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    drop_host_graphs(h);
     for (auto &p : h->raw) cudaFree(p);
     for (auto &p : h->cols) cudaFree(p);
     cudaFree(h->icol);
@@ -345,6 +363,7 @@ static void choose_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p)
 static int ensure_scratch(mcd_handle *h, const LaunchParams &p) {
     const size_t need = (size_t)p.n_chunks * p.n_walkers * p.n_segments;
     if (need > h->partials_cap) {
+        drop_host_graphs(h);
         MCD_CUDA(cudaFree(h->partials));
         h->partials = nullptr;
         h->partials_cap = 0;
@@ -353,6 +372,7 @@ static int ensure_scratch(mcd_handle *h, const LaunchParams &p) {
     }
     const size_t need2 = (size_t)p.n_super * p.n_walkers * p.n_segments;
     if (need2 > h->partials2_cap) {
+        drop_host_graphs(h);
         MCD_CUDA(cudaFree(h->partials2));
         h->partials2 = nullptr;
         h->partials2_cap = 0;
@@ -361,6 +381,7 @@ static int ensure_scratch(mcd_handle *h, const LaunchParams &p) {
     }
     const int n_counters = p.n_segments * p.n_groups * (p.n_super + 1);
     if (n_counters > h->counters_cap) {
+        drop_host_graphs(h);
         MCD_CUDA(cudaFree(h->counters));
         h->counters = nullptr;
         h->counters_cap = 0;
@@ -444,6 +465,7 @@ static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double 
 
 static int ensure_staging(mcd_handle *h, size_t theta_doubles, size_t out_doubles) {
     if (theta_doubles > h->theta_cap) {
+        drop_host_graphs(h);
         cudaFree(h->theta_dev);
         cudaFreeHost(h->theta_pin);
         h->theta_dev = h->theta_pin = nullptr;
@@ -454,6 +476,7 @@ static int ensure_staging(mcd_handle *h, size_t theta_doubles, size_t out_double
         h->theta_cap = cap;
     }
     if (out_doubles > h->out_cap) {
+        drop_host_graphs(h);
         cudaFree(h->out_dev);
         cudaFreeHost(h->out_pin);
         h->out_dev = h->out_pin = nullptr;
@@ -475,12 +498,51 @@ static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, dou
     const size_t rows = (size_t)n_walkers * h->n_segments;        // theta is [segments][walkers][theta]
     const size_t nt = rows * h->desc.n_theta;
     if (int rc = ensure_staging(h, nt, rows)) return rc;
-    if (nt) {
-        memcpy(h->theta_pin, theta_host, sizeof(double) * nt);
-        MCD_CUDA(cudaMemcpyAsync(h->theta_dev, h->theta_pin, sizeof(double) * nt, cudaMemcpyHostToDevice, h->stream));
+    if (nt) memcpy(h->theta_pin, theta_host, sizeof(double) * nt);
+
+    // A sampler calls with the same shape thousands of times: from the third call of a shape on, the
+    // copy-in / kernel / copy-out sequence is one graph launch (the first call sizes the scratch
+    // buffers, the second captures).
+    mcd_handle::HostGraph *slot = nullptr;
+    for (auto &g : h->host_graphs)
+        if (g.seen && g.n_walkers == n_walkers && g.apply_prior == apply_prior) slot = &g;
+    if (!slot) {
+        for (auto &g : h->host_graphs)
+            if (!g.seen && !slot) slot = &g;
+        if (slot) {
+            slot->n_walkers = n_walkers;
+            slot->apply_prior = apply_prior;
+        }
     }
-    if (int rc = launch(h, h->theta_dev, n_walkers, h->out_dev, apply_prior, h->stream)) return rc;
-    MCD_CUDA(cudaMemcpyAsync(h->out_pin, h->out_dev, sizeof(double) * rows, cudaMemcpyDeviceToHost, h->stream));
+    auto enqueue = [&]() -> int {
+        if (nt) MCD_CUDA(cudaMemcpyAsync(h->theta_dev, h->theta_pin, sizeof(double) * nt, cudaMemcpyHostToDevice, h->stream));
+        if (int rc = launch(h, h->theta_dev, n_walkers, h->out_dev, apply_prior, h->stream)) return rc;
+        MCD_CUDA(cudaMemcpyAsync(h->out_pin, h->out_dev, sizeof(double) * rows, cudaMemcpyDeviceToHost, h->stream));
+        return 0;
+    };
+    if (slot && slot->exec) {
+        MCD_CUDA(cudaGraphLaunch(slot->exec, h->stream));
+        h->info.launches += 1;
+    } else if (slot && slot->seen == 1) {
+        MCD_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue();
+        cudaGraph_t graph = nullptr;
+        const cudaError_t end = cudaStreamEndCapture(h->stream, &graph);
+        if (rc != 0 || end != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc ? rc : fail(-2, "capturing the host-call graph failed: %s", cudaGetErrorString(end));
+        }
+        const cudaError_t inst = cudaGraphInstantiate(&slot->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (inst != cudaSuccess) {
+            slot->exec = nullptr;
+            return fail(-2, "instantiating the host-call graph failed: %s", cudaGetErrorString(inst));
+        }
+        MCD_CUDA(cudaGraphLaunch(slot->exec, h->stream));
+    } else {
+        if (int rc = enqueue()) return rc;
+    }
+    if (slot) slot->seen += slot->seen < 2 ? 1 : 0;
     MCD_CUDA(cudaStreamSynchronize(h->stream));
     memcpy(out_host, h->out_pin, sizeof(double) * rows);
     return 0;

@@ -155,10 +155,12 @@ def bins_workflow(n_stars=3000, n_walkers=100, n_steps=100):
                        ('v_maxx', 'rng.normal(loc=0, scale=3, size=n)'), ('v_maxy', 'rng.normal(loc=0, scale=3, size=n)')):
         fit.parameters[name].set(initials=expr)
     pos = fit.get_initials(n_walkers)
-    fit(n_walkers=n_walkers, n_steps=5, pos=pos, seed=1)                 # warm-up: pack, graph
-    t0 = time.perf_counter()
-    fit(n_walkers=n_walkers, n_steps=n_steps, pos=pos, seed=1)
-    batched = time.perf_counter() - t0
+    fit(n_walkers=n_walkers, n_steps=5, pos=pos, seed=1)                 # warm-up: pack, kernels loaded
+    batched = 1e30
+    for _ in range(3):                                                   # best of three (host-side jitter)
+        t0 = time.perf_counter()
+        fit(n_walkers=n_walkers, n_steps=n_steps, pos=pos, seed=1)
+        batched = min(batched, time.perf_counter() - t0)
     models = [fit.bin_model(b) for b in range(fit.n_bins)]
     for m in models:
         m.pack()
