@@ -6,24 +6,23 @@ background in velocity and the density prior ``m = density / (density + f_back)`
 The arithmetic lives in ``csrc/mcd_kernels.cu``; these classes only choose the kernel variant.
 """
 import logging
-import os
 
 import numpy as np
 
 from .. import _native
+from .. import config
 from .. import units as u
 from ..parameter import Parameters
 from .runner import Runner
 
 logger = logging.getLogger(__name__)
-_CONFIG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'config')
 
 
 class ConstantFit(Runner):
     MODEL_PARAMETERS = ['v_sys', 'sigma_max', 'v_maxx', 'v_maxy', 'ra_center', 'dec_center']
     OBSERVABLES = {'v': u.km_s, 'verr': u.km_s, 'ra': u.deg, 'dec': u.deg}
 
-    parameters_file = os.path.join(_CONFIG, 'constant.json')
+    parameters_file = config.default_file('constant')
 
     ROTATION = _native.ROT_CONSTANT
     BACKGROUND = _native.BG_NONE
@@ -42,7 +41,7 @@ class ConstantFitGB(ConstantFit):
     MODEL_PARAMETERS = ConstantFit.MODEL_PARAMETERS + ['v_back', 'sigma_back', 'f_back']
     OBSERVABLES = dict(ConstantFit.OBSERVABLES, **{'density': u.dimensionless_unscaled})
 
-    parameters_file = os.path.join(_CONFIG, 'constant_with_background.json')
+    parameters_file = config.default_file('constant_with_background')
 
     BACKGROUND = _native.BG_GAUSSIAN
 

@@ -8,24 +8,23 @@ dispersion profile ``sigma_los = sigma_max / (1 + r^2 / a^2)^(1/4)`` (``model.py
 fitted fraction ``f_back``.
 """
 import logging
-import os
 
 import numpy as np
 
 from .. import _native
+from .. import config
 from .. import units as u
 from ..parameter import Parameters
 from .runner import Runner
 
 logger = logging.getLogger(__name__)
-_CONFIG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'config')
 
 
 class ModelFit(Runner):
     MODEL_PARAMETERS = ['v_sys', 'v_maxx', 'v_maxy', 'r_peak', 'sigma_max', 'a', 'ra_center', 'dec_center']
     OBSERVABLES = {'v': u.km_s, 'verr': u.km_s, 'ra': u.deg, 'dec': u.deg}
 
-    parameters_file = os.path.join(_CONFIG, 'model.json')
+    parameters_file = config.default_file('model')
 
     ROTATION = _native.ROT_RADIAL
     BACKGROUND = _native.BG_NONE
@@ -92,7 +91,7 @@ class ModelFitGB(ModelFit):
     MODEL_PARAMETERS = ModelFit.MODEL_PARAMETERS + ['v_back', 'sigma_back', 'f_back']
     OBSERVABLES = dict(ModelFit.OBSERVABLES, **{'density': u.dimensionless_unscaled})
 
-    parameters_file = os.path.join(_CONFIG, 'model_with_background.json')
+    parameters_file = config.default_file('model_with_background')
 
     BACKGROUND = _native.BG_GAUSSIAN
 
@@ -113,7 +112,7 @@ class ModelFitConstantBackground(ModelFit):
     MODEL_PARAMETERS = ModelFit.MODEL_PARAMETERS + ['f_back', ]
     OBSERVABLES = dict(ModelFit.OBSERVABLES, **{'density': u.dimensionless_unscaled})
 
-    parameters_file = os.path.join(_CONFIG, 'model_with_background.json')
+    parameters_file = config.default_file('model_with_background')
 
     BACKGROUND = _native.BG_FIXED_DENSITY
 
