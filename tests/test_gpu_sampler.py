@@ -114,3 +114,21 @@ def test_emulated_star_shards_add_up():
     assert parts[7] == -np.inf and total[7] == -np.inf
     keep = np.arange(40) != 7
     assert np.allclose(parts.cpu().numpy()[keep], total.cpu().numpy()[keep], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize('n_walkers', [600, 1024])
+def test_many_walkers_several_walker_groups(n_walkers, sampler_path):
+    """More than 256 active walkers per half-step: several walker groups per launch, each accepting in
+    place in the fused kernel; the resident kernel covers up to 512 active walkers per CTA."""
+    model, truth = _mock_model(n_stars=2500, seed=31)
+    pos = synthetic.initial_ball(truth, model.fitted_parameters, n_walkers, seed=9, scale=0.1)
+    s = samplers.DeviceEnsembleSampler(n_walkers, model.n_fitted_parameters, model.pack(), seed=5)
+    s.run_mcmc(pos, 12)
+    chain, lnp = s.chain, s.lnprobability
+    assert chain.shape == (n_walkers, 12, 6) and np.all(np.isfinite(lnp))
+    for step in (0, 11):
+        again = model.lnprob(np.ascontiguousarray(chain[:, step, :]))
+        assert np.allclose(again, lnp[:, step], rtol=1e-12, atol=0)
+    moved = np.any(chain[:, 1:, :] != chain[:, :-1, :], axis=2)
+    assert np.array_equal(moved, lnp[:, 1:] != lnp[:, :-1])
+    assert 0.1 < (s.naccepted / 12.0).mean() < 0.95
