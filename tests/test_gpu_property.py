@@ -84,3 +84,50 @@ def test_c_abi_error_paths(native_lib):
     th[1, 1] = -1.0
     res = empty.lnprob(th)
     assert res[1] == -np.inf and np.all(np.delete(res, 1) == 0.0)
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=list(HealthCheck))
+@given(variant=st.sampled_from(VARIANTS), math_mode=st.sampled_from(['fast', 'plain']), seed=st.integers(0, 10_000),
+       fixed_mask=st.integers(0, 2 ** 11 - 1), arcmin_units=st.booleans())
+def test_random_routing_of_fixed_and_free_parameters(variant, math_mode, seed, fixed_mask, arcmin_units):
+    """Any subset of parameters fixed (at arbitrary in-bounds values), a and r_peak optionally
+    re-expressed in arcmin: the slot map / unit scales compiled at pack time must reproduce the oracle,
+    which resolves parameters per call like the reference (runner.py:143-180)."""
+    model, _, theta, truth = build(variant, n_stars=257, free_centre=True, seed=seed, math_mode=math_mode)
+    names = list(model.parameters)
+    start = theta(1, seed=seed + 3, scale=0.3)[0]
+    for j, name in enumerate(model.fitted_parameters):
+        if (fixed_mask >> names.index(name)) & 1:
+            model.parameters[name].set(value=float(start[j]), fixed=True)
+    if len(model.fitted_parameters) == 0:
+        model.parameters[names[0]].fixed = False
+    oracle = harness.oracle_for(model)
+    free = model.fitted_parameters
+    th = synthetic.initial_ball(dict(truth, v_back=5.0, sigma_back=55.0, f_back=0.3), free, 9, seed=seed + 5, scale=0.2)
+    assert th.shape[1] == len(free)
+    got = model.lnprob(th)
+    want = oracle.lnprob_many(th)
+    assert np.array_equal(np.isinf(got), np.isinf(want))
+    assert harness.relative_error(got, want) < RTOL
+
+
+def test_example_catalogue_of_the_reference():
+    """BASELINE config 1: the reference's example/data/test.csv (6284 stars) placed on the sky
+    (tests/golden/make_c1_fixture.py), ConstantFit with v_sys fixed as in bin/run.py:487-491."""
+    import os
+    from mcmc_dynamics_b200.analysis import ConstantFit
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'c1_example_catalogue.npz'))
+    data = synthetic.reader_from_columns({k: d[k] for k in ('ra', 'dec', 'v', 'verr')})
+    for mode in ('fast', 'plain'):
+        m = ConstantFit(data, math_mode=mode)
+        m.parameters['ra_center'].set(value=float(d['ra_center']), fixed=True)
+        m.parameters['dec_center'].set(value=float(d['dec_center']), fixed=True)
+        m.parameters['v_sys'].set(value=0.0, fixed=True)
+        rng = np.random.default_rng(4)
+        th = np.column_stack([rng.uniform(20, 60, 16), rng.normal(0, 5, 16), rng.normal(0, 5, 16)])
+        got = m.lnprob(th)
+        want = harness.oracle_for(m).lnprob_many(th)
+        assert np.all(np.isfinite(want)) and harness.relative_error(got, want) < RTOL
+    # the packed unit vectors reproduce the catalogue's own position angles: v_los = v_maxx sin - v_maxy cos
+    theta_pa = d['theta']
+    assert np.allclose(np.arctan2(np.sin(theta_pa), np.cos(theta_pa)), theta_pa)
