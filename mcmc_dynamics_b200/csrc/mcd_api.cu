@@ -440,6 +440,9 @@ static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double 
         p.fuse = *fuse;
         p.fuse.enabled = 1;
     }
+    // a handle with an exchange attached is a star shard: every ensemble launch of the device sampler
+    // (fused half-steps, the initial lnprob, the dry runs) is then a collective over the shards
+    if (fuse && h->xchg_world > 1) exchange = true;
     if (exchange) {
         if (h->xchg_world < 2) return fail(-1, "mcd_exchange_attach has not been called on this handle");
         if (h->n_segments > 1) return fail(-1, "the fused cross-GPU reduction does not support segmented handles");
@@ -448,7 +451,7 @@ static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double 
         p.xchg_world = h->xchg_world;
         p.xchg_rank = h->xchg_rank;
         p.xchg_capacity = h->xchg_capacity;
-        p.xchg_epoch = ++h->xchg_epoch;
+        p.xchg_epoch = fuse ? 0 : ++h->xchg_epoch;      // fused half-steps take their tag from the step counter
         for (int r = 0; r < h->xchg_world; ++r) {
             p.xchg_data[r] = h->xchg_data[r];
             p.xchg_flags[r] = h->xchg_flags[r];
@@ -550,7 +553,7 @@ static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, dou
 
 int mcd::launch_ensemble(mcd_handle *h, const double *theta_dev, int n_walkers, double *out_dev, int apply_prior,
                          cudaStream_t stream) {
-    return launch(h, theta_dev, n_walkers, out_dev, apply_prior, stream);
+    return launch(h, theta_dev, n_walkers, out_dev, apply_prior, stream, h && h->xchg_world > 1);
 }
 int mcd::launch_ensemble_fused(mcd_handle *h, int n_walkers, const FuseParams &fuse, cudaStream_t stream) {
     return launch(h, nullptr, n_walkers, nullptr, 1, stream, false, &fuse);
@@ -559,6 +562,7 @@ int mcd::launch_resident_chain(mcd_handle *h, const ChainParams &chain, cudaStre
     if (!h) return fail(-1, "null handle");
     const size_t smem = chain_shared_bytes(h->var, h->max_segment, chain.n_walkers, h->desc.n_theta);
     if (smem == 0) return 1;                 // does not fit one SM's shared memory: not eligible
+    if (h->xchg_world > 1) return 1;         // star shards exchange sums every half-step: launch engine only
     // One SM per segment against the whole machine per launch: take the resident kernel only where its
     // half-step is estimated to be shorter than a launch (~14 us of fixed latency + the same arithmetic
     // spread over all SMs).  Cycle model: FP64-pipe instructions ~ nominal flops per term, 64 lanes per
@@ -606,11 +610,11 @@ extern "C" int mcd_lnprob_partial_device(mcd_handle *h, const double *theta_dev,
 // ------------------------------------------------------------------------------------------
 // fused cross-GPU reduction over symmetric (peer-mapped) memory
 // ------------------------------------------------------------------------------------------
-static size_t exchange_flag_bytes(int world) { return sizeof(unsigned long long) * 2 * world * kMaxXchgGroups; }
+static size_t exchange_flag_bytes(int world) { return sizeof(unsigned long long) * kXchgSlots * world * kMaxXchgGroups; }
 
 extern "C" int mcd_exchange_bytes(int32_t world, int32_t max_walkers, int64_t *bytes_out) {
     if (world < 2 || world > kMaxRanks || max_walkers < 1 || !bytes_out) return fail(-1, "bad exchange geometry");
-    *bytes_out = (int64_t)(exchange_flag_bytes(world) + sizeof(double) * 2 * world * (size_t)max_walkers);
+    *bytes_out = (int64_t)(exchange_flag_bytes(world) + sizeof(double) * kXchgSlots * world * (size_t)max_walkers);
     return 0;
 }
 

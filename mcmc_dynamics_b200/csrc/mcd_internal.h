@@ -14,6 +14,7 @@ constexpr int kMaxTile = 256;      // stars per shared-memory stage
 constexpr int kStages = 2;         // TMA bulk-copy stages in flight per CTA
 constexpr int kMaxRanks = 8;        // GPUs of one box that can share a star-sharded catalogue
 constexpr int kMaxXchgGroups = 64;  // walker groups per call of the fused cross-GPU reduction
+constexpr int kXchgSlots = 4;       // exchange buffers in rotation: 0/1 host-counted calls, 2/3 sampler half-steps
 constexpr int kSuper = 32;         // chunks per super-chunk of the two-level cross-CTA reduction
 constexpr int kWaves = 8;          // CTA waves a large catalogue is cut into (tail balance)
 constexpr double kDeg2Rad = 0.017453292519943295769236907684886;
@@ -113,8 +114,8 @@ struct LaunchParams {
     // for the other shards' sums and adds them in rank order.  xchg_world <= 1: disabled.
     int xchg_world, xchg_rank, xchg_capacity;
     unsigned long long xchg_epoch;                 // call counter, identical on all ranks, starts at 1
-    double *xchg_data[kMaxRanks];                  // rank p's data region  [2][world][capacity]
-    unsigned long long *xchg_flags[kMaxRanks];     // rank p's flag region  [2][world][kMaxXchgGroups]
+    double *xchg_data[kMaxRanks];                  // rank p's data region  [kXchgSlots][world][capacity]
+    unsigned long long *xchg_flags[kMaxRanks];     // rank p's flag region  [kXchgSlots][world][kMaxXchgGroups]
     FuseParams fuse;
 };
 

@@ -497,10 +497,13 @@ __device__ __forceinline__ unsigned int take_ticket(unsigned int *counter) {
 // symmetric memory; parity double-buffers consecutive calls (a rank can be at most one call ahead,
 // because it cannot finish call k+1 before every peer has published call k+1).  Kept out of line so
 // that this cold path does not take part in the register allocation of the star loop.
+// `buffer` selects one of kXchgSlots buffers, `epoch` is the unique, never repeating tag of this call.
+// Consecutive calls must use different slots (a rank can be one call ahead of a peer that is still
+// reading): host-counted calls alternate 0/1 by epoch parity, the sampler's half-steps alternate 2/3.
 static __device__ __noinline__ double exchange_shard_sums(const LaunchParams &P, double total, int w, int group, bool owner,
-                                                   int *timed_out) {
+                                                   int *timed_out, int buffer, unsigned long long epoch) {
     const int tid = threadIdx.x;
-    const int par = (int)(P.xchg_epoch & 1ull);
+    const int par = buffer;
     const size_t slot = ((size_t)par * P.xchg_world + P.xchg_rank) * P.xchg_capacity + w;
     if (tid == 0) *timed_out = 0;
     if (owner) {
@@ -511,7 +514,7 @@ static __device__ __noinline__ double exchange_shard_sums(const LaunchParams &P,
     if (tid < P.xchg_world) {
         // publish: flag[par][my rank][group] on rank `tid` <- epoch (release, system scope)
         unsigned long long *dst = P.xchg_flags[tid] + ((size_t)par * P.xchg_world + P.xchg_rank) * kMaxXchgGroups + group;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(P.xchg_epoch) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(epoch) : "memory");
         // wait: flag[par][rank tid][group] in MY buffer == epoch (acquire, system scope)
         const unsigned long long *src =
             P.xchg_flags[P.xchg_rank] + ((size_t)par * P.xchg_world + tid) * kMaxXchgGroups + group;
@@ -524,7 +527,7 @@ static __device__ __noinline__ double exchange_shard_sums(const LaunchParams &P,
                 *timed_out = 1;
                 break;
             }
-        } while (seen != P.xchg_epoch);
+        } while (seen != epoch);
     }
     __syncthreads();
     if (owner) {
@@ -603,7 +606,16 @@ __device__ __noinline__ void finish_walker_group(const LaunchParams &P, int seg,
         const bool rejected = P.apply_prior && !prior_ok;
         total = rejected ? __longlong_as_double(0xfff0000000000000LL) : total;
     }
-    if (P.xchg_world > 1) total = exchange_shard_sums(P, total, w, group, owner, s_last);
+    if (P.xchg_world > 1) {
+        int slot = (int)(P.xchg_epoch & 1ull);
+        unsigned long long epoch = P.xchg_epoch;
+        if constexpr (FUSE) {
+            // replayed from a CUDA graph: the tag comes from the device-side step counter
+            slot = 2 + P.fuse.half;
+            epoch = (1ull << 62) | (2ull * P.fuse.step[0] + (unsigned long long)P.fuse.half);
+        }
+        total = exchange_shard_sums(P, total, w, group, owner, s_last, slot, epoch);
+    }
     if constexpr (FUSE) {
         // accept or reject in place.  Safe without further synchronisation: the positions of the active
         // half are read only by the CTAs of their own walker group, all of which have finished (ticket),

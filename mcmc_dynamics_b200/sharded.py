@@ -103,6 +103,19 @@ class ShardedLikelihood(object):
             self._dist.all_reduce(partial, op=self._dist.ReduceOp.SUM, group=self.group)
         return partial
 
+    def device_sampler(self, n_walkers, seed, a=2.0):
+        """Device-resident stretch-move sampler over the shards (fused mode only): every rank holds a
+        replica of the ensemble, replays the same CUDA graph with the SAME `seed`, and the fused
+        half-step kernels exchange the shard sums before accepting in place, so all replicas stay
+        bit-identical without any further communication.  A collective: call ``run_mcmc`` with the
+        same arguments on every rank."""
+        if self.world_size > 1 and not self.fused:
+            raise RuntimeError('the sharded device sampler needs the fused cross-GPU reduction')
+        if n_walkers > self.max_walkers:
+            raise ValueError('n_walkers exceeds max_walkers of the exchange buffer')
+        from .sampler import DeviceEnsembleSampler
+        return DeviceEnsembleSampler(n_walkers, self.model.n_fitted_parameters, self.model.pack(), a=a, seed=seed)
+
     def lnprob(self, theta):
         """Host array in, host array out (what the sampler calls): pinned staging, H2D, shard kernel,
         all-reduce, D2H."""
