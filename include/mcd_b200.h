@@ -189,6 +189,10 @@ int mcd_ensemble_set_state(mcd_ensemble *e, const double *pos_host);
 int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_host, double *lnprob_host,
                      int64_t *n_accepted_host);
 int mcd_ensemble_get_state(mcd_ensemble *e, double *pos_host, double *lnprob_host);
+/* which engine the last mcd_ensemble_run took (diagnostics): *engine 1 = resident chain kernel (the
+ * catalogue stays in shared memory for the whole run), 2 = CUDA graph of fused likelihood launches,
+ * 0 = nothing run yet; *ctas_per_segment = CTAs sharing one segment's stars in the resident kernel */
+int mcd_ensemble_engine(const mcd_ensemble *e, int32_t *engine, int32_t *ctas_per_segment);
 
 /* Roofline denominators measured on the device the caller is on: dependent-free DFMA chains
  * (TFLOP/s, FMA = 2) and a streaming read (GB/s). */

@@ -88,6 +88,7 @@ SYMBOLS = {
     'mcd_ensemble_set_state': (ctypes.c_int, [_vp, _c_double_p]),
     'mcd_ensemble_run': (ctypes.c_int, [_vp, ctypes.c_int32, _c_double_p, _c_double_p, _c_int64_p]),
     'mcd_ensemble_get_state': (ctypes.c_int, [_vp, _c_double_p, _c_double_p]),
+    'mcd_ensemble_engine': (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     'mcd_measure_fp64_peak': (ctypes.c_int, [ctypes.c_int32, _c_double_p, _c_double_p]),
     'mcd_measure_read_bandwidth': (ctypes.c_int, [ctypes.c_int32, ctypes.c_int64, _c_double_p]),
 }

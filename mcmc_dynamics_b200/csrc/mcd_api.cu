@@ -60,6 +60,11 @@ struct mcd_handle {
     size_t partials_cap = 0, partials2_cap = 0;
     unsigned int *counters = nullptr;
     int counters_cap = 0;
+    // resident chains with several CTAs per segment: slice sums, barrier counters, status word
+    double *group_sums = nullptr;
+    size_t group_sums_cap = 0;
+    unsigned long long *group_arrivals = nullptr;   // [n_segments] counters followed by the status word
+    int chain_group = 0;           // CTAs per segment of the last resident launch
     // staging for the host-buffer entry points
     double *theta_dev = nullptr, *out_dev = nullptr, *theta_pin = nullptr, *out_pin = nullptr;
     size_t theta_cap = 0, out_cap = 0;
@@ -182,6 +187,8 @@ extern "C" void mcd_destroy(mcd_handle *h) {
     cudaFree(h->partials);
     cudaFree(h->partials2);
     cudaFree(h->counters);
+    cudaFree(h->group_sums);
+    cudaFree(h->group_arrivals);
     cudaFree(h->theta_dev);
     cudaFree(h->out_dev);
     cudaFree(h->star_dev);
@@ -560,31 +567,86 @@ int mcd::launch_ensemble_fused(mcd_handle *h, int n_walkers, const FuseParams &f
 }
 int mcd::launch_resident_chain(mcd_handle *h, const ChainParams &chain, cudaStream_t stream) {
     if (!h) return fail(-1, "null handle");
-    const size_t smem = chain_shared_bytes(h->var, h->max_segment, chain.n_walkers, h->desc.n_theta);
-    if (smem == 0) return 1;                 // does not fit one SM's shared memory: not eligible
     if (h->xchg_world > 1) return 1;         // star shards exchange sums every half-step: launch engine only
-    // One SM per segment against the whole machine per launch: take the resident kernel only where its
-    // half-step is estimated to be shorter than a launch (~14 us of fixed latency + the same arithmetic
-    // spread over all SMs).  Cycle model: FP64-pipe instructions ~ nominal flops per term, 64 lanes per
-    // SM, 60 % pipe efficiency, 1.9 GHz.  MCD_FORCE_RESIDENT_CHAIN=1 overrides (tests).
-    {
-        const char *force = getenv("MCD_FORCE_RESIDENT_CHAIN");
-        const double flops = (double)variant_flops_per_term(h->var);
-        const double ns = 0.5 * chain.n_walkers;
-        const double per_sm = 64.0 * 1.9e9 * 0.6;
-        const double waves = std::ceil((double)h->n_segments / std::max(1, h->sm_count));
-        const double resident = waves * (2e-6 + ns * (double)h->max_segment * flops / per_sm);
-        const double launched = 14e-6 + ns * (double)h->n * flops / (per_sm * std::max(1, h->sm_count));
-        if (!(force && force[0] == '1') && resident > launched) return 1;
+    if (chain.n_walkers > kChainMaxWalkers) return 1;
+    // `group` CTAs (one per SM) hold one segment's stars in shared memory.  Take the resident kernel
+    // only where its half-step is estimated to be shorter than a launch (~14 us of fixed latency + the
+    // same arithmetic spread over all SMs), with the group size that minimises the estimate.  Cycle
+    // model: FP64-pipe instructions ~ nominal flops per term, 64 lanes per SM, 60 % pipe efficiency,
+    // 1.9 GHz; a group barrier ~1.2 us; the slice sums come back from L2 in batches of 8 loads per
+    // thread at ~0.7 us each.  MCD_FORCE_RESIDENT_CHAIN=1 skips the comparison with the launch engine,
+    // MCD_CHAIN_GROUP=g fixes the group size (tests, experiments).
+    const char *force = getenv("MCD_FORCE_RESIDENT_CHAIN");
+    const char *fixed = getenv("MCD_CHAIN_GROUP");
+    const double flops = (double)variant_flops_per_term(h->var);
+    const double ns = 0.5 * chain.n_walkers;
+    const double per_sm = 64.0 * 1.9e9 * 0.6;
+    const int sms = std::max(1, h->sm_count);
+    const int max_group = h->n_segments <= sms ? sms / h->n_segments : 1;
+    int group = 0;
+    long long per_cta = 0;
+    size_t smem = 0;
+    double resident = 1e30;
+    for (int g = 1; g <= max_group; ++g) {
+        if (fixed && fixed[0] && atoi(fixed) != g) continue;
+        const long long per = (((h->max_segment + g - 1) / g) + 1) & ~1LL;
+        const size_t bytes = chain_shared_bytes(h->var, per, chain.n_walkers, h->desc.n_theta);
+        if (bytes == 0) continue;
+        const double wl = std::min(ns, (double)kChainBlock);
+        double t = 0.8e-6 + ns * (double)per * flops / per_sm;
+        if (g > 1) t += 1.2e-6 + std::ceil(g * wl / (8.0 * kChainBlock)) * 0.7e-6;
+        else t *= std::ceil((double)h->n_segments / sms);
+        if (t < resident) {
+            resident = t;
+            group = g;
+            per_cta = per;
+            smem = bytes;
+        }
     }
+    if (group == 0) return 1;                // does not fit the shared memory of the SMs it may use
+    const double launched = 14e-6 + ns * (double)h->n * flops / (per_sm * sms);
+    if (!(force && force[0] == '1') && resident > launched) return 1;
+
     MCD_CUDA(cudaSetDevice(h->device));
     LaunchParams p{};
     fill_params(h, p);
     p.apply_prior = 1;
     ChainParams c = chain;
-    c.max_segment_padded = (int)(((h->max_segment + 15) / 16) * 16);
-    MCD_CUDA(launch_chain(h->var, p, c, smem, stream));
+    c.max_segment_padded = (int)(((per_cta + 15) / 16) * 16);
+    c.group = group;
+    c.stars_per_cta = (int)per_cta;
+    if (group > 1) {
+        const size_t need = (size_t)2 * h->n_segments * group * kChainBlock;
+        if (need > h->group_sums_cap) {
+            if (h->group_sums) cudaFree(h->group_sums);
+            h->group_sums = nullptr;
+            h->group_sums_cap = 0;
+            MCD_CUDA(cudaMalloc(&h->group_sums, sizeof(double) * need));
+            h->group_sums_cap = need;
+        }
+        if (!h->group_arrivals) MCD_CUDA(cudaMalloc(&h->group_arrivals, sizeof(unsigned long long) * (h->n_segments + 1)));
+        MCD_CUDA(cudaMemsetAsync(h->group_arrivals, 0, sizeof(unsigned long long) * (h->n_segments + 1), stream));
+        c.group_sums = h->group_sums;
+        c.group_arrivals = h->group_arrivals;
+        c.status = reinterpret_cast<int *>(h->group_arrivals + h->n_segments);
+    }
+    const cudaError_t err = launch_chain(h->var, p, c, smem, stream);
+    if (err != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (group > 1) return 1;             // e.g. no cooperative launch in this context: launch engine instead
+        return fail(-2, "resident chain launch: %s", cudaGetErrorString(err));
+    }
     h->info.launches += 1;
+    h->chain_group = group;
+    return 0;
+}
+int mcd::resident_chain_group(const mcd_handle *h) { return h ? h->chain_group : 0; }
+int mcd::resident_chain_status(mcd_handle *h, cudaStream_t stream) {
+    if (!h || !h->group_arrivals) return 0;
+    int status = 0;
+    MCD_CUDA(cudaMemcpyAsync(&status, h->group_arrivals + h->n_segments, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    MCD_CUDA(cudaStreamSynchronize(stream));
+    if (status) return fail(-2, "resident chain: a CTA group did not meet at its barrier");
     return 0;
 }
 int mcd::handle_device(const mcd_handle *h) { return h->device; }

@@ -68,6 +68,11 @@ struct ChainParams {
     int n_walkers;                // W per segment
     int n0;                       // red half
     int max_segment_padded;       // column stride in shared memory (stars, multiple of 16)
+    int group;                    // CTAs sharing one segment's stars (1: one CTA per segment, no grid barrier)
+    int stars_per_cta;            // even; CTA r of a group owns stars [r * stars_per_cta, ...)
+    double *group_sums;           // [2][S][group][kChainBlock] per-CTA sums of a half-step (group > 1)
+    unsigned long long *group_arrivals;   // [S] barrier counters, zero at launch (group > 1)
+    int *status;                  // set non-zero if a barrier wait ran into its time limit
     unsigned int step0;           // global step counter at entry
     double a;
     unsigned long long seed;
@@ -134,7 +139,7 @@ cudaError_t launch_lnlike(const Variant &v, const LaunchParams &p, cudaStream_t 
 // (always PLAIN arithmetic)
 cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out, int membership, cudaStream_t stream);
 // resident-chain kernel: shared memory it needs for this problem, or 0 if the problem does not fit
-size_t chain_shared_bytes(const Variant &v, long long max_segment, int n_walkers, int n_theta);
+size_t chain_shared_bytes(const Variant &v, long long stars_per_cta, int n_walkers, int n_theta);
 cudaError_t launch_chain(const Variant &v, const LaunchParams &p, const ChainParams &c, size_t smem, cudaStream_t stream);
 // resident CTAs per SM of the lnlike kernel of this variant (occupancy API)
 int lnlike_blocks_per_sm(const Variant &v);
@@ -147,6 +152,9 @@ int launch_ensemble(mcd_handle *h, const double *theta_dev, int n_walkers, doubl
 int launch_ensemble_fused(mcd_handle *h, int n_walkers, const FuseParams &fuse, cudaStream_t stream);
 // whole chains in one launch when the catalogue fits shared memory; returns 1 if not eligible
 int launch_resident_chain(mcd_handle *h, const ChainParams &chain, cudaStream_t stream);
+// after the stream was synchronised: < 0 if a group barrier of the last resident launch timed out
+int resident_chain_status(mcd_handle *h, cudaStream_t stream);
+int resident_chain_group(const mcd_handle *h);   // CTAs per segment of the last resident launch
 int handle_device(const mcd_handle *h);
 // record the thread-local message returned by mcd_last_error() and hand back `code`
 int set_error(int code, const char *fmt, ...);

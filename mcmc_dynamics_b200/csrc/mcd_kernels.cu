@@ -770,15 +770,38 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
 }
 
 // ------------------------------------------------------------------------------------------
-// resident chains: whole stretch-move runs of small catalogues inside one CTA per segment
+// resident chains: whole stretch-move runs with the catalogue held in shared memory
 // ------------------------------------------------------------------------------------------
 // For catalogues of a few thousand stars (the per-radial-bin fits of bin/run.py:179-190 and
 // bin/run_tests.py:81-97, BASELINE config 1) a likelihood launch is < 1 us of arithmetic inside
-// ~13 us of launch, first-tile and cross-CTA reduction latency.  Here one CTA per segment loads the
-// segment's packed columns into shared memory ONCE, keeps positions and log-probabilities of its
-// ensemble in shared memory, and runs every emcee iteration (red/blue split, proposals, likelihood
-// over all stars, acceptance) with __syncthreads as the only synchronisation.  Same move, same
-// Philox counters and the same per-term arithmetic (`term<>`) as the launch-per-half-step sampler.
+// ~13 us of launch, first-tile and cross-CTA reduction latency.  Here `group` CTAs per segment load
+// the segment's packed columns into their shared memory ONCE (each CTA an even-sized slice of the
+// stars), every CTA keeps positions and log-probabilities of the whole ensemble in shared memory, and
+// every emcee iteration (red/blue split, proposals, likelihood over all stars, acceptance) runs inside
+// the one launch.  With group == 1 __syncthreads is the only synchronisation.  With group > 1 (a
+// cooperative launch: all CTAs are resident together) the CTAs of a segment exchange their slice sums
+// through L2 once per half-step behind an arrive-and-wait barrier on a global counter, every CTA adds
+// the slices in the same order and so takes the same accept/reject decisions on its own copy of the
+// ensemble.  Same move, same Philox counters and the same per-term arithmetic (`term<>`) as the
+// launch-per-half-step sampler.
+static __device__ __noinline__ void group_barrier(unsigned long long *arrivals, unsigned long long target, int *status) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long seen;
+        asm volatile("atom.add.acq_rel.gpu.global.u64 %0, [%1], 1;" : "=l"(seen) : "l"(arrivals) : "memory");
+        seen += 1;
+        const long long t0 = clock64();
+        while (seen < target) {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(arrivals) : "memory");
+            if (clock64() - t0 > 8000000000LL) {      // ~4 s: a CTA of the group never arrived
+                atomicExch(status, 1);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 template <int ROT, int FREE, int BG, int MATH>
 __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constant__ LaunchParams P,
                                                             const __grid_constant__ ChainParams C) {
@@ -786,13 +809,20 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
     constexpr bool ICOL = has_icol(BG, MATH);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
-    const int seg = blockIdx.x;
+    const int G = C.group;
+    const int seg = blockIdx.x / G;
+    const int member = blockIdx.x - seg * G;          // this CTA's place in the segment's group
+    const int n_segments = gridDim.x / G;
     const int W = C.n_walkers, NP = P.n_theta;
     const int stride = C.max_segment_padded;
 
     const long long seg_first = P.seg_begin ? P.seg_begin[seg] : 0;
-    const int n = (int)((P.seg_begin ? P.seg_begin[seg + 1] : P.n_stars) - seg_first);
-    const long long offset = P.seg_begin ? P.seg_packed[seg] : 0;
+    const int seg_stars = (int)((P.seg_begin ? P.seg_begin[seg + 1] : P.n_stars) - seg_first);
+    const int first = min(seg_stars, member * C.stars_per_cta);
+    const int n = min(seg_stars - first, C.stars_per_cta);             // stars of this CTA's slice
+    const long long offset = (P.seg_begin ? P.seg_packed[seg] : 0) + first;
+    unsigned long long barrier_target = 0;
+    int parity = 0;
 
     // shared-memory carve-up (every block is a multiple of 16 bytes)
     double *cols = reinterpret_cast<double *>(smem_raw);                       // [NC][stride]
@@ -804,11 +834,10 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
     int *perm = reinterpret_cast<int *>(keys + W);                            // [W]
     int *nacc = perm + W;                                                     // [W]
 
-    const int padded = ((n + 15) / 16) * 16;
     for (int c = 0; c < NC; ++c)
-        for (int i = tid; i < padded; i += kChainBlock) cols[(size_t)c * stride + i] = P.cols[c][offset + i];
+        for (int i = tid; i < n; i += kChainBlock) cols[(size_t)c * stride + i] = P.cols[c][offset + i];
     if (ICOL)
-        for (int i = tid; i < padded; i += kChainBlock) icol[i] = P.icol[offset + i];
+        for (int i = tid; i < n; i += kChainBlock) icol[i] = P.icol[offset + i];
     for (int i = tid; i < W * NP; i += kChainBlock) pos[i] = C.pos[(size_t)seg * W * NP + i];
     for (int i = tid; i < W; i += kChainBlock) {
         lnp[i] = C.lnp[(size_t)seg * W + i];
@@ -887,10 +916,37 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
                 }
                 red[tid] = (valid && Wk.prior_ok) ? A.value() : 0.0;
                 __syncthreads();
+                if (G > 1) {
+                    // slice sums of this CTA -> L2, wait for the group, add every CTA's in member order
+                    double *sums = C.group_sums + ((size_t)(parity * n_segments + seg) * G) * kChainBlock;
+                    if (valid && slice == 0) {
+                        double mine = red[lane];
+                        for (int j = 1; j < slices; ++j) mine += red[j * wl + lane];
+                        sums[(size_t)member * kChainBlock + lane] = mine;
+                    }
+                    barrier_target += (unsigned long long)G;
+                    group_barrier(C.group_arrivals + seg, barrier_target, C.status);
+                    double acc = 0.0;
+                    if (valid) {
+                        for (int g0 = slice; g0 < G; g0 += 8 * slices) {
+                            double v[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int g = g0 + u * slices;
+                                v[u] = g < G ? __ldcg(&sums[(size_t)g * kChainBlock + lane]) : 0.0;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) acc += v[u];
+                        }
+                    }
+                    red[tid] = acc;
+                    parity ^= 1;
+                    __syncthreads();
+                }
                 if (valid && slice == 0) {
                     double total = red[lane];
                     for (int j = 1; j < slices; ++j) total += red[j * wl + lane];
-                    if (MATH == MCD_MATH_FAST) total = fma((double)n, -0.5 * kLn2Pi, total);
+                    if (MATH == MCD_MATH_FAST) total = fma((double)seg_stars, -0.5 * kLn2Pi, total);
                     if (!Wk.prior_ok) total = __longlong_as_double(0xfff0000000000000LL);
                     double u0, u1;
                     uniforms(C.seed, step, (uint32_t)half, (uint32_t)(seg * W + k), 1u, u0, u1);
@@ -905,14 +961,15 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
                 __syncthreads();
             }
         }
-        if (C.chain) {
-            const size_t rows = (size_t)gridDim.x * W;
+        if (C.chain && member == 0) {
+            const size_t rows = (size_t)n_segments * W;
             double *dst = C.chain + ((size_t)it * rows + (size_t)seg * W) * NP;
             for (int i = tid; i < W * NP; i += kChainBlock) dst[i] = pos[i];
             double *dl = C.chain_lnp + (size_t)it * rows + (size_t)seg * W;
             for (int i = tid; i < W; i += kChainBlock) dl[i] = lnp[i];
         }
     }
+    if (member != 0) return;
     for (int i = tid; i < W * NP; i += kChainBlock) C.pos[(size_t)seg * W * NP + i] = pos[i];
     for (int i = tid; i < W; i += kChainBlock) {
         C.lnp[(size_t)seg * W + i] = lnp[i];
@@ -1000,7 +1057,14 @@ static cudaError_t chain_one(const LaunchParams &p, const ChainParams &c, size_t
     cudaError_t err = cudaFuncSetAttribute(chain_kernel<ROT, FREE, BG, MATH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem);
     if (err != cudaSuccess) return err;
-    chain_kernel<ROT, FREE, BG, MATH><<<(unsigned)std::max(1, p.n_segments), kChainBlock, smem, stream>>>(p, c);
+    const unsigned grid = (unsigned)(std::max(1, p.n_segments) * std::max(1, c.group));
+    if (c.group > 1) {
+        // the CTAs of a group wait for each other: cooperative launch, all of them resident together
+        void *args[] = {const_cast<LaunchParams *>(&p), const_cast<ChainParams *>(&c)};
+        return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&chain_kernel<ROT, FREE, BG, MATH>), dim3(grid),
+                                           dim3(kChainBlock), args, smem, stream);
+    }
+    chain_kernel<ROT, FREE, BG, MATH><<<grid, kChainBlock, smem, stream>>>(p, c);
     return cudaGetLastError();
 }
 
@@ -1060,9 +1124,9 @@ static size_t chain_bytes(int nc, bool icol, long long stride, int n_walkers, in
     return (b + 15) & ~(size_t)15;
 }
 
-size_t chain_shared_bytes(const Variant &v, long long max_segment, int n_walkers, int n_theta) {
+size_t chain_shared_bytes(const Variant &v, long long stars_per_cta, int n_walkers, int n_theta) {
     if (n_walkers > kChainMaxWalkers) return 0;
-    const long long stride = ((max_segment + 15) / 16) * 16;
+    const long long stride = ((stars_per_cta + 15) / 16) * 16;
     const size_t b = chain_bytes(variant_columns(v), variant_has_icol(v), stride, n_walkers, n_theta);
     return b <= (size_t)220 * 1024 ? b : 0;                // 227 KB per CTA on sm_100a, minus static use
 }

@@ -284,6 +284,8 @@ extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_
             if (lnprob_host) ENS_CUDA(cudaMemcpyAsync(lnprob_host + (size_t)done * rows, E.chain_lnp,
                                                       sizeof(double) * todo * rows, cudaMemcpyDeviceToHost, e->stream));
             ENS_CUDA(cudaStreamSynchronize(e->stream));
+            rc = resident_chain_status(e->h, e->stream);
+            if (rc != 0) break;
             e->steps_done += (unsigned int)todo;
             done += todo;
         }
@@ -334,6 +336,12 @@ extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_
     return rc;
 }
 
+extern "C" int mcd_ensemble_engine(const mcd_ensemble *e, int32_t *engine, int32_t *ctas_per_segment) {
+    if (!e) return -1;
+    if (engine) *engine = e->last_path;
+    if (ctas_per_segment) *ctas_per_segment = e->last_path == 1 ? resident_chain_group(e->h) : 0;
+    return 0;
+}
 extern "C" int mcd_ensemble_get_state(mcd_ensemble *e, double *pos_host, double *lnprob_host) {
     if (!e) return -1;
     ENS_CUDA(cudaSetDevice(e->device));

@@ -230,6 +230,14 @@ class DeviceEnsembleSampler(object):
         self._last_pos = pos.copy()
         return pos, last, None
 
+    @property
+    def engine(self):
+        """``(name, ctas_per_segment)`` of the last ``run_mcmc``: ``'resident'`` (whole run inside one
+        kernel, catalogue in shared memory) or ``'graph'`` (CUDA graph of likelihood launches)."""
+        kind, group = ctypes.c_int32(0), ctypes.c_int32(0)
+        self._lib.mcd_ensemble_engine(self._handle, ctypes.byref(kind), ctypes.byref(group))
+        return {0: None, 1: 'resident', 2: 'graph'}[kind.value], group.value
+
     def close(self):
         if self._handle is not None:
             self._lib.mcd_ensemble_destroy(self._handle)

@@ -10,12 +10,17 @@ from mcmc_dynamics_b200.analysis import ConstantFit, ModelFit
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=['resident', 'graph'])
+@pytest.fixture(params=['resident', 'resident-1', 'resident-7', 'graph'])
 def sampler_path(request, monkeypatch):
-    """Both device-sampler engines: whole chains inside one CTA per segment (small catalogues), and
-    the CUDA graph of fused likelihood launches (any size; forced with MCD_NO_RESIDENT_CHAIN=1)."""
+    """The device-sampler engines: whole chains inside one kernel with the catalogue in shared memory
+    (group size chosen by the library, one CTA, seven CTAs with ragged star slices), and the CUDA
+    graph of fused likelihood launches (any size; forced with MCD_NO_RESIDENT_CHAIN=1)."""
     monkeypatch.setenv('MCD_NO_RESIDENT_CHAIN', '1' if request.param == 'graph' else '0')
-    monkeypatch.setenv('MCD_FORCE_RESIDENT_CHAIN', '1' if request.param == 'resident' else '0')
+    monkeypatch.setenv('MCD_FORCE_RESIDENT_CHAIN', '1' if request.param.startswith('resident') else '0')
+    if '-' in request.param:
+        monkeypatch.setenv('MCD_CHAIN_GROUP', request.param.split('-')[1])
+    else:
+        monkeypatch.delenv('MCD_CHAIN_GROUP', raising=False)
     return request.param
 
 
@@ -35,6 +40,10 @@ def test_device_chain_is_self_consistent_and_reproducible(sampler_path):
         s = samplers.DeviceEnsembleSampler(32, model.n_fitted_parameters, model.pack(), seed=1234)
         s.run_mcmc(pos, 40)
         runs.append((s.chain.copy(), s.lnprobability.copy(), s.naccepted.copy()))
+        kind, group = s.engine
+        assert kind == sampler_path.split('-')[0]
+        if '-' in sampler_path:
+            assert group == int(sampler_path.split('-')[1])
     chain, lnp, nacc = runs[0]
     assert chain.shape == (32, 40, 6) and lnp.shape == (32, 40)
     assert np.array_equal(chain, runs[1][0]) and np.array_equal(lnp, runs[1][1])     # same seed, same chain
@@ -132,3 +141,33 @@ def test_many_walkers_several_walker_groups(n_walkers, sampler_path):
     moved = np.any(chain[:, 1:, :] != chain[:, :-1, :], axis=2)
     assert np.array_equal(moved, lnp[:, 1:] != lnp[:, :-1])
     assert 0.1 < (s.naccepted / 12.0).mean() < 0.95
+
+
+@pytest.mark.parametrize('cls,n_stars,n_walkers', [(ConstantFit, 3001, 16), (ModelFit, 10_000, 128), (ModelFit, 40_000, 32)])
+def test_resident_chain_groups_walk_the_same_chain(cls, n_stars, n_walkers, monkeypatch):
+    """One CTA, a ragged group and a whole-GPU group hold different slices of the stars but draw the same
+    proposals from the same counters: their chains agree to rounding of the slice sums until the
+    first accept/reject decision that falls inside that rounding (none in these few steps)."""
+    model, truth = _mock_model(n_stars=n_stars, seed=31, cls=cls)
+    pos = synthetic.initial_ball(truth, model.fitted_parameters, n_walkers, seed=6)
+    monkeypatch.setenv('MCD_FORCE_RESIDENT_CHAIN', '1')
+    monkeypatch.setenv('MCD_NO_RESIDENT_CHAIN', '0')
+    chains = {}
+    for group in (1, 7, 40, 148):
+        if n_stars / group > 6000:
+            continue                      # a slice of that size does not fit one SM's shared memory
+        monkeypatch.setenv('MCD_CHAIN_GROUP', str(group))
+        s = samplers.DeviceEnsembleSampler(n_walkers, model.n_fitted_parameters, model.pack(), seed=99)
+        s.run_mcmc(pos, 12)
+        kind, used = s.engine
+        if kind != 'resident':
+            continue                      # fewer SMs than the group asks for
+        assert used == group
+        chains[group] = (s.chain.copy(), s.lnprobability.copy())
+    assert len(chains) >= 2
+    ref_chain, ref_lnp = chains[sorted(chains)[0]]
+    for group, (chain, lnp) in chains.items():
+        assert np.allclose(chain, ref_chain, rtol=1e-10, atol=0), group
+        assert np.allclose(lnp, ref_lnp, rtol=1e-12, atol=0), group
+    again = model.lnprob(np.ascontiguousarray(ref_chain[:, -1, :]))
+    assert np.allclose(again, ref_lnp[:, -1], rtol=1e-12, atol=0)
