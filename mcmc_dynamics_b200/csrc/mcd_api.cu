@@ -60,10 +60,9 @@ struct mcd_handle {
     size_t partials_cap = 0, partials2_cap = 0;
     unsigned int *counters = nullptr;
     int counters_cap = 0;
-    // resident chains with several CTAs per segment: slice sums, barrier counters, status word
-    double *group_sums = nullptr;
+    // resident chains with several CTAs per segment
+    unsigned char *group_sums = nullptr;            // status word (16 bytes) followed by the tagged sums
     size_t group_sums_cap = 0;
-    unsigned long long *group_arrivals = nullptr;   // [n_segments] counters followed by the status word
     int chain_group = 0;           // CTAs per segment of the last resident launch
     // staging for the host-buffer entry points
     double *theta_dev = nullptr, *out_dev = nullptr, *theta_pin = nullptr, *out_pin = nullptr;
@@ -188,7 +187,6 @@ extern "C" void mcd_destroy(mcd_handle *h) {
     cudaFree(h->partials2);
     cudaFree(h->counters);
     cudaFree(h->group_sums);
-    cudaFree(h->group_arrivals);
     cudaFree(h->theta_dev);
     cudaFree(h->out_dev);
     cudaFree(h->star_dev);
@@ -565,6 +563,13 @@ int mcd::launch_ensemble(mcd_handle *h, const double *theta_dev, int n_walkers, 
 int mcd::launch_ensemble_fused(mcd_handle *h, int n_walkers, const FuseParams &fuse, cudaStream_t stream) {
     return launch(h, nullptr, n_walkers, nullptr, 1, stream, false, &fuse);
 }
+// Self-validating tagged words save two L2 round trips per half-step but have every thread polling:
+// measured on B200 they win while group^2 * walkers (words read per half-step) stays below ~10^5
+// (C1 and the radial bins), and lose to counter + plain reads above (C2..C4).
+static bool chain_tagged_exchange(int group, double walkers_per_exchange) {
+    return (double)group * group * walkers_per_exchange <= 1.0e5;
+}
+
 int mcd::launch_resident_chain(mcd_handle *h, const ChainParams &chain, cudaStream_t stream) {
     if (!h) return fail(-1, "null handle");
     if (h->xchg_world > 1) return 1;         // star shards exchange sums every half-step: launch engine only
@@ -573,8 +578,8 @@ int mcd::launch_resident_chain(mcd_handle *h, const ChainParams &chain, cudaStre
     // only where its half-step is estimated to be shorter than a launch (~14 us of fixed latency + the
     // same arithmetic spread over all SMs), with the group size that minimises the estimate.  Cycle
     // model: FP64-pipe instructions ~ nominal flops per term, 64 lanes per SM, 60 % pipe efficiency,
-    // 1.9 GHz; a group barrier ~1.2 us; the slice sums come back from L2 in batches of 8 loads per
-    // thread at ~0.7 us each.  MCD_FORCE_RESIDENT_CHAIN=1 skips the comparison with the launch engine,
+    // 1.9 GHz; the exchange of slice sums ~1 us (tagged words) or ~2.2 us (counter, then reads) of L2
+    // latency plus the traffic of every CTA reading every CTA's sums.  MCD_FORCE_RESIDENT_CHAIN=1 skips the comparison with the launch engine,
     // MCD_CHAIN_GROUP=g fixes the group size (tests, experiments).
     const char *force = getenv("MCD_FORCE_RESIDENT_CHAIN");
     const char *fixed = getenv("MCD_CHAIN_GROUP");
@@ -582,7 +587,7 @@ int mcd::launch_resident_chain(mcd_handle *h, const ChainParams &chain, cudaStre
     const double ns = 0.5 * chain.n_walkers;
     const double per_sm = 64.0 * 1.9e9 * 0.6;
     const int sms = std::max(1, h->sm_count);
-    const int max_group = h->n_segments <= sms ? sms / h->n_segments : 1;
+    const int max_group = h->n_segments <= sms ? std::min(sms / h->n_segments, (int)kChainBlock) : 1;
     int group = 0;
     long long per_cta = 0;
     size_t smem = 0;
@@ -594,7 +599,7 @@ int mcd::launch_resident_chain(mcd_handle *h, const ChainParams &chain, cudaStre
         if (bytes == 0) continue;
         const double wl = std::min(ns, (double)kChainBlock);
         double t = 0.8e-6 + ns * (double)per * flops / per_sm;
-        if (g > 1) t += 1.2e-6 + std::ceil(g * wl / (8.0 * kChainBlock)) * 0.7e-6;
+        if (g > 1) t += (chain_tagged_exchange(g, wl) ? 1.0e-6 : 2.2e-6) + (double)g * g * wl * 8.0 / 6e12;
         else t *= std::ceil((double)h->n_segments / sms);
         if (t < resident) {
             resident = t;
@@ -616,19 +621,25 @@ int mcd::launch_resident_chain(mcd_handle *h, const ChainParams &chain, cudaStre
     c.group = group;
     c.stars_per_cta = (int)per_cta;
     if (group > 1) {
-        const size_t need = (size_t)2 * h->n_segments * group * kChainBlock;
+        const int larger_half = chain.n_walkers - chain.n0 > chain.n0 ? chain.n_walkers - chain.n0 : chain.n0;
+        c.sum_stride = std::min((int)kChainBlock, larger_half);
+        const size_t slots = (size_t)2 * h->n_segments * group * c.sum_stride;
+        const size_t header = 16 + (((size_t)h->n_segments * 8 + 15) & ~(size_t)15);     // status word, arrival counters
+        const size_t need = header + slots * 16;
         if (need > h->group_sums_cap) {
             if (h->group_sums) cudaFree(h->group_sums);
             h->group_sums = nullptr;
             h->group_sums_cap = 0;
-            MCD_CUDA(cudaMalloc(&h->group_sums, sizeof(double) * need));
+            MCD_CUDA(cudaMalloc(&h->group_sums, need));
             h->group_sums_cap = need;
         }
-        if (!h->group_arrivals) MCD_CUDA(cudaMalloc(&h->group_arrivals, sizeof(unsigned long long) * (h->n_segments + 1)));
-        MCD_CUDA(cudaMemsetAsync(h->group_arrivals, 0, sizeof(unsigned long long) * (h->n_segments + 1), stream));
-        c.group_sums = h->group_sums;
-        c.group_arrivals = h->group_arrivals;
-        c.status = reinterpret_cast<int *>(h->group_arrivals + h->n_segments);
+        MCD_CUDA(cudaMemsetAsync(h->group_sums, 0, need, stream));      // tag 0 = nothing published yet
+        c.status = reinterpret_cast<int *>(h->group_sums);
+        c.group_arrivals = reinterpret_cast<unsigned long long *>(h->group_sums + 16);
+        c.group_sums = reinterpret_cast<TaggedSum *>(h->group_sums + header);
+        c.tagged = chain_tagged_exchange(group, c.sum_stride) ? 1 : 0;
+        if (const char *mode = getenv("MCD_CHAIN_EXCHANGE"))      // "tagged" / "counter": experiments, tests
+            c.tagged = mode[0] == 't' ? 1 : (mode[0] == 'c' ? 0 : c.tagged);
     }
     const cudaError_t err = launch_chain(h->var, p, c, smem, stream);
     if (err != cudaSuccess) {
@@ -642,11 +653,11 @@ int mcd::launch_resident_chain(mcd_handle *h, const ChainParams &chain, cudaStre
 }
 int mcd::resident_chain_group(const mcd_handle *h) { return h ? h->chain_group : 0; }
 int mcd::resident_chain_status(mcd_handle *h, cudaStream_t stream) {
-    if (!h || !h->group_arrivals) return 0;
+    if (!h || !h->group_sums || h->chain_group <= 1) return 0;
     int status = 0;
-    MCD_CUDA(cudaMemcpyAsync(&status, h->group_arrivals + h->n_segments, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    MCD_CUDA(cudaMemcpyAsync(&status, h->group_sums, sizeof(int), cudaMemcpyDeviceToHost, stream));
     MCD_CUDA(cudaStreamSynchronize(stream));
-    if (status) return fail(-2, "resident chain: a CTA group did not meet at its barrier");
+    if (status) return fail(-2, "resident chain: a CTA of a group never published its sums");
     return 0;
 }
 int mcd::handle_device(const mcd_handle *h) { return h->device; }

@@ -63,16 +63,19 @@ struct FuseParams {
 // leaving the SM.
 constexpr int kChainBlock = 512;      // threads per CTA of the resident-chain kernel
 constexpr int kChainMaxWalkers = 1024;
+struct TaggedSum;
 struct ChainParams {
     int n_steps;
     int n_walkers;                // W per segment
     int n0;                       // red half
     int max_segment_padded;       // column stride in shared memory (stars, multiple of 16)
-    int group;                    // CTAs sharing one segment's stars (1: one CTA per segment, no grid barrier)
+    int group;                    // CTAs sharing one segment's stars (1: one CTA per segment, nothing exchanged)
     int stars_per_cta;            // even; CTA r of a group owns stars [r * stars_per_cta, ...)
-    double *group_sums;           // [2][S][group][kChainBlock] per-CTA sums of a half-step (group > 1)
-    unsigned long long *group_arrivals;   // [S] barrier counters, zero at launch (group > 1)
-    int *status;                  // set non-zero if a barrier wait ran into its time limit
+    struct TaggedSum *group_sums; // [2][S][group][sum_stride] per-CTA sums (tagged words or doubles), zero at launch
+    unsigned long long *group_arrivals;   // [S] CTAs arrived so far, zero at launch (tagged == 0)
+    int sum_stride;               // walkers per exchange = min(kChainBlock, larger half of the ensemble)
+    int tagged;                   // 1: sums travel as self-validating tagged words; 0: plain doubles behind a counter
+    int *status;                  // set non-zero if a wait for a group member ran into its time limit
     unsigned int step0;           // global step counter at entry
     double a;
     unsigned long long seed;
@@ -152,7 +155,7 @@ int launch_ensemble(mcd_handle *h, const double *theta_dev, int n_walkers, doubl
 int launch_ensemble_fused(mcd_handle *h, int n_walkers, const FuseParams &fuse, cudaStream_t stream);
 // whole chains in one launch when the catalogue fits shared memory; returns 1 if not eligible
 int launch_resident_chain(mcd_handle *h, const ChainParams &chain, cudaStream_t stream);
-// after the stream was synchronised: < 0 if a group barrier of the last resident launch timed out
+// after the stream was synchronised: < 0 if a CTA group of the last resident launch lost a member
 int resident_chain_status(mcd_handle *h, cudaStream_t stream);
 int resident_chain_group(const mcd_handle *h);   // CTAs per segment of the last resident launch
 int handle_device(const mcd_handle *h);

@@ -21,6 +21,7 @@
 //           levels (last CTA of a super-chunk, last super-chunk of a walker group) that add in
 //           index order, so the result does not depend on CTA scheduling.
 #include <math.h>
+#include <stdio.h>
 
 #include <algorithm>
 
@@ -780,26 +781,62 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
 // every emcee iteration (red/blue split, proposals, likelihood over all stars, acceptance) runs inside
 // the one launch.  With group == 1 __syncthreads is the only synchronisation.  With group > 1 (a
 // cooperative launch: all CTAs are resident together) the CTAs of a segment exchange their slice sums
-// through L2 once per half-step behind an arrive-and-wait barrier on a global counter, every CTA adds
-// the slices in the same order and so takes the same accept/reject decisions on its own copy of the
-// ensemble.  Same move, same Philox counters and the same per-term arithmetic (`term<>`) as the
+// through L2 once per half-step (tagged words, below), every CTA adds the slices in the same order and
+// so takes the same accept/reject decisions on its own copy of the ensemble.  Same move, same Philox counters and the same per-term arithmetic (`term<>`) as the
 // launch-per-half-step sampler.
-static __device__ __noinline__ void group_barrier(unsigned long long *arrivals, unsigned long long target, int *status) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long seen;
-        asm volatile("atom.add.acq_rel.gpu.global.u64 %0, [%1], 1;" : "=l"(seen) : "l"(arrivals) : "memory");
-        seen += 1;
-        const long long t0 = clock64();
-        while (seen < target) {
-            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(arrivals) : "memory");
-            if (clock64() - t0 > 8000000000LL) {      // ~4 s: a CTA of the group never arrived
-                atomicExch(status, 1);
-                break;
-            }
-        }
+// Small groups: slice sums travel through L2 as two 8-byte words, each carrying half of the double and
+// the 32-bit number of the half-step it belongs to (the scheme of NCCL's LL protocol): a word is valid
+// as soon as its own tag matches, so plain relaxed stores and loads are enough -- no flag, fence or
+// barrier, one L2 round trip between "last CTA published" and "every CTA has every sum".  With many CTAs
+// x many walkers every thread of the GPU polling its words costs more than it saves (measured: C2..C4
+// of BASELINE.json); there the CTAs arrive on a counter per segment, one thread per CTA waits for it
+// and the sums are plain doubles read once (ChainParams::tagged = 0).
+// -DMCD_CHAIN_PROFILE: thread 0 of CTA 0 accumulates clock64() spent in each stage of a half-step and
+// prints the averages when the kernel ends (tools/chain_group_sweep.py with MCD_B200_LIB pointing at
+// such a build).  Not compiled into the product library.
+#ifdef MCD_CHAIN_PROFILE
+#define MCD_STAMP(i)                                   \
+    do {                                               \
+        if (blockIdx.x == 0 && tid == 0) {             \
+            const long long now_ = clock64();          \
+            prof[i] += now_ - last_;                   \
+            last_ = now_;                              \
+        }                                              \
+    } while (0)
+#else
+#define MCD_STAMP(i) do { } while (0)
+#endif
+
+struct alignas(16) TaggedSum {
+    unsigned long long lo, hi;
+};
+__device__ __forceinline__ void publish_sum(TaggedSum *slot, double value, unsigned int tag) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(value);
+    const unsigned long long t = (unsigned long long)tag << 32;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"((bits & 0xffffffffULL) | t),
+                 "l"((bits >> 32) | t)
+                 : "memory");
+}
+__device__ __forceinline__ bool read_sum(const TaggedSum *slot, unsigned int tag, double &value) {
+    unsigned long long lo, hi;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(slot) : "memory");
+    if ((unsigned int)(lo >> 32) != tag || (unsigned int)(hi >> 32) != tag) return false;
+    value = __longlong_as_double((long long)((lo & 0xffffffffULL) | (hi << 32)));
+    return true;
+}
+constexpr long long kGroupWaitCycles = 8000000000LL;      // ~4 s: a CTA of the group never published
+// sum over the star slices of one walker held in red[slice * wl + lane]; fixed order, four chains
+__device__ __forceinline__ double sum_slices(const double *red, int lane, int wl, int slices) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int j = 0;
+    for (; j + 4 <= slices; j += 4) {
+        a0 += red[j * wl + lane];
+        a1 += red[(j + 1) * wl + lane];
+        a2 += red[(j + 2) * wl + lane];
+        a3 += red[(j + 3) * wl + lane];
     }
-    __syncthreads();
+    for (; j < slices; ++j) a0 += red[j * wl + lane];
+    return (a0 + a1) + (a2 + a3);
 }
 
 template <int ROT, int FREE, int BG, int MATH>
@@ -821,8 +858,7 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
     const int first = min(seg_stars, member * C.stars_per_cta);
     const int n = min(seg_stars - first, C.stars_per_cta);             // stars of this CTA's slice
     const long long offset = (P.seg_begin ? P.seg_packed[seg] : 0) + first;
-    unsigned long long barrier_target = 0;
-    int parity = 0;
+    unsigned int phase = 0;         // half-steps exchanged so far in this launch: tag of the slice sums
 
     // shared-memory carve-up (every block is a multiple of 16 bytes)
     double *cols = reinterpret_cast<double *>(smem_raw);                       // [NC][stride]
@@ -845,8 +881,13 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
     }
     __syncthreads();
 
+#ifdef MCD_CHAIN_PROFILE
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long last_ = clock64();
+#endif
     for (int it = 0; it < C.n_steps; ++it) {
         const unsigned int step = C.step0 + (unsigned int)it;
+        MCD_STAMP(7);
         // ---- red/blue partition: rank of a random key ---------------------------------------------
         for (int w = tid; w < W; w += kChainBlock) {
             const uint4 r = philox4x32_10(make_uint4(step, 2u, (uint32_t)(seg * W + w), 7u),
@@ -861,6 +902,7 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
             perm[rank] = w;
         }
         __syncthreads();
+        MCD_STAMP(0);
         for (int half = 0; half < 2; ++half) {
             const int ns = half == 0 ? C.n0 : W - C.n0;
             const int nc = W - ns;
@@ -889,6 +931,7 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
                     for (int p = 0; p < NP; ++p) q[p] = c[p] - (c[p] - s[p]) * z;
                     load_walker<ROT, FREE, BG>(P, q, Wk);
                 }
+                MCD_STAMP(1);
                 Accum<BG, MATH> A;
                 A.reset();
                 if (valid && Wk.prior_ok) {
@@ -915,50 +958,121 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
                     A.end_tile();
                 }
                 red[tid] = (valid && Wk.prior_ok) ? A.value() : 0.0;
+                MCD_STAMP(2);
                 __syncthreads();
+                MCD_STAMP(3);
+                const bool owner = valid && slice == 0;
                 if (G > 1) {
-                    // slice sums of this CTA -> L2, wait for the group, add every CTA's in member order
-                    double *sums = C.group_sums + ((size_t)(parity * n_segments + seg) * G) * kChainBlock;
-                    if (valid && slice == 0) {
-                        double mine = red[lane];
-                        for (int j = 1; j < slices; ++j) mine += red[j * wl + lane];
-                        sums[(size_t)member * kChainBlock + lane] = mine;
+                    // this CTA's slice sums -> L2 ...
+                    ++phase;
+                    const size_t first_slot = ((size_t)((phase & 1u) * n_segments + seg) * G) * C.sum_stride;
+                    if (owner) {
+                        const double mine = sum_slices(red, lane, wl, slices);
+                        if (C.tagged) publish_sum(&C.group_sums[first_slot + (size_t)member * C.sum_stride + lane], mine, phase);
+                        else reinterpret_cast<double *>(C.group_sums)[first_slot + (size_t)member * C.sum_stride + lane] = mine;
                     }
-                    barrier_target += (unsigned long long)G;
-                    group_barrier(C.group_arrivals + seg, barrier_target, C.status);
+                    if (!C.tagged) {
+                        // ... announced by one arrival per CTA on the segment's counter (the bar.sync before
+                        // the release orders the other threads' stores before it)
+                        __syncthreads();
+                        if (tid == 0)
+                            asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(C.group_arrivals + seg) : "memory");
+                    }
+                }
+                // ... and while they travel, the part of the acceptance test that does not depend on them
+                double lz = 0.0, lu = 0.0, old = 0.0;
+                int wa = 0;
+                if (owner) {
+                    double u0, u1;
+                    uniforms(C.seed, step, (uint32_t)half, (uint32_t)(seg * W + k), 1u, u0, u1);
+                    wa = active[k];
+                    lz = (NP - 1.0) * log(z);
+                    lu = log(u0);
+                    old = lnp[wa];
+                }
+                MCD_STAMP(4);
+                if (G > 1) {
+                    // every CTA's sums in member order: thread (lane, slice) takes members slice, slice + slices, ...
+                    const size_t first_slot = ((size_t)((phase & 1u) * n_segments + seg) * G) * C.sum_stride;
                     double acc = 0.0;
-                    if (valid) {
-                        for (int g0 = slice; g0 < G; g0 += 8 * slices) {
-                            double v[8];
+                    if (!C.tagged) {
+                        // large groups: one thread waits for all arrivals, then plain 8-byte reads from L2
+                        if (tid == 0) {
+                            const unsigned long long target = (unsigned long long)phase * (unsigned long long)G;
+                            unsigned long long seen = 0;
+                            const long long t0 = clock64();
+                            do {
+                                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(C.group_arrivals + seg) : "memory");
+                                if (clock64() - t0 > kGroupWaitCycles) {
+                                    atomicExch(C.status, 1);
+                                    break;
+                                }
+                            } while (seen < target);
+                        }
+                        __syncthreads();           // also: red[] is read above and rewritten below
+                        if (valid) {
+                            const double *sums = reinterpret_cast<const double *>(C.group_sums) + first_slot;
+                            constexpr int B = 16;
+                            for (int g0 = slice; g0 < G; g0 += B * slices) {
+                                double v[B];
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                const int g = g0 + u * slices;
-                                v[u] = g < G ? __ldcg(&sums[(size_t)g * kChainBlock + lane]) : 0.0;
+                                for (int u = 0; u < B; ++u) {
+                                    const int g = g0 + u * slices;
+                                    v[u] = g < G ? __ldcg(&sums[(size_t)g * C.sum_stride + lane]) : 0.0;
+                                }
+#pragma unroll
+                                for (int u = 0; u < B; ++u) acc += v[u];
                             }
+                        }
+                    } else {
+                        // small groups: the words carry their own tag, every thread polls the ones it adds
+                        const TaggedSum *sums = C.group_sums + first_slot;
+                        __syncthreads();           // red[] is read above and rewritten below
+                        if (valid) {
+                            constexpr int B = 16;
+                            for (int g0 = slice; g0 < G; g0 += B * slices) {
+                                double v[B];
+                                unsigned int pending = 0u;
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) acc += v[u];
+                                for (int u = 0; u < B; ++u) {
+                                    const int g = g0 + u * slices;
+                                    v[u] = 0.0;
+                                    if (g < G && !read_sum(&sums[(size_t)g * C.sum_stride + lane], phase, v[u])) pending |= 1u << u;
+                                }
+                                const long long t0 = clock64();
+                                while (pending) {
+#pragma unroll
+                                    for (int u = 0; u < B; ++u)
+                                        if ((pending >> u) & 1u)
+                                            if (read_sum(&sums[(size_t)(g0 + u * slices) * C.sum_stride + lane], phase, v[u]))
+                                                pending &= ~(1u << u);
+                                    if (clock64() - t0 > kGroupWaitCycles) {
+                                        atomicExch(C.status, 1);
+                                        break;
+                                    }
+                                }
+#pragma unroll
+                                for (int u = 0; u < B; ++u) acc += v[u];
+                            }
                         }
                     }
                     red[tid] = acc;
-                    parity ^= 1;
                     __syncthreads();
                 }
-                if (valid && slice == 0) {
-                    double total = red[lane];
-                    for (int j = 1; j < slices; ++j) total += red[j * wl + lane];
+                MCD_STAMP(5);
+                if (owner) {
+                    double total = sum_slices(red, lane, wl, slices);
                     if (MATH == MCD_MATH_FAST) total = fma((double)seg_stars, -0.5 * kLn2Pi, total);
                     if (!Wk.prior_ok) total = __longlong_as_double(0xfff0000000000000LL);
-                    double u0, u1;
-                    uniforms(C.seed, step, (uint32_t)half, (uint32_t)(seg * W + k), 1u, u0, u1);
-                    const int wa = active[k];
-                    const double diff = (NP - 1.0) * log(z) + total - lnp[wa];
-                    if (diff > log(u0)) {          // NaN never accepts
+                    const double diff = lz + total - old;
+                    if (diff > lu) {               // NaN never accepts
                         for (int p = 0; p < NP; ++p) pos[(size_t)wa * NP + p] = q[p];
                         lnp[wa] = total;
                         nacc[wa] += 1;
                     }
                 }
                 __syncthreads();
+                MCD_STAMP(6);
             }
         }
         if (C.chain && member == 0) {
@@ -969,6 +1083,14 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
             for (int i = tid; i < W; i += kChainBlock) dl[i] = lnp[i];
         }
     }
+#ifdef MCD_CHAIN_PROFILE
+    if (blockIdx.x == 0 && tid == 0 && C.n_steps >= 100) {
+        const double h = 2.0 * C.n_steps;
+        printf("chain profile (cycles per half-step, group %d): split %.0f | proposal %.0f | stars %.0f | sync %.0f | "
+               "publish+threshold %.0f | gather %.0f | accept %.0f | store %.0f\n", G, prof[0] / h, prof[1] / h,
+               prof[2] / h, prof[3] / h, prof[4] / h, prof[5] / h, prof[6] / h, prof[7] / h);
+    }
+#endif
     if (member != 0) return;
     for (int i = tid; i < W * NP; i += kChainBlock) C.pos[(size_t)seg * W * NP + i] = pos[i];
     for (int i = tid; i < W; i += kChainBlock) {

@@ -153,21 +153,26 @@ def test_resident_chain_groups_walk_the_same_chain(cls, n_stars, n_walkers, monk
     monkeypatch.setenv('MCD_FORCE_RESIDENT_CHAIN', '1')
     monkeypatch.setenv('MCD_NO_RESIDENT_CHAIN', '0')
     chains = {}
-    for group in (1, 7, 40, 148):
+    for group, exchange in ((1, 'tagged'), (7, 'tagged'), (7, 'counter'), (40, 'tagged'), (148, 'tagged'), (148, 'counter')):
         if n_stars / group > 6000:
             continue                      # a slice of that size does not fit one SM's shared memory
         monkeypatch.setenv('MCD_CHAIN_GROUP', str(group))
+        monkeypatch.setenv('MCD_CHAIN_EXCHANGE', exchange)     # how the CTAs of a group trade their sums
         s = samplers.DeviceEnsembleSampler(n_walkers, model.n_fitted_parameters, model.pack(), seed=99)
         s.run_mcmc(pos, 12)
         kind, used = s.engine
         if kind != 'resident':
             continue                      # fewer SMs than the group asks for
         assert used == group
-        chains[group] = (s.chain.copy(), s.lnprobability.copy())
+        chains[group, exchange] = (s.chain.copy(), s.lnprobability.copy())
     assert len(chains) >= 2
     ref_chain, ref_lnp = chains[sorted(chains)[0]]
-    for group, (chain, lnp) in chains.items():
-        assert np.allclose(chain, ref_chain, rtol=1e-10, atol=0), group
-        assert np.allclose(lnp, ref_lnp, rtol=1e-12, atol=0), group
+    for key, (chain, lnp) in chains.items():
+        assert np.allclose(chain, ref_chain, rtol=1e-10, atol=0), key
+        assert np.allclose(lnp, ref_lnp, rtol=1e-12, atol=0), key
+    # the two ways of trading sums add them in the same order: identical chains
+    for group in (7, 148):
+        if (group, 'tagged') in chains and (group, 'counter') in chains:
+            assert np.array_equal(chains[group, 'tagged'][0], chains[group, 'counter'][0])
     again = model.lnprob(np.ascontiguousarray(ref_chain[:, -1, :]))
     assert np.allclose(again, ref_lnp[:, -1], rtol=1e-12, atol=0)
