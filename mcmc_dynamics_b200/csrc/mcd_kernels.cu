@@ -824,7 +824,16 @@ __device__ __forceinline__ bool read_sum(const TaggedSum *slot, unsigned int tag
     value = __longlong_as_double((long long)((lo & 0xffffffffULL) | (hi << 32)));
     return true;
 }
-constexpr long long kGroupWaitCycles = 8000000000LL;      // ~4 s: a CTA of the group never published
+// A wait for the group gives up after ~1 s (a member never published: cannot happen in a cooperative
+// launch, but a spin without a bound would hang the GPU if it did) and raises *status; every 1024
+// failed polls a waiter also looks at *status, so once one wait has failed the rest of the kernel
+// drains at once (`group_lost`) instead of timing out half-step by half-step.
+constexpr long long kGroupWaitCycles = 2000000000LL;
+__device__ __forceinline__ bool group_wait_failed(long long t0, unsigned int &polls, int *status) {
+    if ((++polls & 1023u) != 0u) return false;
+    if (clock64() - t0 > kGroupWaitCycles) atomicExch(status, 1);
+    return *reinterpret_cast<volatile int *>(status) != 0;
+}
 // sum over the star slices of one walker held in red[slice * wl + lane]; fixed order, four chains
 __device__ __forceinline__ double sum_slices(const double *red, int lane, int wl, int slices) {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -859,6 +868,7 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
     const int n = min(seg_stars - first, C.stars_per_cta);             // stars of this CTA's slice
     const long long offset = (P.seg_begin ? P.seg_packed[seg] : 0) + first;
     unsigned int phase = 0;         // half-steps exchanged so far in this launch: tag of the slice sums
+    bool group_lost = false;        // a wait for the group failed: stop waiting, the host reports the error
 
     // shared-memory carve-up (every block is a multiple of 16 bytes)
     double *cols = reinterpret_cast<double *>(smem_raw);                       // [NC][stride]
@@ -1000,14 +1010,12 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
                         if (tid == 0) {
                             const unsigned long long target = (unsigned long long)phase * (unsigned long long)G;
                             unsigned long long seen = 0;
+                            unsigned int polls = 0u;
                             const long long t0 = clock64();
                             do {
                                 asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(C.group_arrivals + seg) : "memory");
-                                if (clock64() - t0 > kGroupWaitCycles) {
-                                    atomicExch(C.status, 1);
-                                    break;
-                                }
-                            } while (seen < target);
+                                if (seen < target && group_wait_failed(t0, polls, C.status)) group_lost = true;
+                            } while (seen < target && !group_lost);
                         }
                         __syncthreads();           // also: red[] is read above and rewritten below
                         if (valid) {
@@ -1039,17 +1047,15 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
                                     v[u] = 0.0;
                                     if (g < G && !read_sum(&sums[(size_t)g * C.sum_stride + lane], phase, v[u])) pending |= 1u << u;
                                 }
+                                unsigned int polls = 0u;
                                 const long long t0 = clock64();
-                                while (pending) {
+                                while (pending && !group_lost) {
 #pragma unroll
                                     for (int u = 0; u < B; ++u)
                                         if ((pending >> u) & 1u)
                                             if (read_sum(&sums[(size_t)(g0 + u * slices) * C.sum_stride + lane], phase, v[u]))
                                                 pending &= ~(1u << u);
-                                    if (clock64() - t0 > kGroupWaitCycles) {
-                                        atomicExch(C.status, 1);
-                                        break;
-                                    }
+                                    if (pending && group_wait_failed(t0, polls, C.status)) group_lost = true;
                                 }
 #pragma unroll
                                 for (int u = 0; u < B; ++u) acc += v[u];
