@@ -275,8 +275,8 @@ struct Accum<BG, MCD_MATH_FAST> {
     __device__ __forceinline__ void end_group() {
         if (BG != MCD_BG_FIXED_PMEMBER) den.renormalise_checked();     // raw factors: fold every pair
     }
-    // mul_ext() keeps the factors' mantissas in [1, 2): the product of a tile (<= 256) cannot overflow
-    __device__ __forceinline__ void end_tile() { num.renormalise(); }
+    // mul_ext() brings the factors' mantissas into [1, 2): the product of a tile (<= 256) cannot overflow
+    __device__ __forceinline__ void end_tile() { num.renormalise_ext(); }
     __device__ __forceinline__ double value() {
         const double n = num.ln();
         return BG == MCD_BG_FIXED_PMEMBER ? n : n - den.ln();
@@ -303,7 +303,8 @@ struct Star {
 // one (walker, star) term
 // ------------------------------------------------------------------------------------------
 template <int ROT, int FREE, int BG, int MATH>
-__device__ __forceinline__ void term(const Walker &W, const Star<total_columns(ROT, FREE, BG)> &S, Accum<BG, MATH> &A) {
+__device__ __forceinline__ void term(const Walker &W, const Star<total_columns(ROT, FREE, BG)> &S, Accum<BG, MATH> &A,
+                                     const double *__restrict__ exp2_table = nullptr) {
     constexpr int NB = base_columns(ROT, FREE);
     constexpr bool FAST = MATH == MCD_MATH_FAST;
     // ---- geometry: numerator `num` of the rotation term, r^2 ---------------------------------
@@ -355,7 +356,7 @@ __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(R
             const double y = ROT == MCD_ROT_RADIAL ? yq * D1 : yq;
             double em;
             int ee;
-            exp_neg_half(z * z, em, ee);
+            exp_neg_half_table(z * z, exp2_table, em, ee);
             const double wm = S.c[NB];
             double bm;
             int be;
@@ -371,7 +372,7 @@ __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(R
                 const double yb = fast_rsqrt(nb);
                 const double zb = (v - W.vb) * yb;
                 double ebm;
-                exp_neg_half(zb * zb, ebm, be);
+                exp_neg_half_table(zb * zb, exp2_table, ebm, be);
                 bm = W.fb * yb * ebm;
                 A.den.mul_raw(wm + W.fb);
             }
@@ -642,6 +643,10 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     __shared__ __align__(8) uint64_t bars[kStages];
     __shared__ double red[kBlock];
     __shared__ int s_last;
+    // 2^(j/64) for the exponentials of the mixture terms (mcd_math.cuh); filled before the first barrier
+    constexpr bool EXP_TABLE = BG != MCD_BG_NONE && MATH == MCD_MATH_FAST;
+    __shared__ double s_exp2[EXP_TABLE ? 64 : 1];
+    if (EXP_TABLE && threadIdx.x < 64) s_exp2[threadIdx.x] = kExp2Table[threadIdx.x];
 
     const int tile = P.tile;                     // stars per stage actually copied (<= kMaxTile)
     constexpr int TS = kMaxTile;                 // column stride in shared memory: compile-time, so
@@ -731,24 +736,24 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
                 Star<NC> s0, s1, s2, s3;
                 load_pair<NC, ICOL>(c, ci, TS, i, s0, s1);
                 load_pair<NC, ICOL>(c, ci, TS, i + step, s2, s3);
-                term<ROT, FREE, BG, MATH>(W, s0, A);
-                term<ROT, FREE, BG, MATH>(W, s1, A);
+                term<ROT, FREE, BG, MATH>(W, s0, A, s_exp2);
+                term<ROT, FREE, BG, MATH>(W, s1, A, s_exp2);
                 A.end_group();
-                term<ROT, FREE, BG, MATH>(W, s2, A);
-                term<ROT, FREE, BG, MATH>(W, s3, A);
+                term<ROT, FREE, BG, MATH>(W, s2, A, s_exp2);
+                term<ROT, FREE, BG, MATH>(W, s3, A, s_exp2);
                 A.end_group();
             }
             for (; i < n2; i += step) {
                 Star<NC> s0, s1;
                 load_pair<NC, ICOL>(c, ci, TS, i, s0, s1);
-                term<ROT, FREE, BG, MATH>(W, s0, A);
-                term<ROT, FREE, BG, MATH>(W, s1, A);
+                term<ROT, FREE, BG, MATH>(W, s0, A, s_exp2);
+                term<ROT, FREE, BG, MATH>(W, s1, A, s_exp2);
                 A.end_group();
             }
             if ((n & 1) && (n2 / 2) % P.slices == slice) {   // odd tail of the last tile
                 Star<NC> s0;
                 load_one<NC, ICOL>(c, ci, TS, n2, s0);
-                term<ROT, FREE, BG, MATH>(W, s0, A);
+                term<ROT, FREE, BG, MATH>(W, s0, A, s_exp2);
                 A.end_group();
             }
             A.end_tile();
@@ -854,6 +859,9 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
     constexpr int NC = total_columns(ROT, FREE, BG);
     constexpr bool ICOL = has_icol(BG, MATH);
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr bool EXP_TABLE = BG != MCD_BG_NONE && MATH == MCD_MATH_FAST;
+    __shared__ double s_exp2[EXP_TABLE ? 64 : 1];          // 2^(j/64), see exp_neg_half_table
+    if (EXP_TABLE && threadIdx.x < 64) s_exp2[threadIdx.x] = kExp2Table[threadIdx.x];
     const int tid = threadIdx.x;
     const int G = C.group;
     const int seg = blockIdx.x / G;
@@ -951,8 +959,8 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
                     for (int i = 2 * slice; i < n2; i += stepi) {
                         Star<NC> s0, s1;
                         load_pair<NC, ICOL>(cols, icol, stride, i, s0, s1);
-                        term<ROT, FREE, BG, MATH>(Wk, s0, A);
-                        term<ROT, FREE, BG, MATH>(Wk, s1, A);
+                        term<ROT, FREE, BG, MATH>(Wk, s0, A, s_exp2);
+                        term<ROT, FREE, BG, MATH>(Wk, s1, A, s_exp2);
                         A.end_group();
                         if (++done == 64) {     // fold the running products before they can overflow
                             A.end_tile();
@@ -962,7 +970,7 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
                     if ((n & 1) && (n2 / 2) % slices == slice) {
                         Star<NC> s0;
                         load_one<NC, ICOL>(cols, icol, stride, n2, s0);
-                        term<ROT, FREE, BG, MATH>(Wk, s0, A);
+                        term<ROT, FREE, BG, MATH>(Wk, s0, A, s_exp2);
                         A.end_group();
                     }
                     A.end_tile();

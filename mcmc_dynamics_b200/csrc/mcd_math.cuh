@@ -87,10 +87,10 @@ __device__ __forceinline__ double pow2_nonpos(int d) {
 struct LogProduct {
     double mant;        // product of the factors' mantissas since the last renormalisation
     long long expo;     // sum of the factors' unbiased exponents
-    int bad;            // a factor was negative, denormal, inf or NaN (result: NaN)
-    int zero;           // a factor was exactly zero (result: -inf)
+    int bad;            // a factor of mul()/renormalise_checked() left the normal positive range (result: NaN)
+    int signs;          // OR of the high words of the mul_ext() factors: sign bit set = a negative factor
 
-    __device__ __forceinline__ void reset() { mant = 1.0; expo = 0; bad = 0; zero = 0; }
+    __device__ __forceinline__ void reset() { mant = 1.0; expo = 0; bad = 0; signs = 0; }
 
     // multiply by x, a normal positive double
     __device__ __forceinline__ void mul(double x) {
@@ -100,16 +100,18 @@ struct LogProduct {
         mant *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
     }
 
-    // multiply by m * 2^e with m >= 0; m == 0 marks the whole product as zero (lnlike = -inf);
-    // anything else outside the normal positive range (negative, denormal, inf, NaN) marks it bad
+    // Multiply by m * 2^e, m >= 0 (hot loop of the mixture kernels).  m is brought into [1, 2) by a
+    // multiplication with 2^-(its exponent) instead of by rewriting its exponent bits, so the special
+    // values take care of themselves: m == 0 makes the product 0 for good (lnlike = -inf), inf and NaN
+    // make it NaN or negative, and ln() sorts those out once at the end -- no compare or select per
+    // factor.  A negative m (a weight outside [0, 1]) is remembered through the sign bit of `signs`.
+    // Denormal m stay exact (they only use up headroom below 1).
     __device__ __forceinline__ void mul_ext(double m, int e) {
         const int hi = __double2hiint(m);
-        const bool is_zero = (hi | __double2loint(m)) == 0;
-        const bool out_of_range = (unsigned)(hi - 0x00100000) >= 0x7fe00000u;
-        zero |= is_zero;
-        bad |= (out_of_range && !is_zero);
-        expo += out_of_range ? 0 : (long long)((hi >> 20) - 1023 + e);
-        mant *= out_of_range ? 1.0 : __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(m));
+        const int biased = (hi >> 20) & 0x7ff;
+        signs |= hi;
+        expo += (long long)(biased - 1023 + e);
+        mant *= m * __hiloint2double((2046 - biased) << 20, 0);
     }
 
     // multiply by x without touching the exponent: the caller renormalises after a small group of
@@ -117,7 +119,14 @@ struct LogProduct {
     // once per factor to once per group
     __device__ __forceinline__ void mul_raw(double x) { mant *= x; }
 
-    // fold the mantissa's own exponent into `expo`; call at least every 1000 mul()/mul_ext() factors
+    // the same for a product of mul_ext() factors, which may be zero (and must stay zero), inf or NaN
+    __device__ __forceinline__ void renormalise_ext() {
+        const int biased = (__double2hiint(mant) >> 20) & 0x7ff;
+        expo += biased - 1023;
+        mant *= __hiloint2double((2046 - biased) << 20, 0);
+    }
+
+    // fold the mantissa's own exponent into `expo`; call at least every 1000 mul() factors
     __device__ __forceinline__ void renormalise() {
         const int hi = __double2hiint(mant);
         expo += (hi >> 20) - 1023;
@@ -133,12 +142,17 @@ struct LogProduct {
         mant = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(mant));
     }
 
-    // ln of the product
+    // ln of the product: -inf if it is exactly zero, NaN if a factor was bad or negative or the
+    // product is not a normal positive number (inf, NaN, negative, denormal)
     __device__ __forceinline__ double ln() {
+        const int hi = __double2hiint(mant);
+        const bool is_zero = (hi | __double2loint(mant)) == 0;
+        const bool out_of_range = (unsigned)(hi - 0x00100000) >= 0x7fe00000u;
         renormalise();
         const double r = fma((double)expo, kLn2, log(mant));
-        return bad ? __longlong_as_double(0x7ff8000000000000LL)
-                   : (zero ? __longlong_as_double(0xfff0000000000000LL) : r);
+        return (bad || signs < 0 || (out_of_range && !is_zero))
+                   ? __longlong_as_double(0x7ff8000000000000LL)
+                   : (is_zero ? __longlong_as_double(0xfff0000000000000LL) : r);
     }
 };
 
@@ -204,6 +218,52 @@ __device__ __forceinline__ void exp_neg_half(double w, double &mant, int &expo) 
     const double nf = shifted - kMagic;
     const double f = fma(wc, kC, -nf);                  // exact product minus the integer part
     mant = exp2_frac(f);
+}
+
+// Table-driven variant for the hot loops of the mixture kernels (the FP64 pipe's issue rate is their
+// bound, so instructions count, not latency): 2^t with t*64 = N + r, |r| <= 1/2, N = 64 expo + j,
+//     exp(-w/2) = 2^expo * T[j] * (1 + q(r)),   T[j] = 2^(j/64),   q(r) = 2^(r/64) - 1  (degree 5, 4e-17)
+// -- 10 FP64 instructions instead of 17.  `table` is a copy of kExp2Table in shared memory (64 lanes'
+// worth of divergent indices: constant memory would serialise).  mant in [0.99, 2.01).
+__constant__ double kExp2Table[64] = {
+    1.00000000000000000e+00, 1.01088928605170048e+00, 1.02189714865411663e+00, 1.03302487902122841e+00,
+    1.04427378242741375e+00, 1.05564517836055716e+00, 1.06714040067682370e+00, 1.07876079775711986e+00,
+    1.09050773266525769e+00, 1.10238258330784089e+00, 1.11438674259589243e+00, 1.12652161860824185e+00,
+    1.13878863475669156e+00, 1.15118922995298267e+00, 1.16372485877757748e+00, 1.17639699165028122e+00,
+    1.18920711500272103e+00, 1.20215673145270308e+00, 1.21524735998046896e+00, 1.22848053610687002e+00,
+    1.24185781207348400e+00, 1.25538075702469110e+00, 1.26905095719173322e+00, 1.28287001607877826e+00,
+    1.29683955465100964e+00, 1.31096121152476441e+00, 1.32523664315974132e+00, 1.33966752405330292e+00,
+    1.35425554693689265e+00, 1.36900242297459052e+00, 1.38390988196383202e+00, 1.39897967253831124e+00,
+    1.41421356237309515e+00, 1.42961333839197002e+00, 1.44518080697704665e+00, 1.46091779418064704e+00,
+    1.47682614593949935e+00, 1.49290772829126484e+00, 1.50916442759342284e+00, 1.52559815074453842e+00,
+    1.54221082540794074e+00, 1.55900440023783693e+00, 1.57598084510788650e+00, 1.59314215134226700e+00,
+    1.61049033194925428e+00, 1.62802742185734783e+00, 1.64575547815396495e+00, 1.66367658032673638e+00,
+    1.68179283050742900e+00, 1.70010635371852348e+00, 1.71861929812247793e+00, 1.73733383527370622e+00,
+    1.75625216037329945e+00, 1.77537649252652119e+00, 1.79470907500310717e+00, 1.81425217550039886e+00,
+    1.83400808640934243e+00, 1.85397912508338547e+00, 1.87416763411029996e+00, 1.89457598158696561e+00,
+    1.91520656139714740e+00, 1.93606179349229435e+00, 1.95714412417540018e+00, 1.97845602638795093e+00};
+// (ln2 / 64)^k / k!, k = 1..5
+__constant__ double kExp2StepCoef[5] = {1.08304246962491451e-02, 5.86490495505616997e-05, 2.11731371554647763e-07,
+                                        5.73285168864040189e-10, 1.24178437017169253e-12};
+
+__device__ __forceinline__ void exp_neg_half_table(double w, const double *__restrict__ table, double &mant, int &expo) {
+    const double kMagic = 6755399441055744.0;            // 1.5 * 2^52
+    const double kC = -32.0 * kLog2e;                    // -1/2 * log2(e) * 64
+    // clamp w to 2^25 on the integer pipe (w >= 0: the high words order like the doubles), so that N
+    // stays inside an int32; a NaN with the sign bit clear is clamped too -- the caller's mantissa is
+    // NaN through its other factors then
+    const double wc = __hiloint2double(min(__double2hiint(w), 0x41800000), __double2loint(w));
+    const double shifted = fma(wc, kC, kMagic);
+    const int N = __double2loint(shifted);
+    const double nf = shifted - kMagic;
+    const double r = fma(wc, kC, -nf);                   // exact product minus the integer part
+    double p = fma(kExp2StepCoef[4], r, kExp2StepCoef[3]);
+    p = fma(p, r, kExp2StepCoef[2]);
+    p = fma(p, r, kExp2StepCoef[1]);
+    p = fma(p, r, kExp2StepCoef[0]);
+    const double t = table[N & 63];
+    expo = N >> 6;
+    mant = fma(t, p * r, t);
 }
 
 // 2^d for d <= 0, exactly zero below 2^-960 (integer pipe only)
