@@ -179,7 +179,8 @@ struct Walker {
     double vsys, s2;            // systemic velocity, sigma_max^2
     double cx, cy;              // rotation: v_rot numerator = x*cx + y*cy
     double ip2, ia2;            // 1/r_peak^2, 1/a^2 in units of the stored coordinates
-    double sb, cb, sdc, cdc;    // free centre: sin/cos(ra_c - ra0), sin/cos(dec_c)
+    double sb, cb, cdc;         // free centre: sin/cos(ra_c - ra0), cos(dec_c)
+    double sbs, cbs;            //              -sin(ra_c - ra0) sin(dec_c), -cos(ra_c - ra0) sin(dec_c)
     double vb, sb2, fb;         // background: v_back, sigma_back^2, f_back
     int prior_ok;
 };
@@ -242,10 +243,13 @@ __device__ __forceinline__ void load_walker(const LaunchParams &P, const double 
         W.ia2 = (L / a) * (L / a);
     }
     if constexpr (FREE) {
+        double sdc;
         sincos((par[MCD_P_RA_CENTER] - P.ra0_deg) * kDeg2Rad, &W.sb, &W.cb);
-        sincos(par[MCD_P_DEC_CENTER] * kDeg2Rad, &W.sdc, &W.cdc);
+        sincos(par[MCD_P_DEC_CENTER] * kDeg2Rad, &sdc, &W.cdc);
+        W.sbs = -W.sb * sdc;
+        W.cbs = -W.cb * sdc;
     } else {
-        W.sb = 0.0; W.cb = 1.0; W.sdc = 0.0; W.cdc = 1.0;
+        W.sb = 0.0; W.cb = 1.0; W.cdc = 1.0; W.sbs = 0.0; W.cbs = 0.0;
     }
     W.vb = par[MCD_P_V_BACK];
     W.sb2 = par[MCD_P_SIGMA_BACK] * par[MCD_P_SIGMA_BACK];
@@ -312,8 +316,9 @@ __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(R
     if constexpr (FREE) {
         const double p1 = S.c[0], p2 = S.c[1], sd = S.c[2];
         const double dx = fma(p2, W.sb, -p1 * W.cb);            // -cos(dec) sin(ra - ra_c)
-        const double u = fma(p2, W.cb, p1 * W.sb);              //  cos(dec) cos(ra - ra_c)
-        const double dy = fma(sd, W.cdc, -u * W.sdc);
+        // sin(dec) cos(dec_c) - cos(dec) cos(ra - ra_c) sin(dec_c), the middle factor expanded into the
+        // stored p1, p2 with the walker's products sin/cos(ra_c - ra0) sin(dec_c): three instructions
+        const double dy = fma(sd, W.cdc, fma(p2, W.cbs, p1 * W.sbs));
         r2 = fma(dx, dx, dy * dy);
         num = fma(dy, W.cy, dx * W.cx);
         if constexpr (ROT == MCD_ROT_CONSTANT) {
