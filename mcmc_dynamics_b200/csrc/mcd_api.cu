@@ -579,8 +579,8 @@ int mcd::launch_resident_chain(mcd_handle *h, const ChainParams &chain, cudaStre
     // same arithmetic spread over all SMs), with the group size that minimises the estimate.  Cycle
     // model: FP64-pipe instructions ~ nominal flops per term, 64 lanes per SM, 60 % pipe efficiency,
     // 1.9 GHz; the exchange of slice sums ~1 us (tagged words) or ~2.2 us (counter, then reads) of L2
-    // latency plus the traffic of every CTA reading every CTA's sums.  MCD_FORCE_RESIDENT_CHAIN=1 skips the comparison with the launch engine,
-    // MCD_CHAIN_GROUP=g fixes the group size (tests, experiments).
+    // latency plus the traffic of every CTA reading every CTA's sums.  MCD_FORCE_RESIDENT_CHAIN=1 skips
+    // the comparison with the launch engine, MCD_CHAIN_GROUP=g fixes the group size (tests, experiments).
     const char *force = getenv("MCD_FORCE_RESIDENT_CHAIN");
     const char *fixed = getenv("MCD_CHAIN_GROUP");
     const double flops = (double)variant_flops_per_term(h->var);

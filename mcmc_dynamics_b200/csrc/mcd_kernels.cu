@@ -892,6 +892,8 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(lnp + W);   // [W]
     int *perm = reinterpret_cast<int *>(keys + W);                            // [W]
     int *nacc = perm + W;                                                     // [W]
+    // proposals of the active half, [larger half][NP] (perm + nacc = 8 bytes per walker: 8-byte aligned)
+    double *prop = reinterpret_cast<double *>(nacc + W);
 
     for (int c = 0; c < NC; ++c)
         for (int i = tid; i < n; i += kChainBlock) cols[(size_t)c * stride + i] = P.cols[c][offset + i];
@@ -905,9 +907,36 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
     __syncthreads();
 
 #ifdef MCD_CHAIN_PROFILE
-    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long last_ = clock64();
 #endif
+    // Everything a half-step draws from the counter-based generator -- stretch factor z, partner index,
+    // (P-1) ln z and ln u of the acceptance test -- depends on (step, half, walker) only, not on the
+    // state of the chain: thread k < (walkers of that half) computes it one half-step ahead, while the
+    // slice sums of the current half-step travel, and keeps it in registers.
+    struct Draw {
+        double z, lz, lu;
+        int partner;
+    };
+    auto draw = [&](unsigned int step, int half) {
+        Draw d{1.0, 0.0, 0.0, 0};
+        const int ns = half == 0 ? C.n0 : W - C.n0;
+        if (tid < ns) {
+            const int nc = W - ns;
+            double u0, u1;
+            uniforms(C.seed, step, (uint32_t)half, (uint32_t)(seg * W + tid), 0u, u0, u1);
+            const double t = (C.a - 1.0) * u0 + 1.0;
+            d.z = t * t / C.a;
+            const int j = (int)(u1 * nc);
+            d.partner = j >= nc ? nc - 1 : j;
+            d.lz = (NP - 1.0) * log(d.z);
+            uniforms(C.seed, step, (uint32_t)half, (uint32_t)(seg * W + tid), 1u, u0, u1);
+            d.lu = log(u0);
+        }
+        return d;
+    };
+    Draw next = draw(C.step0, 0);
+
     for (int it = 0; it < C.n_steps; ++it) {
         const unsigned int step = C.step0 + (unsigned int)it;
         MCD_STAMP(7);
@@ -927,172 +956,158 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
         __syncthreads();
         MCD_STAMP(0);
         for (int half = 0; half < 2; ++half) {
+            // each half of the ensemble fits the CTA (n_walkers <= kChainMaxWalkers = 2 kChainBlock)
             const int ns = half == 0 ? C.n0 : W - C.n0;
-            const int nc = W - ns;
             const int *active = perm + (half == 0 ? 0 : C.n0);
             const int *other = perm + (half == 0 ? C.n0 : 0);
-            // thread = (walker of the active half, star slice); the active half may exceed the CTA
-            for (int base = 0; base < ns; base += kChainBlock) {
-                const int wl = min(ns - base, kChainBlock);
-                const int slices = kChainBlock / wl;
-                const int lane = tid % wl, slice = tid / wl;
-                const int k = base + lane;
-                const bool valid = slice < slices;
-                double q[MCD_MAX_THETA];
-                double z = 1.0;
-                Walker Wk;
-                Wk.prior_ok = 0;
-                if (valid) {
-                    double u0, u1;
-                    uniforms(C.seed, step, (uint32_t)half, (uint32_t)(seg * W + k), 0u, u0, u1);
-                    const double t = (C.a - 1.0) * u0 + 1.0;
-                    z = t * t / C.a;
-                    int j = (int)(u1 * nc);
-                    j = j >= nc ? nc - 1 : j;
-                    const double *s = pos + (size_t)active[k] * NP;
-                    const double *c = pos + (size_t)other[j] * NP;
-                    for (int p = 0; p < NP; ++p) q[p] = c[p] - (c[p] - s[p]) * z;
-                    load_walker<ROT, FREE, BG>(P, q, Wk);
+            // thread = (walker `lane` of the active half, star slice)
+            const int wl = ns;
+            const int slices = kChainBlock / wl;
+            const int lane = tid % wl, slice = tid / wl;
+            const bool valid = slice < slices;
+            const bool owner = tid < wl;               // slice 0: proposes, adds up and accepts for walker `lane`
+            const Draw cur = next;
+            // ---- proposals of the active half -> shared memory (one thread per walker) -------------
+            int wa = 0;
+            if (owner) {
+                wa = active[lane];
+                const double *s = pos + (size_t)wa * NP;
+                const double *c = pos + (size_t)other[cur.partner] * NP;
+                for (int p = 0; p < NP; ++p) prop[(size_t)lane * NP + p] = c[p] - (c[p] - s[p]) * cur.z;
+            }
+            __syncthreads();
+            MCD_STAMP(9);
+            Walker Wk;
+            Wk.prior_ok = 0;
+            if (valid) load_walker<ROT, FREE, BG>(P, prop + (size_t)lane * NP, Wk);
+            MCD_STAMP(1);
+            Accum<BG, MATH> A;
+            A.reset();
+            if (valid && Wk.prior_ok) {
+                const int n2 = n & ~1;
+                const int stepi = 2 * slices;
+                int done = 0;
+                for (int i = 2 * slice; i < n2; i += stepi) {
+                    Star<NC> s0, s1;
+                    load_pair<NC, ICOL>(cols, icol, stride, i, s0, s1);
+                    term<ROT, FREE, BG, MATH>(Wk, s0, A, s_exp2);
+                    term<ROT, FREE, BG, MATH>(Wk, s1, A, s_exp2);
+                    A.end_group();
+                    if (++done == 64) {     // fold the running products before they can overflow
+                        A.end_tile();
+                        done = 0;
+                    }
                 }
-                MCD_STAMP(1);
-                Accum<BG, MATH> A;
-                A.reset();
-                if (valid && Wk.prior_ok) {
-                    const int n2 = n & ~1;
-                    const int stepi = 2 * slices;
-                    int done = 0;
-                    for (int i = 2 * slice; i < n2; i += stepi) {
-                        Star<NC> s0, s1;
-                        load_pair<NC, ICOL>(cols, icol, stride, i, s0, s1);
-                        term<ROT, FREE, BG, MATH>(Wk, s0, A, s_exp2);
-                        term<ROT, FREE, BG, MATH>(Wk, s1, A, s_exp2);
-                        A.end_group();
-                        if (++done == 64) {     // fold the running products before they can overflow
-                            A.end_tile();
-                            done = 0;
+                if ((n & 1) && (n2 / 2) % slices == slice) {
+                    Star<NC> s0;
+                    load_one<NC, ICOL>(cols, icol, stride, n2, s0);
+                    term<ROT, FREE, BG, MATH>(Wk, s0, A, s_exp2);
+                    A.end_group();
+                }
+                A.end_tile();
+            }
+            red[tid] = (valid && Wk.prior_ok) ? A.value() : 0.0;
+            MCD_STAMP(2);
+            __syncthreads();
+            MCD_STAMP(3);
+            if (G > 1) {
+                // this CTA's slice sums -> L2 ...
+                ++phase;
+                const size_t first_slot = ((size_t)((phase & 1u) * n_segments + seg) * G) * C.sum_stride;
+                if (owner) {
+                    const double mine = sum_slices(red, lane, wl, slices);
+                    if (C.tagged) publish_sum(&C.group_sums[first_slot + (size_t)member * C.sum_stride + lane], mine, phase);
+                    else reinterpret_cast<double *>(C.group_sums)[first_slot + (size_t)member * C.sum_stride + lane] = mine;
+                }
+                if (!C.tagged) {
+                    // ... announced by one arrival per CTA on the segment's counter (the bar.sync before
+                    // the release orders the other threads' stores before it)
+                    __syncthreads();
+                    if (tid == 0)
+                        asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(C.group_arrivals + seg) : "memory");
+                }
+            }
+            // ... and while they travel, the random numbers of the next half-step
+            next = half == 0 ? draw(step, 1) : draw(step + 1u, 0);
+            MCD_STAMP(4);
+            if (G > 1) {
+                // every CTA's sums in member order: thread (lane, slice) takes members slice, slice + slices, ...
+                const size_t first_slot = ((size_t)((phase & 1u) * n_segments + seg) * G) * C.sum_stride;
+                double acc = 0.0;
+                if (!C.tagged) {
+                    // large groups: one thread waits for all arrivals, then plain 8-byte reads from L2
+                    if (tid == 0) {
+                        const unsigned long long target = (unsigned long long)phase * (unsigned long long)G;
+                        unsigned long long seen = 0;
+                        unsigned int polls = 0u;
+                        const long long t0 = clock64();
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(C.group_arrivals + seg) : "memory");
+                            if (seen < target && group_wait_failed(t0, polls, C.status)) group_lost = true;
+                        } while (seen < target && !group_lost);
+                    }
+                    __syncthreads();           // also: red[] is read above and rewritten below
+                    if (valid) {
+                        const double *sums = reinterpret_cast<const double *>(C.group_sums) + first_slot;
+                        constexpr int B = 16;
+                        for (int g0 = slice; g0 < G; g0 += B * slices) {
+                            double v[B];
+#pragma unroll
+                            for (int u = 0; u < B; ++u) {
+                                const int g = g0 + u * slices;
+                                v[u] = g < G ? __ldcg(&sums[(size_t)g * C.sum_stride + lane]) : 0.0;
+                            }
+#pragma unroll
+                            for (int u = 0; u < B; ++u) acc += v[u];
                         }
                     }
-                    if ((n & 1) && (n2 / 2) % slices == slice) {
-                        Star<NC> s0;
-                        load_one<NC, ICOL>(cols, icol, stride, n2, s0);
-                        term<ROT, FREE, BG, MATH>(Wk, s0, A, s_exp2);
-                        A.end_group();
-                    }
-                    A.end_tile();
-                }
-                red[tid] = (valid && Wk.prior_ok) ? A.value() : 0.0;
-                MCD_STAMP(2);
-                __syncthreads();
-                MCD_STAMP(3);
-                const bool owner = valid && slice == 0;
-                if (G > 1) {
-                    // this CTA's slice sums -> L2 ...
-                    ++phase;
-                    const size_t first_slot = ((size_t)((phase & 1u) * n_segments + seg) * G) * C.sum_stride;
-                    if (owner) {
-                        const double mine = sum_slices(red, lane, wl, slices);
-                        if (C.tagged) publish_sum(&C.group_sums[first_slot + (size_t)member * C.sum_stride + lane], mine, phase);
-                        else reinterpret_cast<double *>(C.group_sums)[first_slot + (size_t)member * C.sum_stride + lane] = mine;
-                    }
-                    if (!C.tagged) {
-                        // ... announced by one arrival per CTA on the segment's counter (the bar.sync before
-                        // the release orders the other threads' stores before it)
-                        __syncthreads();
-                        if (tid == 0)
-                            asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(C.group_arrivals + seg) : "memory");
-                    }
-                }
-                // ... and while they travel, the part of the acceptance test that does not depend on them
-                double lz = 0.0, lu = 0.0, old = 0.0;
-                int wa = 0;
-                if (owner) {
-                    double u0, u1;
-                    uniforms(C.seed, step, (uint32_t)half, (uint32_t)(seg * W + k), 1u, u0, u1);
-                    wa = active[k];
-                    lz = (NP - 1.0) * log(z);
-                    lu = log(u0);
-                    old = lnp[wa];
-                }
-                MCD_STAMP(4);
-                if (G > 1) {
-                    // every CTA's sums in member order: thread (lane, slice) takes members slice, slice + slices, ...
-                    const size_t first_slot = ((size_t)((phase & 1u) * n_segments + seg) * G) * C.sum_stride;
-                    double acc = 0.0;
-                    if (!C.tagged) {
-                        // large groups: one thread waits for all arrivals, then plain 8-byte reads from L2
-                        if (tid == 0) {
-                            const unsigned long long target = (unsigned long long)phase * (unsigned long long)G;
-                            unsigned long long seen = 0;
+                } else {
+                    // small groups: the words carry their own tag, every thread polls the ones it adds
+                    const TaggedSum *sums = C.group_sums + first_slot;
+                    __syncthreads();           // red[] is read above and rewritten below
+                    if (valid) {
+                        constexpr int B = 16;
+                        for (int g0 = slice; g0 < G; g0 += B * slices) {
+                            double v[B];
+                            unsigned int pending = 0u;
+#pragma unroll
+                            for (int u = 0; u < B; ++u) {
+                                const int g = g0 + u * slices;
+                                v[u] = 0.0;
+                                if (g < G && !read_sum(&sums[(size_t)g * C.sum_stride + lane], phase, v[u])) pending |= 1u << u;
+                            }
                             unsigned int polls = 0u;
                             const long long t0 = clock64();
-                            do {
-                                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(C.group_arrivals + seg) : "memory");
-                                if (seen < target && group_wait_failed(t0, polls, C.status)) group_lost = true;
-                            } while (seen < target && !group_lost);
-                        }
-                        __syncthreads();           // also: red[] is read above and rewritten below
-                        if (valid) {
-                            const double *sums = reinterpret_cast<const double *>(C.group_sums) + first_slot;
-                            constexpr int B = 16;
-                            for (int g0 = slice; g0 < G; g0 += B * slices) {
-                                double v[B];
+                            while (pending && !group_lost) {
 #pragma unroll
-                                for (int u = 0; u < B; ++u) {
-                                    const int g = g0 + u * slices;
-                                    v[u] = g < G ? __ldcg(&sums[(size_t)g * C.sum_stride + lane]) : 0.0;
-                                }
-#pragma unroll
-                                for (int u = 0; u < B; ++u) acc += v[u];
+                                for (int u = 0; u < B; ++u)
+                                    if ((pending >> u) & 1u)
+                                        if (read_sum(&sums[(size_t)(g0 + u * slices) * C.sum_stride + lane], phase, v[u]))
+                                            pending &= ~(1u << u);
+                                if (pending && group_wait_failed(t0, polls, C.status)) group_lost = true;
                             }
-                        }
-                    } else {
-                        // small groups: the words carry their own tag, every thread polls the ones it adds
-                        const TaggedSum *sums = C.group_sums + first_slot;
-                        __syncthreads();           // red[] is read above and rewritten below
-                        if (valid) {
-                            constexpr int B = 16;
-                            for (int g0 = slice; g0 < G; g0 += B * slices) {
-                                double v[B];
-                                unsigned int pending = 0u;
 #pragma unroll
-                                for (int u = 0; u < B; ++u) {
-                                    const int g = g0 + u * slices;
-                                    v[u] = 0.0;
-                                    if (g < G && !read_sum(&sums[(size_t)g * C.sum_stride + lane], phase, v[u])) pending |= 1u << u;
-                                }
-                                unsigned int polls = 0u;
-                                const long long t0 = clock64();
-                                while (pending && !group_lost) {
-#pragma unroll
-                                    for (int u = 0; u < B; ++u)
-                                        if ((pending >> u) & 1u)
-                                            if (read_sum(&sums[(size_t)(g0 + u * slices) * C.sum_stride + lane], phase, v[u]))
-                                                pending &= ~(1u << u);
-                                    if (pending && group_wait_failed(t0, polls, C.status)) group_lost = true;
-                                }
-#pragma unroll
-                                for (int u = 0; u < B; ++u) acc += v[u];
-                            }
+                            for (int u = 0; u < B; ++u) acc += v[u];
                         }
                     }
-                    red[tid] = acc;
-                    __syncthreads();
                 }
-                MCD_STAMP(5);
-                if (owner) {
-                    double total = sum_slices(red, lane, wl, slices);
-                    if (MATH == MCD_MATH_FAST) total = fma((double)seg_stars, -0.5 * kLn2Pi, total);
-                    if (!Wk.prior_ok) total = __longlong_as_double(0xfff0000000000000LL);
-                    const double diff = lz + total - old;
-                    if (diff > lu) {               // NaN never accepts
-                        for (int p = 0; p < NP; ++p) pos[(size_t)wa * NP + p] = q[p];
-                        lnp[wa] = total;
-                        nacc[wa] += 1;
-                    }
-                }
+                red[tid] = acc;
                 __syncthreads();
-                MCD_STAMP(6);
             }
+            MCD_STAMP(5);
+            if (owner) {
+                double total = sum_slices(red, lane, wl, slices);
+                if (MATH == MCD_MATH_FAST) total = fma((double)seg_stars, -0.5 * kLn2Pi, total);
+                if (!Wk.prior_ok) total = __longlong_as_double(0xfff0000000000000LL);
+                const double diff = cur.lz + total - lnp[wa];
+                if (diff > cur.lu) {               // NaN never accepts
+                    for (int p = 0; p < NP; ++p) pos[(size_t)wa * NP + p] = prop[(size_t)lane * NP + p];
+                    lnp[wa] = total;
+                    nacc[wa] += 1;
+                }
+            }
+            __syncthreads();
+            MCD_STAMP(6);
         }
         if (C.chain && member == 0) {
             const size_t rows = (size_t)n_segments * W;
@@ -1105,9 +1120,10 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
 #ifdef MCD_CHAIN_PROFILE
     if (blockIdx.x == 0 && tid == 0 && C.n_steps >= 100) {
         const double h = 2.0 * C.n_steps;
-        printf("chain profile (cycles per half-step, group %d): split %.0f | proposal %.0f | stars %.0f | sync %.0f | "
-               "publish+threshold %.0f | gather %.0f | accept %.0f | store %.0f\n", G, prof[0] / h, prof[1] / h,
-               prof[2] / h, prof[3] / h, prof[4] / h, prof[5] / h, prof[6] / h, prof[7] / h);
+        printf("chain profile (cycles per half-step, group %d): split %.0f | proposals %.0f | load_walker %.0f | "
+               "stars %.0f | sync %.0f | publish + next draws %.0f | gather %.0f | accept %.0f | store %.0f\n",
+               G, prof[0] / h, prof[9] / h, prof[1] / h, prof[2] / h, prof[3] / h, prof[4] / h, prof[5] / h,
+               prof[6] / h, prof[7] / h);
     }
 #endif
     if (member != 0) return;
@@ -1261,7 +1277,8 @@ static size_t chain_bytes(int nc, bool icol, long long stride, int n_walkers, in
     size_t b = (size_t)nc * stride * 8 + (icol ? (size_t)stride * 4 : 0);
     b += (size_t)kChainBlock * 8;                          // red
     b += (size_t)n_walkers * n_theta * 8 + (size_t)n_walkers * 8;   // pos, lnp
-    b += (size_t)n_walkers * (8 + 4 + 4);                  // keys, perm, nacc
+    b += (size_t)n_walkers * (8 + 4 + 4) + 8;              // keys, perm, nacc (+ alignment of prop)
+    b += (size_t)((n_walkers + 1) / 2) * n_theta * 8;      // prop
     return (b + 15) & ~(size_t)15;
 }
 
