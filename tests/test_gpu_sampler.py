@@ -143,6 +143,24 @@ def test_many_walkers_several_walker_groups(n_walkers, sampler_path):
     assert 0.1 < (s.naccepted / 12.0).mean() < 0.95
 
 
+def test_engine_choice_falls_back_to_the_graph_of_launches(monkeypatch):
+    """What the resident kernel cannot hold goes to the launch engine without the caller noticing: more
+    than 1024 walkers (a half-ensemble must fit one CTA), or an odd ensemble on either engine."""
+    monkeypatch.setenv('MCD_FORCE_RESIDENT_CHAIN', '1')
+    monkeypatch.setenv('MCD_NO_RESIDENT_CHAIN', '0')
+    monkeypatch.delenv('MCD_CHAIN_GROUP', raising=False)
+    model, truth = _mock_model(n_stars=1200, seed=33)
+    for n_walkers, engine in ((1100, 'graph'), (33, 'resident')):
+        pos = synthetic.initial_ball(truth, model.fitted_parameters, n_walkers, seed=2, scale=0.1)
+        s = samplers.DeviceEnsembleSampler(n_walkers, model.n_fitted_parameters, model.pack(), seed=8)
+        s.run_mcmc(pos, 6)
+        assert s.engine[0] == engine
+        chain, lnp = s.chain, s.lnprobability
+        again = model.lnprob(np.ascontiguousarray(chain[:, -1, :]))
+        assert np.allclose(again, lnp[:, -1], rtol=1e-12, atol=0)
+        assert s.naccepted.sum() > 0
+
+
 @pytest.mark.parametrize('cls,n_stars,n_walkers', [(ConstantFit, 3001, 16), (ModelFit, 10_000, 128), (ModelFit, 40_000, 32)])
 def test_resident_chain_groups_walk_the_same_chain(cls, n_stars, n_walkers, monkeypatch):
     """One CTA, a ragged group and a whole-GPU group hold different slices of the stars but draw the same
