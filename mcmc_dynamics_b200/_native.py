@@ -65,9 +65,10 @@ SYMBOLS = {
     'mcd_pack_reconfigure': (ctypes.c_int, [_vp, ctypes.POINTER(PackDesc)]),
     'mcd_destroy': (None, [_vp]),
     'mcd_get_info': (ctypes.c_int, [_vp, ctypes.POINTER(Info)]),
-    'mcd_lnlike': (ctypes.c_int, [_vp, _c_double_p, ctypes.c_int32, _c_double_p]),
+    # the two per-call entry points take raw addresses (ndarray.ctypes.data): no pointer object per call
+    'mcd_lnlike': (ctypes.c_int, [_vp, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
     'mcd_lnlike_device': (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, _vp]),
-    'mcd_lnprob': (ctypes.c_int, [_vp, _c_double_p, ctypes.c_int32, _c_double_p]),
+    'mcd_lnprob': (ctypes.c_int, [_vp, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
     'mcd_lnprob_device': (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, _vp]),
     'mcd_lnprob_partial_device': (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, _vp]),
     'mcd_exchange_bytes': (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, _c_int64_p]),

@@ -91,6 +91,8 @@ class Runner(object):
         self.math_mode = math_mode
         self._packed = None
         self._packed_signature = None
+        self._packed_stamps = None
+        self._expression_priors_present = False
 
     # ------------------------------------------------------------------------------------------
     # introspection (analysis/runner.py:108-141, 662-673)
@@ -167,8 +169,13 @@ class Runner(object):
     def pack(self):
         """Upload the star columns (first call) and compile the current parameter routing.  Called
         lazily by every likelihood entry point; cheap when nothing changed."""
+        stamps = (pack.edit_stamps(self.parameters), self.math_mode)
+        if self._packed is not None and stamps == self._packed_stamps:
+            return self._packed                       # nothing was assigned to any parameter since the last call
         signature = (pack.routing_signature(self.parameters, self.MODEL_PARAMETERS), self.math_mode)
+        self._expression_priors_present = any(par.lnprior is not None for par in self.parameters.values())
         if self._packed is not None and signature == self._packed_signature:
+            self._packed_stamps = stamps
             return self._packed
         desc, keep = self._descriptor()
         if self._packed is None:
@@ -177,12 +184,14 @@ class Runner(object):
             desc.n_stars = self._packed.n_stars
             self._packed.reconfigure(desc)
         self._packed_signature = signature
+        self._packed_stamps = stamps
         return self._packed
 
     def __getstate__(self):
         state = self.__dict__.copy()
         state['_packed'] = None              # device handles do not pickle; re-packed on first use
         state['_packed_signature'] = None
+        state['_packed_stamps'] = None
         return state
 
     # ------------------------------------------------------------------------------------------
@@ -261,7 +270,7 @@ class Runner(object):
         come back as exactly ``-inf`` without being evaluated."""
         theta, scalar = self._as_batch(values)
         out = self.pack().lnprob(theta)
-        if self._has_expression_priors():
+        if self._expression_priors_present:           # refreshed by pack() whenever a parameter was edited
             extra = self._lnprior_batch(theta)
             with np.errstate(invalid='ignore'):
                 out = np.where(np.isfinite(extra), out + extra, -np.inf)

@@ -40,6 +40,12 @@ def _unit_scale(name, unit):
             name, unit, SLOT_UNITS[name]))
 
 
+def edit_stamps(parameters):
+    """Cheap change detector for a ``Parameters`` object: the version stamps of its members (every
+    attribute assignment on a ``Parameter`` takes a new stamp).  Equal stamps = nothing was edited."""
+    return tuple([par._version for par in parameters.values()])
+
+
 def routing_signature(parameters, model_parameters):
     """Everything about a ``Parameters`` object the packed state depends on; a change triggers a
     re-pack before the next likelihood call (parameters are usually edited between construction and
@@ -177,15 +183,17 @@ class PackedModel(object):
         """Host buffers in, host buffer out: copy, one kernel launch, copy, synchronise."""
         theta, n_walkers, shape = self._theta(theta)
         out = np.empty(shape, dtype=np.float64)
-        _native.check(self._lib.mcd_lnprob(self.handle, _native.as_double_ptr(theta), n_walkers,
-                                           _native.as_double_ptr(out)))
+        rc = self._lib.mcd_lnprob(self.handle, theta.ctypes.data, n_walkers, out.ctypes.data)
+        if rc != 0:
+            _native.check(rc)
         return out
 
     def lnlike(self, theta):
         theta, n_walkers, shape = self._theta(theta)
         out = np.empty(shape, dtype=np.float64)
-        _native.check(self._lib.mcd_lnlike(self.handle, _native.as_double_ptr(theta), n_walkers,
-                                           _native.as_double_ptr(out)))
+        rc = self._lib.mcd_lnlike(self.handle, theta.ctypes.data, n_walkers, out.ctypes.data)
+        if rc != 0:
+            _native.check(rc)
         return out
 
     def lnlike_per_star(self, theta):

@@ -23,6 +23,8 @@ import re
 from collections import OrderedDict
 from copy import deepcopy
 
+import itertools
+
 import numpy as np
 from scipy import stats
 
@@ -266,6 +268,15 @@ def _jsonable(obj):
 class Parameter(object):
     """One model parameter: value, unit, bounds, fixed flag and the optional ``initials`` /
     ``lnprior`` / ``expr`` expression strings (parameter.py:558-587)."""
+
+    #: source of ``_version`` stamps: every attribute assignment on any parameter takes a new one, so
+    #: ``tuple(p._version for p in parameters.values())`` changes iff something was edited (what the
+    #: likelihood entry points compare per call instead of rebuilding the full routing signature)
+    _stamps = itertools.count(1)
+
+    def __setattr__(self, key, value):
+        object.__setattr__(self, key, value)
+        object.__setattr__(self, '_version', next(Parameter._stamps))
 
     def __init__(self, name, value=None, unit=None, fixed=False, min=-np.inf, max=np.inf, label=None,
                  initials=None, lnprior=None, expr=None, user_data=None):

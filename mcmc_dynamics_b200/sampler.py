@@ -72,16 +72,16 @@ class HostEnsembleSampler(object):
     # -- sampling -----------------------------------------------------------------------------
     def compute_log_prob(self, coords):
         coords = np.asarray(coords, dtype=np.float64)
-        if np.any(np.isinf(coords)):
-            raise ValueError("At least one parameter value was infinite")
-        if np.any(np.isnan(coords)):
+        if not np.isfinite(coords).all():             # one pass in the common case, emcee's messages otherwise
+            if np.any(np.isinf(coords)):
+                raise ValueError("At least one parameter value was infinite")
             raise ValueError("At least one parameter value was NaN")
         self.n_log_prob_calls += 1
         if self.vectorize:
             log_prob = np.asarray(self.log_prob_fn(coords), dtype=np.float64)
         else:
             log_prob = np.array([float(self.log_prob_fn(row)) for row in coords], dtype=np.float64)
-        if np.any(np.isnan(log_prob)):
+        if np.isnan(log_prob).any():
             raise ValueError("Probability function returned NaN")
         return log_prob
 

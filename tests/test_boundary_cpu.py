@@ -214,3 +214,23 @@ def test_radial_bins_partition():
     assert np.all(sizes >= 25) and sizes.sum() == 600
     sub = data.fetch_radial_bin(1)
     assert sub.sample_size == sizes[1]
+
+
+def test_parameter_edit_stamps_detect_every_assignment():
+    """``Runner.pack`` compares the parameters' version stamps per call instead of rebuilding the full
+    routing signature: reading never changes them, any assignment does."""
+    from mcmc_dynamics_b200 import pack
+    from mcmc_dynamics_b200.analysis import ModelFit
+    parameters = ModelFit.default_parameters()
+    before = pack.edit_stamps(parameters)
+    signature = pack.routing_signature(parameters, ModelFit.MODEL_PARAMETERS)
+    for par in parameters.values():
+        par.value, par.unit, par.fixed, par.min, par.max          # reads
+    assert pack.edit_stamps(parameters) == before
+    assert pack.routing_signature(parameters, ModelFit.MODEL_PARAMETERS) == signature
+    name = next(iter(parameters))
+    parameters[name].set(fixed=not parameters[name].fixed)
+    after = pack.edit_stamps(parameters)
+    assert after != before
+    parameters[name].max = 1e6
+    assert pack.edit_stamps(parameters) != after
