@@ -858,6 +858,33 @@ __device__ __forceinline__ double sum_slices(const double *red, int lane, int wl
     return (a0 + a1) + (a2 + a3);
 }
 
+// The counter-based random numbers of one half-step for active walker k = threadIdx.x: stretch factor
+// z = ((a-1) u + 1)^2 / a, partner index, (P-1) ln z and ln u of the acceptance test (emcee
+// StretchMove).  Out of line: one copy of two Philox blocks and two logs instead of three.
+struct Draw {
+    double z, lz, lu;
+    int partner;
+};
+static __device__ __noinline__ Draw draw_half_step(const ChainParams &C, int n_theta, int seg, unsigned int step, int half) {
+    Draw d{1.0, 0.0, 0.0, 0};
+    const int W = C.n_walkers;
+    const int ns = half == 0 ? C.n0 : W - C.n0;
+    const int k = (int)threadIdx.x;
+    if (k < ns) {
+        const int nc = W - ns;
+        double u0, u1;
+        uniforms(C.seed, step, (uint32_t)half, (uint32_t)(seg * W + k), 0u, u0, u1);
+        const double t = (C.a - 1.0) * u0 + 1.0;
+        d.z = t * t / C.a;
+        const int j = (int)(u1 * nc);
+        d.partner = j >= nc ? nc - 1 : j;
+        d.lz = (n_theta - 1.0) * log(d.z);
+        uniforms(C.seed, step, (uint32_t)half, (uint32_t)(seg * W + k), 1u, u0, u1);
+        d.lu = log(u0);
+    }
+    return d;
+}
+
 template <int ROT, int FREE, int BG, int MATH>
 __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constant__ LaunchParams P,
                                                             const __grid_constant__ ChainParams C) {
@@ -910,32 +937,15 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
     long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long last_ = clock64();
 #endif
-    // Everything a half-step draws from the counter-based generator -- stretch factor z, partner index,
-    // (P-1) ln z and ln u of the acceptance test -- depends on (step, half, walker) only, not on the
-    // state of the chain: thread k < (walkers of that half) computes it one half-step ahead, while the
-    // slice sums of the current half-step travel, and keeps it in registers.
-    struct Draw {
-        double z, lz, lu;
-        int partner;
-    };
-    auto draw = [&](unsigned int step, int half) {
-        Draw d{1.0, 0.0, 0.0, 0};
-        const int ns = half == 0 ? C.n0 : W - C.n0;
-        if (tid < ns) {
-            const int nc = W - ns;
-            double u0, u1;
-            uniforms(C.seed, step, (uint32_t)half, (uint32_t)(seg * W + tid), 0u, u0, u1);
-            const double t = (C.a - 1.0) * u0 + 1.0;
-            d.z = t * t / C.a;
-            const int j = (int)(u1 * nc);
-            d.partner = j >= nc ? nc - 1 : j;
-            d.lz = (NP - 1.0) * log(d.z);
-            uniforms(C.seed, step, (uint32_t)half, (uint32_t)(seg * W + tid), 1u, u0, u1);
-            d.lu = log(u0);
-        }
-        return d;
-    };
-    Draw next = draw(C.step0, 0);
+    // Everything a half-step draws from the counter-based generator (`draw_half_step`) depends on (step,
+    // half, walker) only, not on the state of the chain: thread k < (walkers of that half) computes it one
+    // half-step ahead, while the slice sums of the current half-step travel, and keeps it in registers.
+    Draw next = draw_half_step(C, NP, seg, C.step0, 0);
+    // thread = (walker `lane` of the active half, star slice): the mapping of both halves, computed once
+    // (three integer divisions per half otherwise)
+    const int ns0 = C.n0, ns1 = W - C.n0;
+    const int slices0 = kChainBlock / ns0, slices1 = kChainBlock / ns1;
+    const int lane0 = tid % ns0, lane1 = tid % ns1, slice0 = tid / ns0, slice1 = tid / ns1;
 
     for (int it = 0; it < C.n_steps; ++it) {
         const unsigned int step = C.step0 + (unsigned int)it;
@@ -957,13 +967,10 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
         MCD_STAMP(0);
         for (int half = 0; half < 2; ++half) {
             // each half of the ensemble fits the CTA (n_walkers <= kChainMaxWalkers = 2 kChainBlock)
-            const int ns = half == 0 ? C.n0 : W - C.n0;
             const int *active = perm + (half == 0 ? 0 : C.n0);
             const int *other = perm + (half == 0 ? C.n0 : 0);
-            // thread = (walker `lane` of the active half, star slice)
-            const int wl = ns;
-            const int slices = kChainBlock / wl;
-            const int lane = tid % wl, slice = tid / wl;
+            const int wl = half == 0 ? ns0 : ns1, slices = half == 0 ? slices0 : slices1;
+            const int lane = half == 0 ? lane0 : lane1, slice = half == 0 ? slice0 : slice1;
             const bool valid = slice < slices;
             const bool owner = tid < wl;               // slice 0: proposes, adds up and accepts for walker `lane`
             const Draw cur = next;
@@ -1028,7 +1035,7 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
                 }
             }
             // ... and while they travel, the random numbers of the next half-step
-            next = half == 0 ? draw(step, 1) : draw(step + 1u, 0);
+            next = draw_half_step(C, NP, seg, step + (unsigned int)half, half ^ 1);
             MCD_STAMP(4);
             if (G > 1) {
                 // every CTA's sums in member order: thread (lane, slice) takes members slice, slice + slices, ...
@@ -1066,7 +1073,7 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
                     const TaggedSum *sums = C.group_sums + first_slot;
                     __syncthreads();           // red[] is read above and rewritten below
                     if (valid) {
-                        constexpr int B = 16;
+                        constexpr int B = 4;
                         for (int g0 = slice; g0 < G; g0 += B * slices) {
                             double v[B];
                             unsigned int pending = 0u;
