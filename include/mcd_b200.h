@@ -178,7 +178,12 @@ int mcd_gaussian_lnlike(int32_t device, const double *v, const double *verr, int
                         double *out_host);
 
 /* Device-resident affine-invariant ensemble sampler (emcee's default red/blue StretchMove(a=2)
- * as driven by analysis/runner.py:403,416-419).  All state lives on the device. */
+ * as driven by analysis/runner.py:403,416-419).  All state lives on the device.  mcd_ensemble_run picks
+ * one of two engines per call: the resident chain kernel (the whole run is one cooperative launch, every
+ * SM keeps a slice of the stars in shared memory; catalogues up to ~9e5 stars, <= 1024 walkers, one GPU)
+ * or a CUDA graph of likelihood launches with proposal and acceptance fused in (any size, star shards).
+ * Environment overrides for tests and sweeps: MCD_NO_RESIDENT_CHAIN=1, MCD_FORCE_RESIDENT_CHAIN=1,
+ * MCD_CHAIN_GROUP=<CTAs per segment>, MCD_CHAIN_EXCHANGE=tagged|counter. */
 typedef struct mcd_ensemble mcd_ensemble;
 int mcd_ensemble_create(mcd_handle *h, int32_t n_walkers, uint64_t seed, double stretch_a, mcd_ensemble **out);
 void mcd_ensemble_destroy(mcd_ensemble *e);
