@@ -96,7 +96,8 @@ typedef struct mcd_pack_desc {
      * bin/run_tests.py:81-97, one ConstantFit per bin.  Stars [segment_offsets[s],
      * segment_offsets[s+1]) of the columns belong to segment s; theta is then
      * [n_segments][n_walkers][n_theta], results are [n_segments][n_walkers], and `n_walkers` in
-     * every call is the number of walkers PER segment. */
+     * every call is the number of walkers PER segment.  Available for MCD_BG_NONE and
+     * MCD_BG_FIXED_PMEMBER (ConstantFit(data_i, parameters, background=background), bin/run.py:186). */
     int32_t n_segments;               /* 0 or 1: one problem                                    */
     const int64_t *segment_offsets;   /* [n_segments + 1] host array, or NULL                   */
 } mcd_pack_desc;

@@ -5,8 +5,8 @@ The reference's real workflow fits a ``ConstantFit`` to every radial bin in turn
 100 steps per bin), each an independent, latency-bound MCMC over 50-500 stars.  ``RadialBinsFit``
 packs all bins into one segmented device handle: one launch evaluates every walker of every bin, and
 the device sampler advances all per-bin ensembles together (``csrc/mcd_kernels.cu`` segments,
-``csrc/mcd_sampler.cu``).  Bins share the model class and the ``Parameters`` object (bounds, fixed
-values, initials), exactly like the loop bodies of the scripts.
+``csrc/mcd_sampler.cu``).  Bins share the model class, the ``Parameters`` object (bounds, fixed
+values, initials) and the optional background object, exactly like the loop bodies of the scripts.
 """
 import logging
 
@@ -29,16 +29,19 @@ class RadialBinsFit(object):
     Parameters
     ----------
     data : DataReader with a ``bin`` column (integers 0..B-1)
-    model_class : a model class without background component (default ``ConstantFit``)
+    model_class : a model class without fitted background parameters (default ``ConstantFit``)
     parameters : Parameters shared by all bins, or None for the class default
+    background : None, or the background object of ``ConstantFit(data_i, parameters=parameters,
+        background=background)`` (``bin/run.py:186``): every bin is then fitted with the fixed-background
+        mixture, which needs the ``pmember`` column (``analysis/runner.py:272-286``)
     """
 
-    def __init__(self, data, model_class=ConstantFit, parameters=None, device=0, math_mode='fast'):
+    def __init__(self, data, model_class=ConstantFit, parameters=None, background=None, device=0, math_mode='fast'):
         assert isinstance(data, DataReader), "'data' must be instance of {0}".format(DataReader.__module__)
         if 'bin' not in data.data.columns:
             raise IOError("Input data missing required column <bin>; call make_radial_bins() first.")
         if model_class.BACKGROUND != _native.BG_NONE:
-            raise NotImplementedError('RadialBinsFit supports the models without background component')
+            raise NotImplementedError('RadialBinsFit supports the models without fitted background parameters')
         labels = np.asarray(getattr(data.data['bin'], 'value', data.data['bin'])).astype(np.int64)
         if labels.min() < 0:
             raise ValueError('negative bin labels: every star must belong to a bin')
@@ -49,8 +52,9 @@ class RadialBinsFit(object):
         self.bin_sizes = counts
         self.order = order
         # a template model on the whole (bin-sorted) catalogue provides validation, units, parameters
-        self.template = model_class(DataReader(data.data[order]), parameters=parameters, device=device,
-                                    math_mode=math_mode)
+        self.background = background
+        self.template = model_class(DataReader(data.data[order]), parameters=parameters, background=background,
+                                    device=device, math_mode=math_mode)
         self.parameters = self.template.parameters
         self.model_class = model_class
         self.device = device
@@ -72,7 +76,7 @@ class RadialBinsFit(object):
             return self._packed
         t._check_expressions()
         desc, keep = pack.build_descriptor(
-            t.parameters, t.MODEL_PARAMETERS, rotation=t.ROTATION, background=_native.BG_NONE,
+            t.parameters, t.MODEL_PARAMETERS, rotation=t.ROTATION, background=t._background_mode(),
             columns=t._star_columns() if self._packed is None else {},
             math_mode=_native.MATH_FAST if t.math_mode == 'fast' else _native.MATH_PLAIN, device=self.device,
             segment_offsets=self.segment_offsets)
@@ -109,8 +113,8 @@ class RadialBinsFit(object):
         """A stand-alone model object on bin `i` (the reference's loop body), e.g. for cross-checks."""
         lo, hi = self.segment_offsets[i], self.segment_offsets[i + 1]
         sub = DataReader(self.template.data.data[np.arange(lo, hi)])
-        return self.model_class(sub, parameters=self.parameters.copy(), device=self.device,
-                                math_mode=self.template.math_mode)
+        return self.model_class(sub, parameters=self.parameters.copy(), background=self.background,
+                                device=self.device, math_mode=self.template.math_mode)
 
     def __call__(self, n_walkers=100, n_steps=100, pos=None, seed=None):
         """Run every bin's ensemble (``cf(n_walkers=100, n_steps=100)`` of ``bin/run_tests.py:97``) on

@@ -201,7 +201,10 @@ extern "C" void mcd_destroy(mcd_handle *h) {
 static int setup_segments(mcd_handle *h, const mcd_pack_desc *desc) {
     const int S = desc->n_segments;
     if (!desc->segment_offsets) return fail(-1, "n_segments > 1 needs segment_offsets");
-    if (desc->background != MCD_BG_NONE) return fail(-1, "segmented handles support the models without background component");
+    // the per-bin fits of bin/run.py:186 are ConstantFit(data_i, parameters, background=background):
+    // no background component, or the fixed-background mixture with per-star pmember
+    if (desc->background != MCD_BG_NONE && desc->background != MCD_BG_FIXED_PMEMBER)
+        return fail(-1, "segmented handles support the models without fitted background parameters");
     if (S > 65535) return fail(-1, "at most 65535 segments per handle");
     std::vector<long long> begin(S + 1), packed(S);
     long long pos = 0, longest = 0;

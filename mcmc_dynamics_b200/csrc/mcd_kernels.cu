@@ -1190,8 +1190,8 @@ static cudaError_t launch_one(const LaunchParams &p, cudaStream_t stream) {
     const size_t smem = (size_t)kStages * kMaxTile * (NC * 8 + (has_icol(BG, MATH) ? 4 : 0));
     dim3 grid((unsigned)p.n_chunks * (unsigned)p.n_groups, (unsigned)std::max(1, p.n_segments));
     if (p.seg_begin) {
-        // segmented handles exist for the models without background component (RadialBinsFit)
-        if constexpr (BG == MCD_BG_NONE) {
+        // segmented handles (RadialBinsFit) exist for the models without fitted background parameters
+        if constexpr (BG == MCD_BG_NONE || BG == MCD_BG_FIXED_PMEMBER) {
             if (p.fuse.enabled) lnlike_kernel<ROT, FREE, BG, MATH, true, true><<<grid, kBlock, smem, stream>>>(p);
             else lnlike_kernel<ROT, FREE, BG, MATH, true, false><<<grid, kBlock, smem, stream>>>(p);
         } else {

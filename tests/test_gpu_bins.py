@@ -78,3 +78,42 @@ def test_bins_need_labels_and_plain_models():
     data, truth = synthetic.mock_cluster(100, seed=1)
     with pytest.raises(IOError):
         RadialBinsFit(data)
+
+
+@pytest.mark.parametrize('path', ['resident', 'graph'])
+def test_binned_fits_with_a_background_object(path, monkeypatch):
+    """``ConstantFit(data_i, parameters=parameters, background=background)`` per radial bin
+    (bin/run.py:186): the fixed-background mixture (analysis/runner.py:272-286) in one segmented launch
+    equals one model object per bin and the oracle; the batched device sampler runs on it."""
+    from mcmc_dynamics_b200.background import SingleStars
+    monkeypatch.setenv('MCD_NO_RESIDENT_CHAIN', '1' if path == 'graph' else '0')
+    monkeypatch.setenv('MCD_FORCE_RESIDENT_CHAIN', '1' if path == 'resident' else '0')
+    columns, truth = synthetic.mock_cluster(1800, seed=12, as_reader=False)
+    columns, sample_field = synthetic.add_background(columns, truth, seed=112)
+    data = synthetic.reader_from_columns(columns)
+    data.make_radial_bins(truth['ra_center'], truth['dec_center'], nstars=60, dlogr=0.1)
+    background = SingleStars(sample_field(300, seed=5))
+    fit = RadialBinsFit(data, model_class=ConstantFit, background=background)
+    fit.parameters['ra_center'].set(value=truth['ra_center'], fixed=True)
+    fit.parameters['dec_center'].set(value=truth['dec_center'], fixed=True)
+    n_walkers = 20
+    theta = np.stack([synthetic.initial_ball(truth, fit.fitted_parameters, n_walkers, seed=30 + b, scale=0.3)
+                      for b in range(fit.n_bins)])
+    got = fit.lnprob(theta)
+    assert got.shape == (fit.n_bins, n_walkers) and np.all(np.isfinite(got))
+    plain = RadialBinsFit(data, model_class=ConstantFit)
+    plain.parameters['ra_center'].set(value=truth['ra_center'], fixed=True)
+    plain.parameters['dec_center'].set(value=truth['dec_center'], fixed=True)
+    assert not np.allclose(got, plain.lnprob(theta))                  # the mixture is really evaluated
+    for b in (0, fit.n_bins // 2, fit.n_bins - 1):
+        single = fit.bin_model(b)
+        assert harness.relative_error(got[b], single.lnprob(theta[b])) < 1e-13
+        want = harness.oracle_for(single).lnprob_many(theta[b])
+        assert harness.relative_error(got[b], want) < 1e-9
+    engine = fit(n_walkers=n_walkers, n_steps=40, pos=theta, seed=3)
+    assert engine.engine[0] == path
+    chain, lnp = engine.chain, engine.lnprobability
+    assert chain.shape == (fit.n_bins, n_walkers, 40, fit.n_fitted_parameters) and np.all(np.isfinite(lnp))
+    again = fit.lnprob(np.ascontiguousarray(chain[:, :, -1, :]))
+    assert np.allclose(again, lnp[:, :, -1], rtol=1e-12, atol=0)
+    assert 0.1 < (engine.naccepted / 40.0).mean() < 0.95
