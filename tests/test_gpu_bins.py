@@ -117,3 +117,22 @@ def test_binned_fits_with_a_background_object(path, monkeypatch):
     again = fit.lnprob(np.ascontiguousarray(chain[:, :, -1, :]))
     assert np.allclose(again, lnp[:, :, -1], rtol=1e-12, atol=0)
     assert 0.1 < (engine.naccepted / 40.0).mean() < 0.95
+
+
+def test_segmented_lnprob_with_a_free_centre():
+    """Bins that also fit the centre (the free-centre kernels in a segmented launch)."""
+    data, truth = synthetic.mock_cluster(1500, seed=14)
+    data.make_radial_bins(truth['ra_center'], truth['dec_center'], nstars=80, dlogr=0.1)
+    fit = RadialBinsFit(data, model_class=ConstantFit)
+    fit.parameters['ra_center'].set(value=truth['ra_center'], fixed=False)
+    fit.parameters['dec_center'].set(value=truth['dec_center'], fixed=False)
+    assert 'ra_center' in fit.fitted_parameters
+    n_walkers = 12
+    theta = np.stack([synthetic.initial_ball(truth, fit.fitted_parameters, n_walkers, seed=50 + b, scale=0.2)
+                      for b in range(fit.n_bins)])
+    got = fit.lnprob(theta)
+    for b in (0, fit.n_bins - 1):
+        single = fit.bin_model(b)
+        assert harness.relative_error(got[b], single.lnprob(theta[b])) < 1e-12
+        want = harness.oracle_for(single).lnprob_many(theta[b])
+        assert harness.relative_error(got[b], want) < 1e-9
