@@ -194,3 +194,23 @@ def test_resident_chain_groups_walk_the_same_chain(cls, n_stars, n_walkers, monk
             assert np.array_equal(chains[group, 'tagged'][0], chains[group, 'counter'][0])
     again = model.lnprob(np.ascontiguousarray(ref_chain[:, -1, :]))
     assert np.allclose(again, ref_lnp[:, -1], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize('variant', ['ConstantFit+bg', 'ConstantFitGB', 'ModelFitGB', 'ModelFitConstantBackground'])
+def test_device_sampler_on_the_background_variants(variant, sampler_path):
+    """Every mixture kernel inside both sampler engines: the stored log-probabilities are the model's
+    lnprob of the stored positions (checked against the oracle too), walkers move and stay inside the
+    box prior."""
+    from oracle import harness
+    model, oracle, theta, truth = build(variant, n_stars=1500, seed=3)
+    n_walkers = 4 * model.n_fitted_parameters
+    pos = theta(n_walkers, seed=11, scale=0.05)
+    s = samplers.DeviceEnsembleSampler(n_walkers, model.n_fitted_parameters, model.pack(), seed=21)
+    s.run_mcmc(pos, 25)
+    assert s.engine[0] == sampler_path.split('-')[0]
+    chain, lnp = s.chain, s.lnprobability
+    assert np.all(np.isfinite(lnp))
+    last = np.ascontiguousarray(chain[:, -1, :])
+    assert np.allclose(model.lnprob(last), lnp[:, -1], rtol=1e-12, atol=0)
+    assert harness.relative_error(lnp[:8, -1], oracle.lnprob_many(last[:8])) < 1e-9
+    assert 0.05 < (s.naccepted / 25.0).mean() < 0.95
