@@ -364,8 +364,14 @@ static void choose_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p)
     p.n_tiles = (int)((h->max_segment + best_tile - 1) / best_tile);
     p.tiles_per_chunk = best_tpc;
     p.n_chunks = std::max(1, (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk);
-    p.super = kSuper;
-    p.n_super = (p.n_chunks + kSuper - 1) / kSuper;
+    // Cross-CTA reduction: the CTA that takes the last ticket adds the per-CTA sums with all its threads,
+    // kGatherDepth * slices rows per L2 round trip (measured ~0.9 us each, tools/probe/launch_timeline.sh).
+    // One level while that is a single round trip; otherwise two levels with super-chunks of at least one
+    // round trip's worth of rows, sqrt(chunks) for large launches.
+    const int per_trip = kGatherDepth * p.slices;
+    p.super = p.n_chunks <= per_trip ? std::max(1, p.n_chunks)
+                                     : std::max(per_trip, (int)std::ceil(std::sqrt((double)p.n_chunks)));
+    p.n_super = (p.n_chunks + p.super - 1) / p.super;
 }
 
 static int ensure_scratch(mcd_handle *h, const LaunchParams &p) {

@@ -15,7 +15,7 @@ constexpr int kStages = 2;         // TMA bulk-copy stages in flight per CTA
 constexpr int kMaxRanks = 8;        // GPUs of one box that can share a star-sharded catalogue
 constexpr int kMaxXchgGroups = 64;  // walker groups per call of the fused cross-GPU reduction
 constexpr int kXchgSlots = 4;       // exchange buffers in rotation: 0/1 host-counted calls, 2/3 sampler half-steps
-constexpr int kSuper = 32;         // chunks per super-chunk of the two-level cross-CTA reduction
+constexpr int kGatherDepth = 8;     // per-CTA sums one thread of the reducing CTA loads per L2 round trip
 constexpr int kWaves = 8;          // CTA waves a large catalogue is cut into (tail balance)
 constexpr double kDeg2Rad = 0.017453292519943295769236907684886;
 constexpr double kR0Arcmin = 3437.7467707849392526078892888463;   // 10800/pi, calc_xy_offset.py:11

@@ -572,9 +572,60 @@ static __device__ __noinline__ void accept_proposal(const LaunchParams &P, int s
 // applies the prior mask and hands the result on (output vector, cross-GPU exchange or the fused
 // acceptance).  `owner` threads (slice 0 of a valid walker) carry walker `w`.  Out of line on
 // purpose: the register allocation of the star loop must not depend on this cold code.
+// -DMCD_KERNEL_PROFILE: thread 0 of every CTA stamps %globaltimer at the stages of a likelihood launch;
+// the CTA that finishes the launch prints its own timeline relative to the earliest CTA start
+// (tools/profile_config.py with MCD_B200_LIB pointing at such a build).  Not in the product library.
+#ifdef MCD_KERNEL_PROFILE
+__device__ unsigned long long g_kernel_start[2] = {~0ull, ~0ull};
+__device__ unsigned int g_kernel_launch = 0;
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define MCD_KSTAMP(arr, i) do { if (threadIdx.x == 0) (arr)[i] = global_ns(); } while (0)
+#else
+#define MCD_KSTAMP(arr, i) do { } while (0)
+#endif
+
+// Sum rows [first, last) of a [rows][n_walkers] array of per-CTA sums for walker w, with every thread
+// of the CTA loading (thread (lane, slice) takes rows first + slice, first + slice + slices, ...:
+// kGatherDepth independent loads in flight per thread, one L2 round trip for up to kGatherDepth * slices rows).  The order
+// of the additions depends on the launch geometry only, not on which CTA runs this.  All threads of
+// the CTA must call; the result is valid in the owner threads (slice 0).
+__device__ __forceinline__ double gather_rows(const double *rows, int first, int last, const LaunchParams &P, int w,
+                                              double *red) {
+    const int tid = threadIdx.x;
+    const int lane = tid % P.wl, slice = tid / P.wl;
+    const bool valid = slice < P.slices && w < P.n_walkers;
+    double acc = 0.0;
+    if (valid) {
+        const size_t stride = (size_t)P.n_walkers;
+        const int step = P.slices;
+        for (int c = first + slice; c < last; c += kGatherDepth * step) {
+            double v[kGatherDepth];
+#pragma unroll
+            for (int u = 0; u < kGatherDepth; ++u) {
+                const int row = c + u * step;
+                v[u] = row < last ? __ldcg(&rows[(size_t)row * stride + w]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < kGatherDepth; ++u) acc += v[u];
+        }
+    }
+    __syncthreads();                       // red[] may still be read by the caller's slice sum
+    red[tid] = acc;
+    __syncthreads();
+    double total = 0.0;
+    if (valid && slice == 0)
+        for (int j = 0; j < P.slices; ++j) total += red[j * P.wl + lane];
+    return total;
+}
+
 template <int MATH, bool FUSE>
 __device__ __noinline__ void finish_walker_group(const LaunchParams &P, int seg, int chunk, int group, int w, int n_chunks,
-                                                 long long seg_stars, bool owner, int prior_ok, int *s_last) {
+                                                 long long seg_stars, bool owner, int prior_ok, int *s_last, double *red,
+                                                 unsigned long long *stamps = nullptr) {
     const int tid = threadIdx.x;
     const int n_super = (n_chunks + P.super - 1) / P.super;
     unsigned int *cnt = P.counters + ((size_t)seg * P.n_groups + group) * (P.n_super + 1);
@@ -584,26 +635,20 @@ __device__ __noinline__ void finish_walker_group(const LaunchParams &P, int seg,
     __syncthreads();
     if (tid == 0) *s_last = (take_ticket(&cnt[sup]) == (unsigned int)(c_end - c_begin) - 1u);
     __syncthreads();
+    MCD_KSTAMP(stamps, 7);
     if (!*s_last) return;
-    double level1 = 0.0;
-    if (owner) {
-#pragma unroll 4
-        for (int cidx = c_begin; cidx < c_end; ++cidx)
-            level1 += __ldcg(&P.partials[((size_t)seg * P.n_chunks + cidx) * P.n_walkers + w]);
-    }
+    const double level1 = gather_rows(P.partials + (size_t)seg * P.n_chunks * P.n_walkers, c_begin, c_end, P, w, red);
     if (tid == 0) cnt[sup] = 0u;
+    MCD_KSTAMP(stamps, 8);
     double total = 0.0;
     if (n_super > 1) {
         if (owner) P.partials2[((size_t)seg * P.n_super + sup) * P.n_walkers + w] = level1;
         __syncthreads();
         if (tid == 0) *s_last = (take_ticket(&cnt[P.n_super]) == (unsigned int)n_super - 1u);
         __syncthreads();
+        MCD_KSTAMP(stamps, 9);
         if (!*s_last) return;
-        if (owner) {
-#pragma unroll 4
-            for (int k = 0; k < n_super; ++k)
-                total += __ldcg(&P.partials2[((size_t)seg * P.n_super + k) * P.n_walkers + w]);
-        }
+        total = gather_rows(P.partials2 + (size_t)seg * P.n_super * P.n_walkers, 0, n_super, P, w, red);
         if (tid == 0) cnt[P.n_super] = 0u;
     } else {
         total = level1;            // at most P.super chunks: one level is the whole reduction
@@ -631,6 +676,21 @@ __device__ __noinline__ void finish_walker_group(const LaunchParams &P, int seg,
     } else {
         if (owner) P.out[(size_t)seg * P.n_walkers + w] = total;
     }
+#ifdef MCD_KERNEL_PROFILE
+    if (tid == 0 && stamps && group == P.n_groups - 1) {
+        const unsigned long long end = global_ns();
+        const unsigned int launch = g_kernel_launch;
+        const unsigned long long t0 = g_kernel_start[launch & 1u];
+        printf("launch %u (grid %u x %u, chunks %d, super %d): finishing CTA %u entered +%llu ns | barriers ready +%llu | "
+               "walker loaded +%llu | first tile +%llu | star loop done +%llu | slices summed +%llu | partial stored +%llu | "
+               "ticket 1 +%llu | level 1 summed +%llu | ticket 2 +%llu | end +%llu\n",
+               launch, gridDim.x, gridDim.y, n_chunks, n_super, blockIdx.x, stamps[0] - t0, stamps[1] - t0, stamps[2] - t0,
+               stamps[3] - t0, stamps[4] - t0, stamps[5] - t0, stamps[6] - t0, stamps[7] - t0, stamps[8] - t0,
+               n_super > 1 ? stamps[9] - t0 : 0ull, end - t0);
+        g_kernel_start[launch & 1u] = ~0ull;
+        g_kernel_launch = launch + 1u;
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -653,6 +713,15 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     __shared__ double s_exp2[EXP_TABLE ? 64 : 1];
     if (EXP_TABLE && threadIdx.x < 64) s_exp2[threadIdx.x] = kExp2Table[threadIdx.x];
 
+#ifdef MCD_KERNEL_PROFILE
+    __shared__ unsigned long long s_stamp[12];
+    if (threadIdx.x == 0) {
+        s_stamp[0] = global_ns();
+        atomicMin(&g_kernel_start[g_kernel_launch & 1u], s_stamp[0]);
+    }
+#else
+    unsigned long long *s_stamp = nullptr;
+#endif
     const int tile = P.tile;                     // stars per stage actually copied (<= kMaxTile)
     constexpr int TS = kMaxTile;                 // column stride in shared memory: compile-time, so
                                                  // that the LDS offsets of the star loop are immediates
@@ -691,6 +760,7 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     }
     __syncthreads();
 
+    MCD_KSTAMP(s_stamp, 1);
     const uint32_t stage_bytes = (uint32_t)tile * (NC * 8u + (ICOL ? 4u : 0u));
     auto issue = [&](int k) {   // tid 0 only
         const int stage = k % kStages;
@@ -719,6 +789,7 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     }
     // a walker outside its box prior is never evaluated by the reference (runner.py:303-306)
     const bool active = valid && (W.prior_ok || !P.apply_prior);
+    MCD_KSTAMP(s_stamp, 2);
 
     Accum<BG, MATH> A;
     A.reset();
@@ -727,6 +798,9 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
         const int stage = k % kStages;
         if (tid == 0 && k + 1 < n_my_tiles) issue(k + 1);
         mbar_wait(&bars[stage], (uint32_t)(k / kStages) & 1u);
+#ifdef MCD_KERNEL_PROFILE
+        if (k == 0) MCD_KSTAMP(s_stamp, 3);
+#endif
         const long long first = (long long)(t_begin + k) * tile;
         const int n = (int)min((long long)tile, seg_stars - first);
         if (active) {
@@ -767,17 +841,20 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     }
 
     // ---- slices -> one value per walker of this CTA ----------------------------------------
+    MCD_KSTAMP(s_stamp, 4);
     red[tid] = active ? A.value() : 0.0;
     __syncthreads();
+    MCD_KSTAMP(s_stamp, 5);
     if (valid && slice == 0) {
         double s = red[lane];
         for (int j = 1; j < P.slices; ++j) s += red[j * P.wl + lane];
         P.partials[((size_t)seg * P.n_chunks + chunk) * P.n_walkers + w] = s;
     }
+    MCD_KSTAMP(s_stamp, 6);
 
     // ---- chunks -> result (and shards -> catalogue, proposal acceptance): cold path, out of line ----
     finish_walker_group<MATH, FUSE>(P, seg, chunk, group, w, n_chunks, seg_stars, valid && slice == 0, W.prior_ok,
-                                    &s_last);
+                                    &s_last, red, s_stamp);
 }
 
 // ------------------------------------------------------------------------------------------
