@@ -588,6 +588,20 @@ __device__ __forceinline__ unsigned long long global_ns() {
 #define MCD_KSTAMP(arr, i) do { } while (0)
 #endif
 
+// sum over the star slices of one walker held in red[slice * wl + lane]; fixed order, four chains
+__device__ __forceinline__ double sum_slices(const double *red, int lane, int wl, int slices) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int j = 0;
+    for (; j + 4 <= slices; j += 4) {
+        a0 += red[j * wl + lane];
+        a1 += red[(j + 1) * wl + lane];
+        a2 += red[(j + 2) * wl + lane];
+        a3 += red[(j + 3) * wl + lane];
+    }
+    for (; j < slices; ++j) a0 += red[j * wl + lane];
+    return (a0 + a1) + (a2 + a3);
+}
+
 // Sum rows [first, last) of a [rows][n_walkers] array of per-CTA sums for walker w, with every thread
 // of the CTA loading (thread (lane, slice) takes rows first + slice, first + slice + slices, ...:
 // kGatherDepth independent loads in flight per thread, one L2 round trip for up to kGatherDepth * slices rows).  The order
@@ -616,10 +630,7 @@ __device__ __forceinline__ double gather_rows(const double *rows, int first, int
     __syncthreads();                       // red[] may still be read by the caller's slice sum
     red[tid] = acc;
     __syncthreads();
-    double total = 0.0;
-    if (valid && slice == 0)
-        for (int j = 0; j < P.slices; ++j) total += red[j * P.wl + lane];
-    return total;
+    return (valid && slice == 0) ? sum_slices(red, lane, P.wl, P.slices) : 0.0;
 }
 
 template <int MATH, bool FUSE>
@@ -845,11 +856,8 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     red[tid] = active ? A.value() : 0.0;
     __syncthreads();
     MCD_KSTAMP(s_stamp, 5);
-    if (valid && slice == 0) {
-        double s = red[lane];
-        for (int j = 1; j < P.slices; ++j) s += red[j * P.wl + lane];
-        P.partials[((size_t)seg * P.n_chunks + chunk) * P.n_walkers + w] = s;
-    }
+    if (valid && slice == 0)
+        P.partials[((size_t)seg * P.n_chunks + chunk) * P.n_walkers + w] = sum_slices(red, lane, P.wl, P.slices);
     MCD_KSTAMP(s_stamp, 6);
 
     // ---- chunks -> result (and shards -> catalogue, proposal acceptance): cold path, out of line ----
@@ -920,19 +928,6 @@ __device__ __forceinline__ bool group_wait_failed(long long t0, unsigned int &po
     if ((++polls & 1023u) != 0u) return false;
     if (clock64() - t0 > kGroupWaitCycles) atomicExch(status, 1);
     return *reinterpret_cast<volatile int *>(status) != 0;
-}
-// sum over the star slices of one walker held in red[slice * wl + lane]; fixed order, four chains
-__device__ __forceinline__ double sum_slices(const double *red, int lane, int wl, int slices) {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int j = 0;
-    for (; j + 4 <= slices; j += 4) {
-        a0 += red[j * wl + lane];
-        a1 += red[(j + 1) * wl + lane];
-        a2 += red[(j + 2) * wl + lane];
-        a3 += red[(j + 3) * wl + lane];
-    }
-    for (; j < slices; ++j) a0 += red[j * wl + lane];
-    return (a0 + a1) + (a2 + a3);
 }
 
 // The counter-based random numbers of one half-step for active walker k = threadIdx.x: stretch factor
