@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 2
+#define MCD_ABI_VERSION 3
 
 /* Rotation / dispersion model.
  *   CONSTANT: analysis/constant.py:52-111  (ConstantFit.rotation_model / dispersion_model)
@@ -158,6 +158,15 @@ int mcd_lnprob_partial_device(mcd_handle *h, const double *theta_dev, int32_t n_
 int mcd_exchange_bytes(int32_t world, int32_t max_walkers, int64_t *bytes_out);
 int mcd_exchange_attach(mcd_handle *h, int32_t rank, int32_t world, const uint64_t *peer_buffers, int32_t max_walkers);
 int mcd_lnprob_allreduce_device(mcd_handle *h, const double *theta_dev, int32_t n_walkers, double *out_dev, void *stream);
+/* The same with HOST buffers -- what a host sampler calls per half-ensemble on every rank (the
+ * vectorised log_prob_fn of analysis/runner.py:403 on a star-sharded catalogue): pinned copy-in, shard
+ * kernel with the exchange in its tail, copy-out, replayed as ONE CUDA graph from the third call of a
+ * shape on (the call's exchange tag travels to the device inside the theta copy).  Returns -5 if a peer
+ * never published its sums (the values are NaN then). */
+int mcd_lnprob_allreduce(mcd_handle *h, const double *theta_host, int32_t n_walkers, double *out_host);
+/* After the caller synchronised its stream: 0, or -5 (and a message) if a kernel launched through one of
+ * the *_device collective entry points gave up waiting for a peer since the last check. */
+int mcd_exchange_status(mcd_handle *h);
 
 /* Per-star log-likelihood of ONE parameter vector (`no_sum=True`, model.py:565,620-621). */
 int mcd_lnlike_per_star(mcd_handle *h, const double *theta_host, double *out_host /* [N] */);
@@ -173,6 +182,11 @@ int mcd_membership_per_star_device(mcd_handle *h, const double *theta_dev, doubl
  * M x N intermediate.  v_bg[M], v[N], verr[N] are HOST arrays; out[N]. */
 int mcd_single_stars_lnlike(int32_t device, const double *v_bg, int64_t m, const double *v, const double *verr,
                             int64_t n, double sigma_int, double *out_host);
+/* The same on DEVICE arrays, asynchronous on `stream`; v_bg_sorted_dev[M] must be in ascending order
+ * (the kernel finds each star's nearest background velocity -- the exponent shift of
+ * single_stars.py:74 -- by binary search). */
+int mcd_single_stars_lnlike_device(int32_t device, const double *v_bg_sorted_dev, int64_t m, const double *v_dev,
+                                   const double *verr_dev, int64_t n, double sigma_int, double *out_dev, void *stream);
 
 /* Gaussian.__call__ (background/gaussian.py:23-28); v[N], verr[N] HOST arrays, out[N]. */
 int mcd_gaussian_lnlike(int32_t device, const double *v, const double *verr, int64_t n, double mean, double sigma,

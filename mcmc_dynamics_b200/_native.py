@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('MCD_B200_LIB') or os.path.join(_HERE, '_lib', 'libmcd_b200.so')
 TORCH_LIB_PATH = os.path.join(_HERE, '_lib', 'libmcd_torch.so')
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 NPARAM = 11
 MAX_THETA = 16
 
@@ -75,12 +75,16 @@ SYMBOLS = {
     'mcd_exchange_attach': (ctypes.c_int, [_vp, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint64),
                                            ctypes.c_int32]),
     'mcd_lnprob_allreduce_device': (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, _vp]),
+    'mcd_lnprob_allreduce': (ctypes.c_int, [_vp, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
+    'mcd_exchange_status': (ctypes.c_int, [_vp]),
     'mcd_lnlike_per_star': (ctypes.c_int, [_vp, _c_double_p, _c_double_p]),
     'mcd_lnlike_per_star_device': (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     'mcd_membership_per_star': (ctypes.c_int, [_vp, _c_double_p, _c_double_p]),
     'mcd_membership_per_star_device': (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     'mcd_single_stars_lnlike': (ctypes.c_int, [ctypes.c_int32, _c_double_p, ctypes.c_int64, _c_double_p, _c_double_p,
                                                ctypes.c_int64, ctypes.c_double, _c_double_p]),
+    'mcd_single_stars_lnlike_device': (ctypes.c_int, [ctypes.c_int32, _vp, ctypes.c_int64, _vp, _vp, ctypes.c_int64,
+                                                      ctypes.c_double, _vp, _vp]),
     'mcd_gaussian_lnlike': (ctypes.c_int, [ctypes.c_int32, _c_double_p, _c_double_p, ctypes.c_int64, ctypes.c_double,
                                            ctypes.c_double, _c_double_p]),
     'mcd_ensemble_create': (ctypes.c_int, [_vp, ctypes.c_int32, ctypes.c_uint64, ctypes.c_double,

@@ -74,7 +74,13 @@ class RadialBinsFit(object):
         signature = (pack.routing_signature(t.parameters, t.MODEL_PARAMETERS), t.math_mode)
         if self._packed is not None and signature == self._signature:
             return self._packed
-        t._check_expressions()
+        derived = pack.derived_parameters(t.parameters)
+        if derived:
+            # the batched bins run on the device sampler, which cannot evaluate host-side expressions
+            raise pack.PackError(
+                "Parameter(s) {0} are constrained by expressions that depend on sampled parameters; per-walker "
+                "constraint expressions are not supported by the batched radial-bin fit (fit the bins with "
+                "individual models and sampler='host' instead).".format(derived))
         desc, keep = pack.build_descriptor(
             t.parameters, t.MODEL_PARAMETERS, rotation=t.ROTATION, background=t._background_mode(),
             columns=t._star_columns() if self._packed is None else {},

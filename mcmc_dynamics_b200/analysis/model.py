@@ -134,4 +134,5 @@ class ModelFitConstantBackground(ModelFit):
             return super(ModelFitConstantBackground, self).lnlike(values)
         values = np.asarray(values, dtype=np.float64)
         assert values.ndim == 1 and values.size == self.n_fitted_parameters, 'Not all parameters used.'
-        return self.pack().lnlike_per_star(values)
+        packed = self.pack()
+        return packed.lnlike_per_star(self._device_theta(values[None, :])[0])

@@ -15,6 +15,7 @@ import pickle
 import numpy as np
 
 from .. import _native
+from .. import expressions
 from .. import pack
 from .. import sampler as _sampler
 from .. import units as u
@@ -93,6 +94,7 @@ class Runner(object):
         self._packed_signature = None
         self._packed_stamps = None
         self._expression_priors_present = False
+        self._derived = []
 
     # ------------------------------------------------------------------------------------------
     # introspection (analysis/runner.py:108-141, 662-673)
@@ -150,21 +152,13 @@ class Runner(object):
             columns['lnlike_background'] = u.strip(self.lnlike_background, None)
         return columns
 
-    def _check_expressions(self):
-        free = set(self.fitted_parameters)
-        for name, par in self.parameters.items():
-            if par.expr is not None and free.intersection(getattr(par, '_expr_deps', [])):
-                raise pack.PackError(
-                    "Parameter '{0}' is constrained by the expression '{1}', which depends on sampled parameters; "
-                    "per-walker constraint expressions are not supported by the device likelihood.".format(
-                        name, par.expr))
-
     def _descriptor(self):
-        self._check_expressions()
+        self._derived = pack.derived_parameters(self.parameters)
         return pack.build_descriptor(
             self.parameters, self.MODEL_PARAMETERS, rotation=self.ROTATION, background=self._background_mode(),
             columns=self._star_columns() if self._packed is None else {},
-            math_mode=_native.MATH_FAST if self.math_mode == 'fast' else _native.MATH_PLAIN, device=self.device)
+            math_mode=_native.MATH_FAST if self.math_mode == 'fast' else _native.MATH_PLAIN, device=self.device,
+            derived=self._derived)
 
     def pack(self):
         """Upload the star columns (first call) and compile the current parameter routing.  Called
@@ -174,6 +168,7 @@ class Runner(object):
             return self._packed                       # nothing was assigned to any parameter since the last call
         signature = (pack.routing_signature(self.parameters, self.MODEL_PARAMETERS), self.math_mode)
         self._expression_priors_present = any(par.lnprior is not None for par in self.parameters.values())
+        self._derived = pack.derived_parameters(self.parameters)
         if self._packed is not None and signature == self._packed_signature:
             self._packed_stamps = stamps
             return self._packed
@@ -220,30 +215,85 @@ class Runner(object):
         assert theta.shape[1] == self.n_fitted_parameters, 'Not all parameters used.'
         return theta, scalar
 
-    def _expression_priors(self):
-        return [(i, self.parameters[name]) for i, name in enumerate(self.fitted_parameters)
-                if self.parameters[name].lnprior is not None]
+    def _derived_columns(self, theta):
+        """Per-walker values of the ``expr``-constrained parameters that depend on sampled ones
+        (``analysis/runner.py:163-176`` evaluates them through the shared asteval table on every call,
+        ``parameter.py:865-874``), shape ``[n_walkers, n_derived]`` in ``self._derived`` order.  Every
+        sampled parameter carries the walker's value when an expression is evaluated; the reference's
+        iteration-order staleness (a parameter later in the table still holds the previous call's value
+        during ``lnprior``) is not reproduced.  Nothing is written back into ``self.parameters``."""
+        names = self._derived
+        n = theta.shape[0]
+        out = np.empty((n, len(names)), dtype=np.float64)
+        if not names or n == 0:
+            return out
+        self.parameters._sync_symbols()
+        base = dict(self.parameters.symtable)
+        free = self.fitted_parameters
+        trees = [self.parameters[name]._expr_ast for name in names]
+
+        def one_row(w):
+            sym = dict(base)
+            for j, name in enumerate(free):
+                sym[name] = float(theta[w, j])
+            row = np.empty(len(names))
+            for k, name in enumerate(names):
+                row[k] = float(expressions.evaluate(trees[k], sym))
+                sym[name] = row[k]
+            return row
+
+        first = one_row(0)
+        try:                                   # all rows at once where the expressions are plain arithmetic
+            sym = dict(base)
+            for j, name in enumerate(free):
+                sym[name] = theta[:, j]
+            for k, name in enumerate(names):
+                column = np.asarray(expressions.evaluate(trees[k], sym), dtype=np.float64)
+                out[:, k] = np.broadcast_to(column, (n,))
+                sym[name] = out[:, k]
+            if np.array_equal(out[0], first, equal_nan=True):
+                return out
+        except Exception:                      # noqa: BLE001 -- e.g. builtin min/max or a conditional on arrays
+            pass
+        out[0] = first
+        for w in range(1, n):
+            out[w] = one_row(w)
+        return out
+
+    def _device_theta(self, theta):
+        """theta as the kernel wants it: the free parameters followed by the per-walker constrained ones."""
+        if not self._derived:
+            return theta
+        return np.ascontiguousarray(np.hstack([theta, self._derived_columns(theta)]))
 
     def _lnprior_batch(self, theta, parameters_to_ignore=None):
         """Box prior over every parameter plus optional expression priors (runner.py:206-217,
         parameter.py:684-705), for all rows of theta at once."""
         lnp = np.zeros(theta.shape[0], dtype=np.float64)
+        derived = pack.derived_parameters(self.parameters)
+        derived_values = None
+        if derived:
+            self._derived = derived
+            derived_values = self._derived_columns(theta)
         j = 0
         for name, par in self.parameters.items():
-            if par.fixed:
+            if par.fixed and name not in derived:
                 value = par.value
                 if value < par.min or value > par.max:
                     lnp[:] = -np.inf
                 elif par.lnprior is not None:
                     lnp += par.evaluate_lnprior(value)
             else:
-                column = theta[:, j]
+                if par.fixed:
+                    column = derived_values[:, derived.index(name)]
+                else:
+                    column = theta[:, j]
+                    j += 1
                 outside = (column < par.min) | (column > par.max)
                 lnp[outside] = -np.inf
                 if par.lnprior is not None:
                     for w in np.flatnonzero(~outside & np.isfinite(lnp)):
                         lnp[w] += par.evaluate_lnprior(column[w])
-                j += 1
         lnp[~np.isfinite(lnp)] = -np.inf
         return lnp
 
@@ -262,14 +312,16 @@ class Runner(object):
         """Log-likelihood without priors (``constant.py:113-154``, ``model.py:182-223`` and the
         background variants), for one parameter vector or a batch."""
         theta, scalar = self._as_batch(values)
-        out = self.pack().lnlike(theta)
+        packed = self.pack()
+        out = packed.lnlike(self._device_theta(theta))
         return float(out[0]) if scalar else out
 
     def lnprob(self, values):
         """``analysis/runner.py:288-306``: box prior fused into the kernel; walkers outside the prior
         come back as exactly ``-inf`` without being evaluated."""
         theta, scalar = self._as_batch(values)
-        out = self.pack().lnprob(theta)
+        packed = self.pack()
+        out = packed.lnprob(self._device_theta(theta))
         if self._expression_priors_present:           # refreshed by pack() whenever a parameter was edited
             extra = self._lnprior_batch(theta)
             with np.errstate(invalid='ignore'):
@@ -281,8 +333,20 @@ class Runner(object):
 
     def lnprob_tensor(self, theta):
         """``lnprob`` for an ``[n_walkers, n_free]`` float64 CUDA tensor, asynchronous on the current
-        stream, result stays on the device.  Expression priors are not applied here."""
-        return self.pack().lnprob_tensor(theta)
+        stream, result stays on the device.  Box priors only: expression priors (``lnprior`` strings) and
+        per-walker ``expr`` constraints are evaluated on the host, so a model that has either raises
+        here instead of silently returning a different posterior -- use :meth:`lnprob`."""
+        packed = self.pack()
+        self._require_box_priors('lnprob_tensor')
+        return packed.lnprob_tensor(theta)
+
+    def _require_box_priors(self, what):
+        if self._expression_priors_present or self._derived:
+            raise ValueError(
+                "{0} supports box priors only: this model has {1}, which are evaluated on the host "
+                "(use lnprob / sampler='host')".format(
+                    what, 'expression priors' if self._expression_priors_present
+                    else "per-walker 'expr' constraints ({0})".format(', '.join(self._derived))))
 
     # ------------------------------------------------------------------------------------------
     # sampling
@@ -327,9 +391,9 @@ class Runner(object):
                     "Invalid initial guesses for walker {0}: {1}={2}".format(i, self.fitted_parameters, pos[i]))
 
         if sampler == 'device':
-            if self._has_expression_priors():
-                raise ValueError("sampler='device' supports box priors only")
-            engine = _sampler.DeviceEnsembleSampler(n_walkers, self.n_fitted_parameters, self.pack(), seed=seed)
+            packed = self.pack()
+            self._require_box_priors("sampler='device'")
+            engine = _sampler.DeviceEnsembleSampler(n_walkers, self.n_fitted_parameters, packed, seed=seed)
         else:
             engine = _sampler.make_host_sampler(n_walkers, self.n_fitted_parameters, self.lnprob, seed=seed)
         logger.info("Running MCMC chain ...")
@@ -449,7 +513,8 @@ class Runner(object):
             raise NotImplementedError('membership probabilities need a background component')
         median = self.compute_percentiles(chain, n_burn=n_burn, pct=[50])[0]
         self.compute_bestfit_values(chain, n_burn)          # the reference updates parameter values here
-        return self.pack().membership_per_star(median)
+        packed = self.pack()
+        return packed.membership_per_star(self._device_theta(np.atleast_2d(median))[0])
 
 
 def get_amplitude_and_angle(pars, return_samples=False):

@@ -33,8 +33,7 @@ class Gaussian(object):
         lib = _native.load_library()
         rc = lib.mcd_gaussian_lnlike(self.device, _native.as_double_ptr(v), _native.as_double_ptr(verr), v.size,
                                      float(self.mean.value), float(self.sigma.value), _native.as_double_ptr(out))
-        if rc != 0:
-            raise _native.NativeError('mcd_gaussian_lnlike failed with code {0}'.format(rc))
+        _native.check(rc)
         return out
 
 
@@ -57,8 +56,7 @@ class SingleStars(object):
         lib = _native.load_library()
         rc = lib.mcd_single_stars_lnlike(self.device, _native.as_double_ptr(v_bg), v_bg.size, _native.as_double_ptr(v),
                                          _native.as_double_ptr(verr), v.size, sigma_int, _native.as_double_ptr(out))
-        if rc != 0:
-            raise _native.NativeError('mcd_single_stars_lnlike failed with code {0}'.format(rc))
+        _native.check(rc)
         return out
 
 

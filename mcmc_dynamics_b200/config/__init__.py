@@ -52,18 +52,36 @@ def build(name):
     return pars
 
 
+def default_text(name):
+    """JSON text of set `name` in the layout of the reference's ``config/*.json``: ``unique_symbols``
+    (``rng_seed: null``) and ``params`` -- and, like those files, NO ``random_state`` entry, so that a
+    ``Parameters`` object loaded from it keeps the unseeded generator it was constructed with
+    (``mcmc_dynamics/parameter.py:73-74,207-209``; ``config/model.json:1-5``).  ``Parameters.dumps`` itself
+    stores the generator state (``parameter.py:458-466``), which is right for a user's snapshot but would
+    freeze the start positions drawn from the defaults in every process."""
+    import json
+    state = json.loads(build(name).dumps())
+    state.pop('random_state', None)
+    return json.dumps(state)
+
+
 def default_file(name):
-    """Path of the JSON serialisation of set `name` (written on first use)."""
+    """Path of the JSON serialisation of set `name` (written on first use, rewritten if stale)."""
+    text = default_text(name)
     for out_dir in (os.path.join(_HERE, '_generated'),
                     os.path.join(tempfile.gettempdir(), 'mcmc_dynamics_b200_config_%d' % os.getuid())):
         path = os.path.join(out_dir, name + '.json')
-        if os.path.exists(path):
-            return path
+        try:
+            with open(path) as f:
+                if f.read() == text:
+                    return path
+        except OSError:
+            pass
         try:
             os.makedirs(out_dir, exist_ok=True)
             tmp = path + '.%d.tmp' % os.getpid()
             with open(tmp, 'w') as f:
-                build(name).dump(f)
+                f.write(text)
             os.replace(tmp, path)
             return path
         except OSError:            # read-only installation: fall back to the temporary directory

@@ -73,15 +73,25 @@ struct mcd_handle {
     // host-buffer calls replayed as CUDA graphs (H2D theta -> kernel -> D2H result), one per
     // (walkers per call, prior on/off); dropped whenever a pointer or the routing baked into them changes
     struct HostGraph {
-        int n_walkers = 0, apply_prior = 0, seen = 0;
+        int n_walkers = 0, apply_prior = 0, exchange = 0, seen = 0;
         cudaGraphExec_t exec = nullptr;
     };
     HostGraph host_graphs[8];
     // fused cross-GPU reduction (mcd_exchange_attach)
     int xchg_world = 0, xchg_rank = 0, xchg_capacity = 0;
     unsigned long long xchg_epoch = 0;
+    unsigned long long fuse_nonce = 0;          // ensembles created on this handle so far (exchange tag of their half-steps)
     double *xchg_data[kMaxRanks] = {};
     unsigned long long *xchg_flags[kMaxRanks] = {};
+    int *xchg_status = nullptr;                 // device word: set to 1 by a kernel whose wait for a peer timed out
+    // Everything a captured graph bakes in (scratch pointers, packed columns, routing, exchange buffers)
+    // belongs to one generation; whoever replays a graph compares the generation it captured at.
+    unsigned long long generation = 1;
+    // launches through one handle share its reduction scratch: they are ordered across streams by making
+    // a launch on a new stream wait for everything issued so far on the previous one
+    cudaStream_t last_stream = nullptr;
+    bool last_stream_valid = false;
+    cudaEvent_t order_event = nullptr;
     mcd_info info{};
 };
 
@@ -107,6 +117,7 @@ static int validate_routing(const mcd_pack_desc *d) {
 static int repack(mcd_handle *h) {
     const mcd_pack_desc &d = h->desc;
     drop_host_graphs(h);
+    h->generation += 1;
     h->var.rotation = d.rotation;
     h->var.background = d.background;
     h->var.math_mode = d.math_mode;
@@ -168,6 +179,7 @@ static int repack(mcd_handle *h) {
 }
 
 static void drop_host_graphs(mcd_handle *h) {
+    h->generation += 1;      // whatever invalidates the host-call graphs invalidates every other captured graph too
     for (auto &g : h->host_graphs) {
         if (g.exec) cudaGraphExecDestroy(g.exec);
         g = mcd_handle::HostGraph();
@@ -190,6 +202,8 @@ extern "C" void mcd_destroy(mcd_handle *h) {
     cudaFree(h->theta_dev);
     cudaFree(h->out_dev);
     cudaFree(h->star_dev);
+    cudaFree(h->xchg_status);
+    if (h->order_event) cudaEventDestroy(h->order_event);
     cudaFreeHost(h->theta_pin);
     cudaFreeHost(h->out_pin);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -256,6 +270,7 @@ extern "C" int mcd_pack_create(const mcd_pack_desc *desc, mcd_handle **out) {
         if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) { rc = fail(-2, "cudaGetDeviceProperties failed"); break; }
         h->sm_count = prop.multiProcessorCount;
         if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(-2, "cudaStreamCreate failed"); break; }
+        if (cudaEventCreateWithFlags(&h->order_event, cudaEventDisableTiming) != cudaSuccess) { rc = fail(-2, "cudaEventCreate failed"); break; }
         h->n = desc->n_stars;
         h->n_alloc = ((h->n + kMaxTile - 1) / kMaxTile + 1) * kMaxTile;   // full bulk copies at the tail
         h->max_segment = h->n;
@@ -429,8 +444,37 @@ static void fill_params(const mcd_handle *h, LaunchParams &p) {
     p.ra0_deg = h->ra0_deg;
 }
 
+// Launches through one handle share its reduction scratch, counters and exchange slots (mcd_b200.h:
+// "they must be ordered").  Callers use several streams -- the handle's own for the host-buffer entry
+// points, torch's current stream for the tensor ops, an ensemble's stream for the sampler -- so the
+// first launch on a different stream than the previous one waits for everything issued there so far.
+// Free in the common case (same stream as before).  Inside a stream capture nothing is added: a
+// capture follows un-captured launches on the same stream, and a cross-stream edge out of a capture
+// is an error (cudaErrorStreamCaptureIsolation).
+int mcd::order_on_stream(mcd_handle *h, cudaStream_t stream) {
+    if (h->last_stream_valid && h->last_stream != stream) {
+        cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &capturing) != cudaSuccess) (void)cudaGetLastError();
+        if (capturing != cudaStreamCaptureStatusNone) return 0;
+        if (cudaEventRecord(h->order_event, h->last_stream) == cudaSuccess) {
+            MCD_CUDA(cudaStreamWaitEvent(stream, h->order_event, 0));
+        } else {
+            (void)cudaGetLastError();      // the previous stream no longer exists: its owner synchronised it
+        }
+    }
+    h->last_stream = stream;
+    h->last_stream_valid = true;
+    return 0;
+}
+void mcd::forget_stream(mcd_handle *h, cudaStream_t stream) {
+    if (h && h->last_stream_valid && h->last_stream == stream) h->last_stream_valid = false;
+}
+unsigned long long mcd::handle_generation(const mcd_handle *h) { return h ? h->generation : 0ull; }
+unsigned long long mcd::next_fuse_nonce(mcd_handle *h) { return ++h->fuse_nonce; }
+
 static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double *out_dev, int apply_prior,
-                  cudaStream_t stream, bool exchange = false, const FuseParams *fuse = nullptr) {
+                  cudaStream_t stream, bool exchange = false, const FuseParams *fuse = nullptr,
+                  const unsigned long long *epoch_dev = nullptr) {
     if (!h) return fail(-1, "null handle");
     if (n_walkers < 0) return fail(-1, "n_walkers < 0");
     if (n_walkers == 0) return 0;
@@ -439,6 +483,7 @@ static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double 
         if (!out_dev) return fail(-1, "null out");
     }
     MCD_CUDA(cudaSetDevice(h->device));
+    if (int rc = order_on_stream(h, stream)) return rc;
     LaunchParams p{};
     fill_params(h, p);
     p.n_walkers = n_walkers;
@@ -465,7 +510,11 @@ static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double 
         p.xchg_world = h->xchg_world;
         p.xchg_rank = h->xchg_rank;
         p.xchg_capacity = h->xchg_capacity;
-        p.xchg_epoch = fuse ? 0 : ++h->xchg_epoch;      // fused half-steps take their tag from the step counter
+        // fused half-steps take their tag from the device-side step counter; host-buffer calls replayed as
+        // a graph read it from device memory (epoch_dev, refreshed by the same copy that brings theta)
+        p.xchg_epoch = (fuse || epoch_dev) ? 0 : ++h->xchg_epoch;
+        p.xchg_epoch_ptr = epoch_dev;
+        p.xchg_status = h->xchg_status;
         for (int r = 0; r < h->xchg_world; ++r) {
             p.xchg_data[r] = h->xchg_data[r];
             p.xchg_flags[r] = h->xchg_flags[r];
@@ -506,34 +555,48 @@ static int ensure_staging(mcd_handle *h, size_t theta_doubles, size_t out_double
     return 0;
 }
 
-static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, double *out_host, int apply_prior) {
+static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, double *out_host, int apply_prior,
+                     int exchange = 0) {
     if (!h) return fail(-1, "null handle");
     if (n_walkers < 0) return fail(-1, "n_walkers < 0");
     if (n_walkers == 0) return 0;
     if (!out_host || (!theta_host && h->desc.n_theta > 0)) return fail(-1, "null buffer");
+    if (exchange && h->xchg_world < 2) return fail(-1, "mcd_exchange_attach has not been called on this handle");
     MCD_CUDA(cudaSetDevice(h->device));
     const size_t rows = (size_t)n_walkers * h->n_segments;        // theta is [segments][walkers][theta]
     const size_t nt = rows * h->desc.n_theta;
-    if (int rc = ensure_staging(h, nt, rows)) return rc;
+    // one word after theta carries the call's exchange epoch to the device inside the same copy, so that
+    // the replayed graph (whose kernel arguments are frozen) sees a fresh tag on every call
+    if (int rc = ensure_staging(h, nt + 1, rows)) return rc;
     if (nt) memcpy(h->theta_pin, theta_host, sizeof(double) * nt);
+    const unsigned long long *epoch_dev = nullptr;
+    if (exchange) {
+        const unsigned long long epoch = ++h->xchg_epoch;
+        memcpy(h->theta_pin + nt, &epoch, sizeof(epoch));
+        epoch_dev = reinterpret_cast<const unsigned long long *>(h->theta_dev + nt);
+    }
+    const size_t n_copy = nt + (exchange ? 1 : 0);
 
     // A sampler calls with the same shape thousands of times: from the third call of a shape on, the
     // copy-in / kernel / copy-out sequence is one graph launch (the first call sizes the scratch
     // buffers, the second captures).
     mcd_handle::HostGraph *slot = nullptr;
     for (auto &g : h->host_graphs)
-        if (g.seen && g.n_walkers == n_walkers && g.apply_prior == apply_prior) slot = &g;
+        if (g.seen && g.n_walkers == n_walkers && g.apply_prior == apply_prior && g.exchange == exchange) slot = &g;
     if (!slot) {
         for (auto &g : h->host_graphs)
             if (!g.seen && !slot) slot = &g;
         if (slot) {
             slot->n_walkers = n_walkers;
             slot->apply_prior = apply_prior;
+            slot->exchange = exchange;
         }
     }
+    if (int rc = order_on_stream(h, h->stream)) return rc;
     auto enqueue = [&]() -> int {
-        if (nt) MCD_CUDA(cudaMemcpyAsync(h->theta_dev, h->theta_pin, sizeof(double) * nt, cudaMemcpyHostToDevice, h->stream));
-        if (int rc = launch(h, h->theta_dev, n_walkers, h->out_dev, apply_prior, h->stream)) return rc;
+        if (n_copy) MCD_CUDA(cudaMemcpyAsync(h->theta_dev, h->theta_pin, sizeof(double) * n_copy, cudaMemcpyHostToDevice, h->stream));
+        if (int rc = launch(h, h->theta_dev, n_walkers, h->out_dev, apply_prior, h->stream, exchange != 0, nullptr, epoch_dev))
+            return rc;
         MCD_CUDA(cudaMemcpyAsync(h->out_pin, h->out_dev, sizeof(double) * rows, cudaMemcpyDeviceToHost, h->stream));
         return 0;
     };
@@ -562,6 +625,26 @@ static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, dou
     if (slot) slot->seen += slot->seen < 2 ? 1 : 0;
     MCD_CUDA(cudaStreamSynchronize(h->stream));
     memcpy(out_host, h->out_pin, sizeof(double) * rows);
+    if (exchange) {
+        // a peer that never published turns the sums into NaN after the kernel's time limit: say so
+        for (size_t i = 0; i < rows; ++i)
+            if (out_host[i] != out_host[i]) return exchange_status(h, h->stream);
+    }
+    return 0;
+}
+
+// After the stream is synchronised: < 0 (with a message) if a kernel of this handle gave up waiting for a
+// peer rank's shard sums since the last check.
+int mcd::exchange_status(mcd_handle *h, cudaStream_t stream) {
+    if (!h || !h->xchg_status) return 0;
+    int status = 0;
+    MCD_CUDA(cudaMemcpyAsync(&status, h->xchg_status, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    MCD_CUDA(cudaStreamSynchronize(stream));
+    if (status) {
+        MCD_CUDA(cudaMemsetAsync(h->xchg_status, 0, sizeof(int), stream));
+        return fail(-5, "fused cross-GPU reduction: a peer rank never published its shard sums (timed out); "
+                        "the values of that call are NaN");
+    }
     return 0;
 }
 
@@ -622,6 +705,7 @@ int mcd::launch_resident_chain(mcd_handle *h, const ChainParams &chain, cudaStre
     if (!(force && force[0] == '1') && resident > launched) return 1;
 
     MCD_CUDA(cudaSetDevice(h->device));
+    if (int rc = order_on_stream(h, stream)) return rc;
     LaunchParams p{};
     fill_params(h, p);
     p.apply_prior = 1;
@@ -705,6 +789,12 @@ extern "C" int mcd_exchange_attach(mcd_handle *h, int32_t rank, int32_t world, c
     if (!h || !peer_buffers) return fail(-1, "null argument");
     if (world < 2 || world > kMaxRanks || rank < 0 || rank >= world || max_walkers < 1)
         return fail(-1, "bad exchange geometry (world %d, rank %d)", world, rank);
+    MCD_CUDA(cudaSetDevice(h->device));
+    drop_host_graphs(h);                 // bumps the generation: exchange pointers are baked into captured graphs
+    if (!h->xchg_status) {
+        MCD_CUDA(cudaMalloc(&h->xchg_status, sizeof(int)));
+        MCD_CUDA(cudaMemset(h->xchg_status, 0, sizeof(int)));
+    }
     h->xchg_world = world;
     h->xchg_rank = rank;
     h->xchg_capacity = max_walkers;
@@ -721,6 +811,16 @@ extern "C" int mcd_exchange_attach(mcd_handle *h, int32_t rank, int32_t world, c
 extern "C" int mcd_lnprob_allreduce_device(mcd_handle *h, const double *theta_dev, int32_t n_walkers, double *out_dev,
                                            void *stream) {
     return launch(h, theta_dev, n_walkers, out_dev, 1, static_cast<cudaStream_t>(stream), true);
+}
+
+extern "C" int mcd_lnprob_allreduce(mcd_handle *h, const double *theta_host, int32_t n_walkers, double *out_host) {
+    return host_call(h, theta_host, n_walkers, out_host, 1, 1);
+}
+
+extern "C" int mcd_exchange_status(mcd_handle *h) {
+    if (!h) return fail(-1, "null handle");
+    MCD_CUDA(cudaSetDevice(h->device));
+    return exchange_status(h, h->stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -56,6 +56,7 @@ struct FuseParams {
     const int *perm;              // [S][W] red/blue partition of this step
     long long *n_accepted;        // [S][W]
     const unsigned int *step;     // [0]: global step counter (Philox counter word)
+    unsigned long long tag_base;  // exchange tag of this ensemble's half-steps: (1 << 62) | nonce << 36
 };
 
 // Whole chains inside one kernel (small catalogues): one CTA per segment keeps the segment's packed
@@ -122,6 +123,8 @@ struct LaunchParams {
     // for the other shards' sums and adds them in rank order.  xchg_world <= 1: disabled.
     int xchg_world, xchg_rank, xchg_capacity;
     unsigned long long xchg_epoch;                 // call counter, identical on all ranks, starts at 1
+    const unsigned long long *xchg_epoch_ptr;      // non-null: the epoch is read from device memory (graph replays)
+    int *xchg_status;                              // set to 1 when the wait for a peer ran into its time limit
     double *xchg_data[kMaxRanks];                  // rank p's data region  [kXchgSlots][world][capacity]
     unsigned long long *xchg_flags[kMaxRanks];     // rank p's flag region  [kXchgSlots][world][kMaxXchgGroups]
     FuseParams fuse;
@@ -144,6 +147,9 @@ cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out
 // resident-chain kernel: shared memory it needs for this problem, or 0 if the problem does not fit
 size_t chain_shared_bytes(const Variant &v, long long stars_per_cta, int n_walkers, int n_theta);
 cudaError_t launch_chain(const Variant &v, const LaunchParams &p, const ChainParams &c, size_t smem, cudaStream_t stream);
+// SingleStars background column (mcd_background.cu): device pointers, v_bg sorted ascending
+cudaError_t launch_single_stars(const double *v_bg_sorted_dev, long long m, const double *v_dev, const double *verr_dev,
+                                long long n, double sigma_int, double *out_dev, int sm_count, cudaStream_t stream);
 // resident CTAs per SM of the lnlike kernel of this variant (occupancy API)
 int lnlike_blocks_per_sm(const Variant &v);
 
@@ -159,6 +165,16 @@ int launch_resident_chain(mcd_handle *h, const ChainParams &chain, cudaStream_t 
 int resident_chain_status(mcd_handle *h, cudaStream_t stream);
 int resident_chain_group(const mcd_handle *h);   // CTAs per segment of the last resident launch
 int handle_device(const mcd_handle *h);
+// make `stream` wait for whatever was last launched through the handle on another stream (mcd_api.cu)
+int order_on_stream(mcd_handle *h, cudaStream_t stream);
+// `stream` is about to be destroyed (and has been synchronised): never record an event on it again
+void forget_stream(mcd_handle *h, cudaStream_t stream);
+// changes whenever something a captured CUDA graph bakes in changes (scratch, columns, routing, exchange)
+unsigned long long handle_generation(const mcd_handle *h);
+// per-ensemble nonce of the fused half-step exchange tags (identical on every rank: same creation order)
+unsigned long long next_fuse_nonce(mcd_handle *h);
+// after `stream` was synchronised: < 0 if a kernel gave up waiting for a peer's shard sums
+int exchange_status(mcd_handle *h, cudaStream_t stream);
 // record the thread-local message returned by mcd_last_error() and hand back `code`
 int set_error(int code, const char *fmt, ...);
 

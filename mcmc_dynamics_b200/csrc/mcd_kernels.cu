@@ -532,6 +532,7 @@ static __device__ __noinline__ double exchange_shard_sums(const LaunchParams &P,
             // a peer that never arrives (crashed rank) must not hang the GPU: give up after ~10 s
             if (clock64() - t0 > 20000000000LL) {
                 *timed_out = 1;
+                if (P.xchg_status) *P.xchg_status = 1;       // read by the host after the run (exchange_status)
                 break;
             }
         } while (seen != epoch);
@@ -670,12 +671,15 @@ __device__ __noinline__ void finish_walker_group(const LaunchParams &P, int seg,
         total = rejected ? __longlong_as_double(0xfff0000000000000LL) : total;
     }
     if (P.xchg_world > 1) {
-        int slot = (int)(P.xchg_epoch & 1ull);
-        unsigned long long epoch = P.xchg_epoch;
+        // host-counted calls: the epoch is a kernel argument, or -- when the launch is replayed from a
+        // CUDA graph -- a word in device memory refreshed by the copy that brought theta
+        unsigned long long epoch = P.xchg_epoch_ptr ? *P.xchg_epoch_ptr : P.xchg_epoch;
+        int slot = (int)(epoch & 1ull);
         if constexpr (FUSE) {
-            // replayed from a CUDA graph: the tag comes from the device-side step counter
+            // sampler half-steps: the tag comes from the device-side step counter plus the ensemble's
+            // nonce (the step counter restarts with every ensemble, the flags persist on the handle)
             slot = 2 + P.fuse.half;
-            epoch = (1ull << 62) | (2ull * P.fuse.step[0] + (unsigned long long)P.fuse.half);
+            epoch = P.fuse.tag_base | (2ull * P.fuse.step[0] + (unsigned long long)P.fuse.half);
         }
         total = exchange_shard_sums(P, total, w, group, owner, s_last, slot, epoch);
     }

@@ -93,6 +93,8 @@ struct mcd_ensemble {
     bool graph_stores = false;
     size_t chain_cap_steps = 0;
     bool have_state = false;
+    unsigned long long graph_generation = 0;   // handle_generation() the graph was captured at
+    unsigned long long tag_base = 0;           // exchange tag of this ensemble's fused half-steps
     unsigned int steps_done = 0;     // host mirror of E.step[0]
     int last_path = 0;               // 1: resident-chain kernel, 2: CUDA graph of launches (diagnostics)
 };
@@ -110,7 +112,11 @@ static void free_ensemble(mcd_ensemble *e) {
     cudaFree(e->E.step);
     cudaFree(e->E.chain);
     cudaFree(e->E.chain_lnp);
-    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream) {
+        cudaStreamSynchronize(e->stream);
+        forget_stream(e->h, e->stream);
+        cudaStreamDestroy(e->stream);
+    }
     delete e;
 }
 
@@ -135,6 +141,9 @@ extern "C" int mcd_ensemble_create(mcd_handle *h, int32_t n_walkers, uint64_t se
     if (!e) return set_error(-4, "out of host memory");
     e->h = h;
     e->device = handle_device(h);
+    // bits 36..61: ensembles created on this handle so far (every rank of a sharded run creates them in the
+    // same order); bits 0..35: 2 * step + half
+    e->tag_base = (1ull << 62) | ((next_fuse_nonce(h) & 0x3ffffffull) << 36);
     Ensemble &E = e->E;
     E.n_segments = std::max(1, (int)info.n_segments);
     E.n_walkers = n_walkers;
@@ -195,6 +204,7 @@ static int enqueue_step(mcd_ensemble *e) {
         f.perm = E.perm;
         f.n_accepted = E.n_accepted;
         f.step = E.step;
+        f.tag_base = e->tag_base;
         if (int rc = launch_ensemble_fused(e->h, ns, f, e->stream)) return rc;
     }
     const int total = E.n_segments * E.n_walkers * std::max(1, E.n_theta);
@@ -228,6 +238,7 @@ static int build_graph(mcd_ensemble *e) {
     }
     e->graph = g;
     ENS_CUDA(cudaGraphInstantiate(&e->exec, e->graph, 0));
+    e->graph_generation = handle_generation(e->h);
     return 0;
 }
 
@@ -303,7 +314,9 @@ extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_
     // the graph bakes in whether the chain is stored (E.chain pointer): rebuild when that changes
     double *saved_chain = E.chain, *saved_lnp = E.chain_lnp;
     if (!store) E.chain = E.chain_lnp = nullptr;
-    if (!e->exec || e->graph_stores != store) {
+    // the graph bakes in the handle's scratch buffers, packed columns, routing and exchange pointers: a
+    // larger lnprob call, a re-pack or an exchange attach since the capture makes it stale
+    if (!e->exec || e->graph_stores != store || e->graph_generation != handle_generation(e->h)) {
         const int rc = build_graph(e);
         if (rc) {
             E.chain = saved_chain;
@@ -312,7 +325,7 @@ extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_
         }
         e->graph_stores = store;
     }
-    int rc = 0;
+    int rc = order_on_stream(e->h, e->stream);
     for (int done = 0; done < n_steps && rc == 0;) {
         const int todo = (int)std::min<size_t>(chunk, (size_t)(n_steps - done));
         if (cudaMemsetAsync(E.step + 1, 0, sizeof(unsigned int), e->stream) != cudaSuccess) { rc = -2; break; }
@@ -333,6 +346,7 @@ extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_
         if (cudaMemcpy(n_accepted_host, E.n_accepted, sizeof(long long) * rows, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -2;
     }
     if (rc == 0 && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = -2;
+    if (rc == 0) rc = exchange_status(e->h, e->stream);
     return rc;
 }
 

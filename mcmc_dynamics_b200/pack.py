@@ -51,14 +51,37 @@ def routing_signature(parameters, model_parameters):
     re-pack before the next likelihood call (parameters are usually edited between construction and
     the run: ``bin/run_tests.py:88-93,137-148``)."""
     sig = []
+    derived = set(derived_parameters(parameters))
     for name, par in parameters.items():
-        sig.append((name, bool(par.fixed), None if not par.fixed else float(par.value), str(par.unit), float(par.min),
-                    float(par.max), par.expr))
+        # the value of a per-walker constrained parameter is not part of the packed state (it travels as
+        # an extra column of theta)
+        value = None if (not par.fixed or name in derived) else float(par.value)
+        sig.append((name, bool(par.fixed), value, str(par.unit), float(par.min), float(par.max), par.expr))
     return tuple(sig), tuple(model_parameters)
 
 
+def derived_parameters(parameters):
+    """Names of the parameters whose ``expr`` constraint depends -- directly or through other constrained
+    parameters -- on a sampled parameter, in insertion order.  The reference re-evaluates them through
+    asteval on every call (``analysis/runner.py:163-176``, ``parameter.py:865-874``); here they are
+    evaluated on the host once per walker and handed to the kernel as extra columns of theta."""
+    free = {name for name, par in parameters.items() if not par.fixed}
+    derived = []
+    changed = True
+    while changed:
+        changed = False
+        for name, par in parameters.items():
+            if name in derived or par.expr is None:
+                continue
+            deps = set(getattr(par, '_expr_deps', []))
+            if deps & free or deps & set(derived):
+                derived.append(name)
+                changed = True
+    return [name for name in parameters if name in derived]
+
+
 def build_descriptor(parameters, model_parameters, rotation, background, columns, math_mode=_native.MATH_FAST,
-                     device=0, n_stars_total=0, segment_offsets=None):
+                     device=0, n_stars_total=0, segment_offsets=None, derived=()):
     """Fill a ``PackDesc`` from a ``Parameters`` object.
 
     Parameters
@@ -69,6 +92,8 @@ def build_descriptor(parameters, model_parameters, rotation, background, columns
         ``MODEL_PARAMETERS`` of the class: which of them actually enter the likelihood.
     columns : dict name -> contiguous float64 array (``ra, dec, v, verr`` and optionally ``pmember``,
         ``density``, ``lnlike_background``)
+    derived : names of per-walker constrained parameters (:func:`derived_parameters`): they occupy the
+        columns of theta after the free ones, with their own bounds, and are filled in by the caller.
 
     Returns
     -------
@@ -83,9 +108,11 @@ def build_descriptor(parameters, model_parameters, rotation, background, columns
     desc.device = device
     desc.n_stars_total = n_stars_total
 
-    free = [name for name, par in parameters.items() if not par.fixed]
+    derived = list(derived)
+    free = [name for name, par in parameters.items() if not par.fixed] + derived
     if len(free) > _native.MAX_THETA:
-        raise PackError('At most {0} free parameters are supported, got {1}.'.format(_native.MAX_THETA, len(free)))
+        raise PackError('At most {0} free (plus per-walker constrained) parameters are supported, got {1}.'.format(
+            _native.MAX_THETA, len(free)))
     desc.n_theta = len(free)
     for j in range(_native.MAX_THETA):
         desc.lower[j] = -np.inf
@@ -97,7 +124,7 @@ def build_descriptor(parameters, model_parameters, rotation, background, columns
     # every parameter -- fixed ones too -- is bounds-checked by Runner.lnprior (runner.py:206-217)
     fixed_ok = 1
     for name, par in parameters.items():
-        if par.fixed:
+        if par.fixed and name not in derived:
             value = float(par.value)
             if value < par.min or value > par.max:
                 fixed_ok = 0
@@ -113,7 +140,7 @@ def build_descriptor(parameters, model_parameters, rotation, background, columns
         desc.unit_scale[k] = _unit_scale(slot_name, par.unit)
         value = par.value
         desc.fixed_value[k] = 0.0 if value is None else float(value)
-        if not par.fixed:
+        if not par.fixed or slot_name in derived:
             desc.slot[k] = free.index(slot_name)
 
     keep = []

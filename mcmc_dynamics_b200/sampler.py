@@ -198,14 +198,34 @@ class DeviceEnsembleSampler(object):
         return self.naccepted / float(max(1, self.iteration))
 
     def run_mcmc(self, initial_state, nsteps, log_prob0=None, rstate0=None, progress=False, store=True, **kwargs):
+        """emcee's ``run_mcmc`` as far as ``analysis/runner.py:416-419`` uses it.  ``log_prob0`` is
+        accepted and not used: the initial log-probabilities are always evaluated on the device (one
+        launch), so a stale value handed in by the caller cannot enter the chain.
+        ``rstate0`` must be ``None``: the random numbers are counter-based (Philox, keyed by the ``seed``
+        given at construction and the step number), there is no generator state to restore; the state
+        returned is ``None`` accordingly."""
         nsteps = int(nsteps)
+        if rstate0 is not None:
+            raise ValueError("DeviceEnsembleSampler draws counter-based random numbers keyed by its `seed`; "
+                             "rstate0 cannot be applied")
+        if initial_state is None and not self._have_state:
+            raise ValueError("Cannot have `initial_state=None` if run_mcmc has never been called.")
         if initial_state is not None and (not self._have_state or not np.array_equal(initial_state, self._last_pos)):
             pos = _native.contiguous(initial_state)
             if pos.shape != self._rows_shape + (self.ndim,):
                 raise ValueError("incompatible input dimensions {0}".format(pos.shape))
+            if not np.isfinite(pos).all():
+                raise ValueError("At least one parameter value was infinite" if np.any(np.isinf(pos))
+                                 else "At least one parameter value was NaN")
             rc = self._lib.mcd_ensemble_set_state(self._handle, _native.as_double_ptr(pos))
             if rc != 0:
                 _native.check(rc)
+            first = np.empty(self._rows_shape, dtype=np.float64)
+            rc = self._lib.mcd_ensemble_get_state(self._handle, None, _native.as_double_ptr(first))
+            if rc != 0:
+                _native.check(rc)
+            if np.any(np.isnan(first)):                   # emcee: checked before the first step, not after the last
+                raise ValueError("The initial log_prob was NaN")
             self._have_state = True
         chain = np.empty((nsteps,) + self._rows_shape + (self.ndim,), dtype=np.float64) if store else None
         lnp = np.empty((nsteps,) + self._rows_shape, dtype=np.float64) if store else None

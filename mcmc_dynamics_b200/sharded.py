@@ -117,11 +117,22 @@ class ShardedLikelihood(object):
         return DeviceEnsembleSampler(n_walkers, self.model.n_fitted_parameters, self.model.pack(), a=a, seed=seed)
 
     def lnprob(self, theta):
-        """Host array in, host array out (what the sampler calls): pinned staging, H2D, shard kernel,
-        all-reduce, D2H."""
+        """Host array in, host array out (what a host sampler calls on every rank).  Fused mode: ONE C-ABI
+        call, ``mcd_lnprob_allreduce`` -- pinned copy-in, shard kernel with the cross-GPU exchange in its
+        tail, copy-out, replayed as one CUDA graph.  NCCL mode: pinned staging, H2D, shard kernel,
+        ``all_reduce``, D2H through torch."""
         torch = self._torch
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         n, p = theta.shape
+        if self.fused and n <= self.max_walkers:
+            packed = self.model.pack()
+            if p != packed.n_theta:
+                raise ValueError('theta must have shape (n_walkers, {0}), got {1}'.format(packed.n_theta, theta.shape))
+            out = np.empty(n, dtype=np.float64)
+            rc = packed._lib.mcd_lnprob_allreduce(packed.handle, theta.ctypes.data, n, out.ctypes.data)
+            if rc != 0:
+                _native.check(rc)
+            return out
         on_gpu = self.device.type == 'cuda'
         if self._pinned_in is None or self._pinned_in.shape[0] < n or self._pinned_in.shape[1] != p:
             self._pinned_in = torch.empty((max(n, 64), p), dtype=torch.float64)

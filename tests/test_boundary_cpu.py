@@ -159,9 +159,57 @@ def test_descriptor_routing_and_units():
     model.parameters['v_sys'].min = 2.0                       # fixed value 1.0 now violates its bounds
     assert model._descriptor()[0].fixed_prior_ok == 0
     model.parameters['v_sys'].min = -np.inf
-    model.parameters['a'].set(expr='2 * r_peak')              # per-walker constraint: rejected at pack time
-    with pytest.raises(pack.PackError):
-        model._descriptor()
+    # per-walker constraint (reference: asteval per call, analysis/runner.py:163-176): the constrained
+    # parameter leaves theta and comes back as an extra kernel column evaluated on the host per walker
+    model.parameters['a'].set(expr='2 * r_peak')
+    free = model.fitted_parameters
+    assert 'a' not in free and pack.derived_parameters(model.parameters) == ['a']
+    desc, keep = model._descriptor()
+    assert desc.n_theta == len(free) + 1
+    slots = dict(zip(_native.PARAM_SLOTS, list(desc.slot)))
+    assert slots['a'] == len(free) and slots['r_peak'] == free.index('r_peak')
+    assert desc.lower[len(free)] == 0.0 and desc.upper[len(free)] == np.inf      # bounds of `a` itself
+    theta = np.abs(np.random.default_rng(0).normal(size=(5, len(free)))) + 0.1
+    theta[:, free.index('f_back')] = 0.5
+    full = model._device_theta(theta)
+    assert full.shape == (5, len(free) + 1)
+    assert np.array_equal(full[:, -1], 2 * theta[:, free.index('r_peak')])
+    # expressions the vectorised evaluation cannot handle fall back to one evaluation per walker
+    model.parameters['a'].set(expr='max(2 * r_peak, 1.0)')
+    model._derived = pack.derived_parameters(model.parameters)
+    assert np.array_equal(model._device_theta(theta)[:, -1], np.maximum(2 * theta[:, free.index('r_peak')], 1.0))
+    # the prior bounds-checks the constrained value per walker (parameter.py:691-692 via runner.py:207-216)
+    model.parameters['a'].set(expr='2 * r_peak', max=1.0)
+    lnp = model.lnprior(theta)
+    assert np.array_equal(np.isfinite(lnp), 2 * theta[:, free.index('r_peak')] <= 1.0)
+    # a constraint on fixed parameters only stays a plain fixed value
+    model.parameters['r_peak'].set(value=3.0, fixed=True)
+    assert pack.derived_parameters(model.parameters) == []
+    assert model._descriptor()[0].n_theta == len(model.fitted_parameters)
+
+
+def test_default_parameter_files_do_not_freeze_the_generator():
+    """The reference's config/*.json carry ``rng_seed: null`` and no ``random_state``
+    (config/model.json:1-5), so initials drawn from the defaults differ from object to object
+    (parameter.py:73-74); ``Parameters(rng_seed=...)`` stays reproducible (parameter.py:207-209)."""
+    import json
+    from mcmc_dynamics_b200 import config
+    from mcmc_dynamics_b200.parameter import Parameters
+    for name in config.SETS:
+        with open(config.default_file(name)) as f:
+            state = json.load(f)
+        assert 'random_state' not in state and state['unique_symbols'] == {'rng_seed': None}
+    a = Parameters().load(open(config.default_file('model')))
+    b = Parameters().load(open(config.default_file('model')))
+    assert not np.array_equal(a['v_sys'].evaluate_initials(8), b['v_sys'].evaluate_initials(8))
+    c = Parameters(rng_seed=5).load(open(config.default_file('model')))
+    d = Parameters(rng_seed=5).load(open(config.default_file('model')))
+    assert np.array_equal(c['v_sys'].evaluate_initials(8), d['v_sys'].evaluate_initials(8))
+    # a user's own snapshot keeps the generator state, as in the reference (parameter.py:458-466)
+    snap = json.loads(c.dumps())
+    assert snap['random_state'] is not None
+    e = Parameters().loads(c.dumps())
+    assert np.array_equal(c['sigma_max'].evaluate_initials(4), e['sigma_max'].evaluate_initials(4))
 
 
 def test_superfluous_free_parameters_are_prior_checked_only():

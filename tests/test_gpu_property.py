@@ -131,3 +131,38 @@ def test_example_catalogue_of_the_reference():
     # the packed unit vectors reproduce the catalogue's own position angles: v_los = v_maxx sin - v_maxy cos
     theta_pa = d['theta']
     assert np.allclose(np.arctan2(np.sin(theta_pa), np.cos(theta_pa)), theta_pa)
+
+
+def test_expr_constrained_parameter_is_evaluated_per_walker():
+    """``a`` tied to a sampled parameter by an expression (the reference re-evaluates it through asteval
+    on every call: analysis/runner.py:163-176, parameter.py:865-874).  The constrained model must return
+    what the unconstrained one returns when handed the constrained values explicitly; the oracle agrees."""
+    from common import RTOL, build
+    from oracle import harness
+    model, oracle, theta, truth = build('ModelFit', n_stars=1200)
+    free = list(model.fitted_parameters)
+    th = theta(24)
+    th[:, free.index('a')] = 0.5 * th[:, free.index('r_peak')] + 1.0
+    want = model.lnprob(th)
+    assert harness.relative_error(want, oracle.lnprob_many(th)) < RTOL
+    model.parameters['a'].set(expr='0.5 * r_peak + 1.0')
+    assert 'a' not in model.fitted_parameters
+    th_c = np.delete(th, free.index('a'), axis=1)
+    got = model.lnprob(th_c)
+    assert np.array_equal(got, want)
+    assert isinstance(model.lnprob(th_c[0]), float) and model.lnprob(th_c[0]) == want[0]
+    # the host sampler drives the same path (W >= 2 P with P = 5 sampled parameters)
+    run = model(n_walkers=24, n_steps=5, pos=th_c, prefix=None, seed=3)
+    assert run.chain.shape == (24, 5, 5) and np.all(np.isfinite(run.lnprobability))
+    # the constrained value is bounds-checked like every other parameter (runner.py:207-216)
+    model.parameters['a'].set(max=float(np.median(th[:, free.index('a')])))
+    out = model.lnprob(th_c)
+    inside = th[:, free.index('a')] <= model.parameters['a'].max
+    assert np.array_equal(np.isfinite(out), inside) and np.array_equal(out[inside], want[inside])
+    # the device-only paths say why they cannot evaluate host-side expressions
+    model.parameters['a'].set(max=np.inf)
+    import torch
+    with pytest.raises(ValueError, match='box priors only'):
+        model.lnprob_tensor(torch.as_tensor(th_c, device='cuda:0'))
+    with pytest.raises(ValueError, match='box priors only'):
+        model(n_walkers=24, n_steps=2, pos=th_c, sampler='device', prefix=None)

@@ -214,3 +214,49 @@ def test_device_sampler_on_the_background_variants(variant, sampler_path):
     assert np.allclose(model.lnprob(last), lnp[:, -1], rtol=1e-12, atol=0)
     assert harness.relative_error(lnp[:8, -1], oracle.lnprob_many(last[:8])) < 1e-9
     assert 0.05 < (s.naccepted / 25.0).mean() < 0.95
+
+
+def test_graph_sampler_survives_scratch_growth_and_repack(monkeypatch):
+    """A captured ensemble graph bakes in the handle's scratch buffers, packed columns and routing.  A
+    larger lnprob call (scratch re-allocated) or a re-pack between two ``run_mcmc`` calls must make the
+    sampler re-capture instead of replaying through freed pointers: the continued chain equals an
+    uninterrupted one bit for bit."""
+    monkeypatch.setenv('MCD_NO_RESIDENT_CHAIN', '1')
+    model, truth = _mock_model(n_stars=6000, seed=31)
+    pos = synthetic.initial_ball(truth, model.fitted_parameters, 24, seed=3)
+    ref = samplers.DeviceEnsembleSampler(24, model.n_fitted_parameters, model.pack(), seed=77)
+    ref.run_mcmc(pos, 30)
+    s = samplers.DeviceEnsembleSampler(24, model.n_fitted_parameters, model.pack(), seed=77)
+    s.run_mcmc(pos, 10)
+    assert s.engine[0] == 'graph'
+    big = synthetic.initial_ball(truth, model.fitted_parameters, 2000, seed=9)
+    lnp_big = model.lnprob(big)                        # many more walkers: partials / counters grow
+    assert np.all(np.isfinite(lnp_big))
+    s.run_mcmc(None, 10)
+    model.math_mode = 'plain'                          # re-pack (new kernel variant, columns rewritten) ...
+    model.lnprob(big[:3])
+    model.math_mode = 'fast'                           # ... and back
+    model.lnprob(big[:3])
+    s.run_mcmc(None, 10)
+    assert np.array_equal(s.chain, ref.chain) and np.array_equal(s.lnprobability, ref.lnprobability)
+
+
+def test_device_sampler_rejects_bad_initial_state():
+    """emcee raises before the first step when the initial log-probability is NaN or a coordinate is not
+    finite; so does the device sampler, and it refuses an `rstate0`."""
+    model, truth = _mock_model(n_stars=200)
+    pos = synthetic.initial_ball(truth, model.fitted_parameters, 16, seed=3)
+    s = samplers.DeviceEnsembleSampler(16, model.n_fitted_parameters, model.pack(), seed=1)
+    bad = pos.copy()
+    bad[2, 0] = np.nan
+    with pytest.raises(ValueError, match='NaN'):
+        s.run_mcmc(bad, 2)
+    bad[2, 0] = np.inf
+    with pytest.raises(ValueError, match='infinite'):
+        s.run_mcmc(bad, 2)
+    with pytest.raises(ValueError, match='rstate0'):
+        s.run_mcmc(pos, 2, rstate0=np.random.RandomState(1).get_state())
+    with pytest.raises(ValueError, match='initial_state'):
+        s.run_mcmc(None, 2)
+    out = s.run_mcmc(pos, 2, log_prob0=np.zeros(16))   # accepted, recomputed on the device
+    assert np.allclose(model.lnprob(out[0]), out[1], rtol=1e-12)

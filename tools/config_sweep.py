@@ -19,73 +19,23 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+from mcmc_dynamics_b200 import configs  # noqa: E402
 from mcmc_dynamics_b200 import sampler as samplers  # noqa: E402
 from mcmc_dynamics_b200 import synthetic  # noqa: E402
-from mcmc_dynamics_b200.analysis import ConstantFit, ModelFit, ModelFitGB  # noqa: E402
-from mcmc_dynamics_b200.background import SingleStars  # noqa: E402
+from mcmc_dynamics_b200.analysis import ConstantFit  # noqa: E402
 from oracle import harness  # noqa: E402
 
 
-def fix_centre(model, truth, free=False):
-    model.parameters['ra_center'].set(value=truth['ra_center'], fixed=not free)
-    model.parameters['dec_center'].set(value=truth['dec_center'], fixed=not free)
-
-
-def config_c1():
-    d = np.load(os.path.join(ROOT, 'tests', 'golden', 'c1_example_catalogue.npz'))
-    data = synthetic.reader_from_columns({k: d[k] for k in ('ra', 'dec', 'v', 'verr')})
-    truth = {'ra_center': float(d['ra_center']), 'dec_center': float(d['dec_center']), 'v_sys': 0.0,
-             'sigma_max': 30.0, 'v_maxx': 2.0, 'v_maxy': -2.0}
-    m = ConstantFit(data)
-    fix_centre(m, truth)
-    m.parameters['v_sys'].set(value=0.0, fixed=True)        # bin/run.py:487-491
-    return 'C1 example catalogue, ConstantFit, v_sys fixed', m, truth, 16
-
-
-def config_c2():
-    data, truth = synthetic.mock_cluster(10_000, seed=1)
-    m = ModelFit(data)
-    fix_centre(m, truth)
-    return 'C2 1e4 stars, ModelFit fixed centre', m, truth, 128
-
-
 def config_c3(gb=False):
-    cols, truth = synthetic.mock_cluster(100_000, seed=2, as_reader=False)
-    cols, sample_field = synthetic.add_background(cols, truth, seed=102)
-    truth = dict(truth, v_back=5.0, sigma_back=55.0, f_back=0.3)
-    data = synthetic.reader_from_columns(cols)
     if gb:
-        m = ModelFitGB(data)
-        name = 'C3b 1e5 stars, ModelFitGB (fitted Gaussian background)'
-    else:
-        t0 = time.perf_counter()
-        bg = SingleStars(sample_field(2000, seed=202))
-        m = ModelFit(data, background=bg)
-        name = 'C3 1e5 stars, ModelFit + SingleStars(M=2000) mixture [bg precompute %.0f ms]' % (
-            1e3 * (time.perf_counter() - t0))
-    fix_centre(m, truth)
-    return name, m, truth, 256
+        return configs.config_c3b()
+    t0 = time.perf_counter()
+    name, m, truth, w = configs.config_c3()
+    return name + ' [construction incl. bg precompute %.0f ms]' % (1e3 * (time.perf_counter() - t0)), m, truth, w
 
 
-def config_c4():
-    data, truth = synthetic.mock_cluster(300_000, seed=3, ra_center=201.696718746, dec_center=-47.479909445555,
-                                         v_sys=232.5)
-    m = ModelFit(data)
-    fix_centre(m, truth, free=True)
-    m.parameters['v_sys'].set(value=232.5, fixed=True)      # bin/run_test_5139_center.py:157-165
-    m.parameters['sigma_max'].set(min=0, max=100)
-    m.parameters['a'].set(min=0, max=300)
-    m.parameters['v_maxx'].set(min=-100, max=100)
-    m.parameters['v_maxy'].set(min=-100, max=100)
-    m.parameters['r_peak'].set(min=0, max=500)
-    return 'C4 3e5 stars, ModelFit free centre, omega Cen-like bounds', m, truth, 128
-
-
-def config_c5(free=False, n=10_000_000):
-    data, truth = synthetic.mock_cluster(n, seed=4)
-    m = ModelFit(data)
-    fix_centre(m, truth, free=free)
-    return 'C5 %.0e stars, ModelFit %s centre' % (n, 'free' if free else 'fixed'), m, truth, 1024
+config_c1, config_c2, config_c4, config_c5, fix_centre = (configs.config_c1, configs.config_c2, configs.config_c4,
+                                                          configs.config_c5, configs.fix_centre)
 
 
 def time_device(model, theta_dev, reps):
