@@ -338,15 +338,24 @@ static void choose_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p)
     p.wl = best_wl;
     p.slices = best_s;
     p.n_groups = best_g;
-    // Star tiling: stars per stage (`tile`, multiple of 16) and tiles per CTA are chosen together so
-    // that the grid fills whole waves of resident CTAs (a grid of 1.3 waves runs as long as one of
-    // 2.0) while the per-CTA prologue/epilogue stays amortised.  Cost model per candidate, in star
-    // iterations per thread: (waves + 0.3) * (tiles_per_chunk * (tile / slices + 3) + overhead); the 0.3
-    // accounts for CTAs of the last wave finishing at different times (measured: a single wave
-    // leaves the FP64 pipe partly idle in the tail), 3 for the barrier and stage hand-over of every
-    // tile, `overhead` for walker set-up and reduction.
-    const int wave = std::max(1, h->sm_count * h->blocks_per_sm);
-    const int per_wave = std::max(1, wave / (p.n_groups * h->n_segments));
+    // Star tiling: stars per stage (`tile`, multiple of 16) and tiles per CTA are chosen together.  The
+    // kernel is FP64-pipe bound, so co-resident CTAs share the pipe and the launch takes as long as the most
+    // loaded SM needs for its CTAs one after the other.  Cost of a candidate, in star iterations per thread:
+    //   cta   = tiles_per_chunk * (tile / slices + 3) + overhead      (3: barrier + stage hand-over per tile;
+    //           overhead: walker set-up and reduction, ~24 iterations' worth of pipe time)
+    //   load  = CTAs on the most loaded SM
+    //           - grid fits one wave of resident CTAs: the hardware deals them out round-robin and nothing
+    //             rebalances, so load = ceil(CTAs / SMs); 5 % is added for the differences between SMs that
+    //             only a multi-wave grid evens out (measured on the 1e7-star workload: 8 waves beat 1), and
+    //             25 % when an SM holds a single CTA (8 warps do not keep the FP64 pipe busy: measured 18 %)
+    //           - several waves: CTAs / SMs on average, plus a third of a CTA for the ragged end
+    //   cost  = load * cta
+    // Fitted to a (tile, tiles_per_chunk) sweep of BASELINE configs C3 and C4 (profiles/r02_geometry.md):
+    // measured time / cost is constant within +-8 % over 24 geometries, where the round-1 model (whole waves
+    // of SMs x CTAs-per-SM, blind to a partly filled wave) was off by up to 35 %.
+    const int sms = std::max(1, h->sm_count);
+    const int resident = sms * std::max(1, h->blocks_per_sm);
+    const int problems = std::max(1, p.n_groups * h->n_segments);      // CTAs per star chunk
     const double overhead = 24.0;
     const long long n = std::max<long long>(h->max_segment, 1);     // grid sized for the largest segment
     int min_tile = ((2 * p.slices + 15) / 16) * 16;
@@ -355,12 +364,17 @@ static void choose_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p)
     int best_tile = kMaxTile, best_tpc = 1;
     for (int tile = min_tile; tile <= kMaxTile; tile += 16) {
         const long long n_tiles = (n + tile - 1) / tile;
-        for (int target = 1; target <= kWaves; ++target) {
-            const long long slots = (long long)target * per_wave;
+        // candidates: k CTAs per SM for k = 1 .. kWaves * CTAs-per-SM
+        for (int k = 1; k <= kWaves * std::max(1, h->blocks_per_sm); ++k) {
+            const long long slots = std::max<long long>(1, (long long)k * sms / problems);
             const long long tpc = std::max<long long>(1, (n_tiles + slots - 1) / slots);
             const long long chunks = (n_tiles + tpc - 1) / tpc;
-            const long long waves = (chunks + per_wave - 1) / per_wave;
-            const double cost = ((double)waves + 0.3) * ((double)tpc * ((double)tile / p.slices + 3.0) + overhead);
+            const long long ctas = chunks * problems;
+            const double cta = (double)tpc * ((double)tile / p.slices + 3.0) + overhead;
+            const long long per_sm = (ctas + sms - 1) / sms;
+            const double load = ctas <= resident ? (per_sm == 1 ? 1.25 : 1.05) * (double)per_sm
+                                                 : (double)ctas / sms + 0.3;
+            const double cost = load * cta;
             if (cost < best * (1.0 - 1e-12)) {
                 best = cost;
                 best_tile = tile;

@@ -58,6 +58,7 @@ namespace mcd {
 // ------------------------------------------------------------------------------------------
 // packed column layout
 // ------------------------------------------------------------------------------------------
+//   (FAST mixture variants store v * kExpArgScale instead of v)
 //   free centre            : p1 = cos(dec) sin(ra-ra0), p2 = cos(dec) cos(ra-ra0), sin(dec), v, verr^2
 //   fixed centre, constant : cos(theta_i), sin(theta_i), v, verr^2
 //   fixed centre, radial   : x, y [arcmin], r^2, v, verr^2
@@ -140,7 +141,9 @@ __global__ void pack_kernel(const PackParams P) {
             P.cols[c++][o] = dx * dx + dy * dy;
         }
     }
-    P.cols[c++][o] = v;
+    // FAST mixture kernels take the velocity in units of 1 / kExpArgScale (see `term`)
+    const bool scaled = P.math_mode == MCD_MATH_FAST && P.background != MCD_BG_NONE;
+    P.cols[c++][o] = scaled ? v * kExpArgScale : v;
     P.cols[c++][o] = e2;
     if (P.background == MCD_BG_FIXED_PMEMBER || P.background == MCD_BG_FIXED_DENSITY) {
         const double w = P.background == MCD_BG_FIXED_PMEMBER ? P.raw.pmember[i] : P.raw.density[i];
@@ -151,8 +154,16 @@ __global__ void pack_kernel(const PackParams P) {
             int e, invalid = 0;
             exp_split(lbg, m, e, invalid);
             const double wb = P.background == MCD_BG_FIXED_PMEMBER ? (1.0 - w) : 1.0;
-            P.cols[c++][o] = invalid ? __longlong_as_double(0x7ff8000000000000LL) : wb * kSqrt2Pi * m;
-            P.icol[o] = e;
+            const double mant = invalid ? __longlong_as_double(0x7ff8000000000000LL) : wb * kSqrt2Pi * m;
+            // Background term B = mant * 2^e.  Where it is a comfortable plain double (the rule, not the
+            // exception: |log2 B| <= kMixComfort means lbg within ~ +-140 nats) the star takes the kernel's
+            // fast path -- B is stored as it is and the exponent column carries kMixFastFlag; otherwise
+            // (p = 1, a star hundreds of sigma from every background velocity, invalid input) the
+            // (mantissa, exponent) pair is kept for the extended-range path.
+            const int mexp = ((__double2hiint(mant) >> 20) & 0x7ff) - 1023;
+            const bool comfortable = !invalid && mant > 0.0 && mexp > -1000 && abs(mexp + e) <= kMixComfort && abs(e) < 2000;
+            P.cols[c++][o] = comfortable ? ldexp(mant, e) : mant;
+            P.icol[o] = comfortable ? kMixFastFlag : e;
         } else {
             P.cols[c++][o] = lbg;
         }
@@ -183,6 +194,9 @@ struct Walker {
     double sbs, cbs;            //              -sin(ra_c - ra0) sin(dec_c), -cos(ra_c - ra0) sin(dec_c)
     double vb, sb2, fb;         // background: v_back, sigma_back^2, f_back
     int prior_ok;
+    int slow;                   // FAST mixtures: every term of this walker takes the extended-range path
+    // FAST mixture kernels (SCALED): vsys, cx, cy, vb are multiplied by kExpArgScale, so that residuals come
+    // out as u = z * kExpArgScale, the argument of exp_neg_sq_split
 };
 
 // stretch-move proposal of active walker k of segment `seg` (emcee RedBlueMove/StretchMove):
@@ -208,7 +222,7 @@ __device__ __forceinline__ double draw_proposal(const LaunchParams &P, int seg, 
     return z;
 }
 
-template <int ROT, int FREE, int BG>
+template <int ROT, int FREE, int BG, bool SCALED = false>
 __device__ __forceinline__ void load_walker(const LaunchParams &P, const double *row, Walker &W) {
     double par[MCD_NPARAM];
 #pragma unroll
@@ -254,6 +268,17 @@ __device__ __forceinline__ void load_walker(const LaunchParams &P, const double 
     W.vb = par[MCD_P_V_BACK];
     W.sb2 = par[MCD_P_SIGMA_BACK] * par[MCD_P_SIGMA_BACK];
     W.fb = par[MCD_P_F_BACK];
+    W.slow = 0;
+    if constexpr (SCALED) {
+        W.vsys *= kExpArgScale;
+        W.cx *= kExpArgScale;
+        W.cy *= kExpArgScale;
+        W.vb *= kExpArgScale;
+        // The fast path keeps the per-star factor as a plain double and renormalises the running product
+        // every four stars: it needs the background weight f_back inside a sane range.  A walker with a
+        // (nearly) vanishing or non-finite f_back evaluates all its terms in extended range instead.
+        if constexpr (BG == MCD_BG_FIXED_DENSITY || BG == MCD_BG_GAUSSIAN) W.slow = !(W.fb >= 1e-9 && W.fb <= 1e9);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -275,15 +300,30 @@ struct Accum<MCD_BG_NONE, MCD_MATH_FAST> {
 template <int BG>
 struct Accum<BG, MCD_MATH_FAST> {
     LogProduct num, den;
-    __device__ __forceinline__ void reset() { num.reset(); den.reset(); }
+    int dead;            // a star's likelihood is exactly zero (extended-range path): lnlike = -inf
+    __device__ __forceinline__ void reset() { num.reset(); den.reset(); dead = 0; }
+    // Called after at most four stars.  Fast-path factors lie within 2^+-(kMixComfort + a few), so the
+    // product of four stays a normal number; anything else (NaN, inf, zero, negative) raises `bad`.
     __device__ __forceinline__ void end_group() {
-        if (BG != MCD_BG_FIXED_PMEMBER) den.renormalise_checked();     // raw factors: fold every pair
+        num.renormalise_checked();
+        if (BG != MCD_BG_FIXED_PMEMBER) den.renormalise_checked();
     }
-    // mul_ext() brings the factors' mantissas into [1, 2): the product of a tile (<= 256) cannot overflow
-    __device__ __forceinline__ void end_tile() { num.renormalise_ext(); }
+    __device__ __forceinline__ void end_tile() {}
+    // one factor m * 2^e from the extended-range path
+    __device__ __forceinline__ void mul_slow(double m, int e) {
+        if (m > 0.0) {
+            num.mul_ext(m, e);
+            num.renormalise_ext();
+        } else if (m == 0.0) {
+            dead = 1;
+        } else {
+            num.bad = 1;        // negative weight or NaN
+        }
+    }
     __device__ __forceinline__ double value() {
         const double n = num.ln();
-        return BG == MCD_BG_FIXED_PMEMBER ? n : n - den.ln();
+        const double r = BG == MCD_BG_FIXED_PMEMBER ? n : n - den.ln();
+        return (dead && r == r) ? __longlong_as_double(0xfff0000000000000LL) : r;
     }
 };
 template <int BG>
@@ -303,12 +343,55 @@ struct Star {
     int e;        // exponent column (FAST fixed-background variants)
 };
 
+// Extended-range evaluation of one mixture factor (times sqrt(2 pi)) as mantissa * 2^exponent: the
+// exponentials come as (mantissa, exponent) pairs without the clamp of the fast path and the two
+// components are added in that form, so nothing can underflow -- the analogue of the reference's
+// max-shifted log-sum-exp (analysis/runner.py:279-284) including its -inf corner.  Out of line and by
+// value: the rare path must not take part in the register allocation of the star loop.
+//   u, ub : member / background residual in units of 1 / kExpArgScale;  y : norm^-1/2;  wm : member weight
+//   b     : fixed backgrounds: the packed background column (mantissa, or the plain term when bexp is
+//           kMixFastFlag); fitted background: yb = (verr^2 + sigma_back^2)^-1/2
+struct ExtFactor {
+    double m;
+    int e;
+};
+template <int BG>
+static __device__ __noinline__ ExtFactor mix_term_slow(double fb, double u, double y, double wm, double b, int bexp, double ub) {
+    const double zz = u * (1.0 / kExpArgScale);
+    double sm, bm;
+    int se, be;
+    exp_neg_half(zz * zz, sm, se);
+    if constexpr (BG == MCD_BG_GAUSSIAN) {
+        const double zb = ub * (1.0 / kExpArgScale);
+        double ebm;
+        exp_neg_half(zb * zb, ebm, be);
+        bm = fb * b * ebm;
+    } else {
+        bm = BG == MCD_BG_FIXED_DENSITY ? fb * b : b;
+        be = bexp == kMixFastFlag ? 0 : bexp;
+    }
+    ExtFactor f;
+    ext_add(wm * y * sm, se, bm, be, f.m, f.e);
+    return f;
+}
+
+// 2^(j / kMixTableSize) into shared memory (called by the first kMixTableSize threads' worth of a CTA before
+// its first barrier)
+__device__ __forceinline__ void fill_exp2_table(double *table) {
+#if MCD_MIX_LEAN
+    for (int j = threadIdx.x; j < kMixTableSize; j += blockDim.x) table[j] = exp2((double)j * (1.0 / kMixTableSize));
+#else
+    if (threadIdx.x < 64) table[threadIdx.x] = kExp2Table[threadIdx.x];
+#endif
+}
+
 // ------------------------------------------------------------------------------------------
 // one (walker, star) term
 // ------------------------------------------------------------------------------------------
-template <int ROT, int FREE, int BG, int MATH>
+// ASSUME_FAST (FAST mixtures with a per-star flag): the caller has checked that this star takes the fast path
+template <int ROT, int FREE, int BG, int MATH, bool ASSUME_FAST = false>
 __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(ROT, FREE, BG)> &S, Accum<BG, MATH> &A,
-                                     const double *__restrict__ exp2_table = nullptr) {
+                                     uint32_t exp2_table = 0) {
     constexpr int NB = base_columns(ROT, FREE);
     constexpr bool FAST = MATH == MCD_MATH_FAST;
     // ---- geometry: numerator `num` of the rotation term, r^2 ---------------------------------
@@ -335,6 +418,7 @@ __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(R
         r2 = S.c[2];
     }
     const double v = S.c[NB - 2], e2 = S.c[NB - 1];
+    // FAST mixtures: the packed v and the walker's v_sys both carry kExpArgScale (pack kernel, load_walker)
     const double dv = v - W.vsys;
 
     if constexpr (FAST) {
@@ -343,7 +427,8 @@ __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(R
         if constexpr (ROT == MCD_ROT_RADIAL) {
             D1 = fma(r2, W.ip2, 1.0);
             const double D2 = fma(r2, W.ia2, 1.0);
-            norm = fma(W.s2, fast_rsqrt(D2), e2);          // sigma_max^2 / sqrt(1 + r^2/a^2) + verr^2
+            // sigma_max^2 / sqrt(1 + r^2/a^2) + verr^2
+            norm = fma(W.s2, BG == MCD_BG_NONE ? fast_rsqrt(D2) : mix_rsqrt(D2), e2);
         } else {
             norm = e2 + W.s2;
         }
@@ -355,36 +440,47 @@ __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(R
             A.chi = fma(t * t, fast_rcp(q), A.chi);
             A.norm.mul_raw(norm);
         } else {
-            // member Gaussian without its 1/sqrt(2 pi): y exp(-z^2/2), y = norm^-1/2, z = t y / D1
-            const double yq = fast_rsqrt(q);
-            const double z = t * yq;
+            // Mixture factor times sqrt(2 pi):  wm y exp(-z^2/2) + (background term),  y = norm^-1/2,
+            // z = t y / D1, u = z kExpArgScale.  Fast path: both components as plain doubles, one FMA, the
+            // factor multiplied into the running product (exponent folded every four stars).  It is valid
+            // when the background term is a comfortable double (flag set by the pack kernel per star for the
+            // fixed backgrounds, checked per term for the fitted one); everything else -- weights of exactly
+            // 0 or 1, components hundreds of sigma out, the reference's -inf corner of runner.py:280-286 --
+            // goes through the (mantissa, exponent) arithmetic below, which cannot underflow.
+            const double yq = mix_rsqrt(q);
+            const double u = t * yq;
             const double y = ROT == MCD_ROT_RADIAL ? yq * D1 : yq;
-            double em;
-            int ee;
-            exp_neg_half_table(z * z, exp2_table, em, ee);
             const double wm = S.c[NB];
-            double bm;
-            int be;
+            bool slow = false;
+            if constexpr (!ASSUME_FAST) {
+                slow = W.slow != 0;
+                if constexpr (has_icol(BG, MATH)) slow |= (S.e != kMixFastFlag);
+            }
+            int Nm, Nb = 0;
+            const double em = exp_neg_sq_split(u, exp2_table, Nm);
+            double bterm, yb = 0.0, ub = 0.0;
             if constexpr (BG == MCD_BG_FIXED_PMEMBER) {
-                bm = S.c[NB + 1];
-                be = S.e;
+                bterm = S.c[NB + 1];
             } else if constexpr (BG == MCD_BG_FIXED_DENSITY) {
-                bm = W.fb * S.c[NB + 1];
-                be = S.e;
+                bterm = W.fb * S.c[NB + 1];
                 A.den.mul_raw(wm + W.fb);
             } else {
-                const double nb = e2 + W.sb2;
-                const double yb = fast_rsqrt(nb);
-                const double zb = (v - W.vb) * yb;
-                double ebm;
-                exp_neg_half_table(zb * zb, exp2_table, ebm, be);
-                bm = W.fb * yb * ebm;
+                yb = mix_rsqrt(e2 + W.sb2);
+                ub = (v - W.vb) * yb;
+                const double eb = exp_neg_sq_split(ub, exp2_table, Nb);
+                bterm = (W.fb * yb) * scale_by_table_exponent(eb, Nb);
                 A.den.mul_raw(wm + W.fb);
+                slow |= max(Nm, Nb) < kMixSlowExp * kMixTableSize;
             }
-            double m;
-            int e;
-            ext_add(wm * y * em, ee, bm, be, m, e);
-            A.num.mul_ext(m, e);
+            if (!slow) {
+                A.num.mul_raw(fma(wm * y, scale_by_table_exponent(em, Nm), bterm));
+            } else {
+                const ExtFactor f = mix_term_slow<BG>(W.fb, u, y, wm, BG == MCD_BG_GAUSSIAN ? yb : S.c[NB + 1],
+                                                      BG == MCD_BG_GAUSSIAN ? 0 : S.e, ub);
+                const double m = f.m;
+                const int e = f.e;
+                A.mul_slow(m, e);
+            }
         }
     } else {
         // ---- PLAIN: the reference's formulas with library div / sqrt / log / exp ----------
@@ -451,6 +547,26 @@ __device__ __forceinline__ void load_one(const double *__restrict__ c, const int
 #pragma unroll
     for (int k = 0; k < NC; ++k) a.c[k] = c[k * tile + i];
     a.e = ICOL ? ci[i] : 0;
+}
+
+// two adjacent stars; the FAST mixtures decide once per pair whether both take the fast path
+template <int ROT, int FREE, int BG, int MATH>
+__device__ __forceinline__ void term_pair(const Walker &W, const Star<total_columns(ROT, FREE, BG)> &a,
+                                          const Star<total_columns(ROT, FREE, BG)> &b, Accum<BG, MATH> &A, uint32_t exp2_table) {
+    if constexpr (MATH == MCD_MATH_FAST && BG != MCD_BG_NONE) {
+        int slow = W.slow;
+        if constexpr (has_icol(BG, MATH)) slow |= (a.e ^ kMixFastFlag) | (b.e ^ kMixFastFlag);
+        if (slow == 0) {
+            term<ROT, FREE, BG, MATH, true>(W, a, A, exp2_table);
+            term<ROT, FREE, BG, MATH, true>(W, b, A, exp2_table);
+        } else {
+            term<ROT, FREE, BG, MATH, false>(W, a, A, exp2_table);
+            term<ROT, FREE, BG, MATH, false>(W, b, A, exp2_table);
+        }
+    } else {
+        term<ROT, FREE, BG, MATH>(W, a, A, exp2_table);
+        term<ROT, FREE, BG, MATH>(W, b, A, exp2_table);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -725,8 +841,9 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     __shared__ int s_last;
     // 2^(j/64) for the exponentials of the mixture terms (mcd_math.cuh); filled before the first barrier
     constexpr bool EXP_TABLE = BG != MCD_BG_NONE && MATH == MCD_MATH_FAST;
-    __shared__ double s_exp2[EXP_TABLE ? 64 : 1];
-    if (EXP_TABLE && threadIdx.x < 64) s_exp2[threadIdx.x] = kExp2Table[threadIdx.x];
+    __shared__ double s_exp2[EXP_TABLE ? kMixTableSize : 1];
+    if constexpr (EXP_TABLE) fill_exp2_table(s_exp2);
+    const uint32_t exp2_addr = EXP_TABLE ? smem_u32(s_exp2) : 0u;
 
 #ifdef MCD_KERNEL_PROFILE
     __shared__ unsigned long long s_stamp[12];
@@ -797,10 +914,10 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
             double q[MCD_MAX_THETA];
             int row_index;
             draw_proposal(P, seg, w, q, row_index);
-            load_walker<ROT, FREE, BG>(P, q, W);
+            load_walker<ROT, FREE, BG, EXP_TABLE>(P, q, W);
         }
     } else {
-        if (valid) load_walker<ROT, FREE, BG>(P, P.theta + (size_t)(seg * P.n_walkers + w) * P.n_theta, W);
+        if (valid) load_walker<ROT, FREE, BG, EXP_TABLE>(P, P.theta + (size_t)(seg * P.n_walkers + w) * P.n_theta, W);
     }
     // a walker outside its box prior is never evaluated by the reference (runner.py:303-306)
     const bool active = valid && (W.prior_ok || !P.apply_prior);
@@ -830,24 +947,21 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
                 Star<NC> s0, s1, s2, s3;
                 load_pair<NC, ICOL>(c, ci, TS, i, s0, s1);
                 load_pair<NC, ICOL>(c, ci, TS, i + step, s2, s3);
-                term<ROT, FREE, BG, MATH>(W, s0, A, s_exp2);
-                term<ROT, FREE, BG, MATH>(W, s1, A, s_exp2);
-                A.end_group();
-                term<ROT, FREE, BG, MATH>(W, s2, A, s_exp2);
-                term<ROT, FREE, BG, MATH>(W, s3, A, s_exp2);
+                term_pair<ROT, FREE, BG, MATH>(W, s0, s1, A, exp2_addr);
+                if constexpr (EXP_TABLE == false) A.end_group();       // FAST mixtures fold every four stars
+                term_pair<ROT, FREE, BG, MATH>(W, s2, s3, A, exp2_addr);
                 A.end_group();
             }
             for (; i < n2; i += step) {
                 Star<NC> s0, s1;
                 load_pair<NC, ICOL>(c, ci, TS, i, s0, s1);
-                term<ROT, FREE, BG, MATH>(W, s0, A, s_exp2);
-                term<ROT, FREE, BG, MATH>(W, s1, A, s_exp2);
+                term_pair<ROT, FREE, BG, MATH>(W, s0, s1, A, exp2_addr);
                 A.end_group();
             }
             if ((n & 1) && (n2 / 2) % P.slices == slice) {   // odd tail of the last tile
                 Star<NC> s0;
                 load_one<NC, ICOL>(c, ci, TS, n2, s0);
-                term<ROT, FREE, BG, MATH>(W, s0, A, s_exp2);
+                term<ROT, FREE, BG, MATH>(W, s0, A, exp2_addr);
                 A.end_group();
             }
             A.end_tile();
@@ -968,8 +1082,9 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
     constexpr bool ICOL = has_icol(BG, MATH);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr bool EXP_TABLE = BG != MCD_BG_NONE && MATH == MCD_MATH_FAST;
-    __shared__ double s_exp2[EXP_TABLE ? 64 : 1];          // 2^(j/64), see exp_neg_half_table
-    if (EXP_TABLE && threadIdx.x < 64) s_exp2[threadIdx.x] = kExp2Table[threadIdx.x];
+    __shared__ double s_exp2[EXP_TABLE ? kMixTableSize : 1];          // 2^(j / kMixTableSize), see exp_neg_sq_split
+    if constexpr (EXP_TABLE) fill_exp2_table(s_exp2);
+    const uint32_t exp2_addr = EXP_TABLE ? smem_u32(s_exp2) : 0u;
     const int tid = threadIdx.x;
     const int G = C.group;
     const int seg = blockIdx.x / G;
@@ -1062,7 +1177,7 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
             MCD_STAMP(9);
             Walker Wk;
             Wk.prior_ok = 0;
-            if (valid) load_walker<ROT, FREE, BG>(P, prop + (size_t)lane * NP, Wk);
+            if (valid) load_walker<ROT, FREE, BG, EXP_TABLE>(P, prop + (size_t)lane * NP, Wk);
             MCD_STAMP(1);
             Accum<BG, MATH> A;
             A.reset();
@@ -1073,8 +1188,7 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
                 for (int i = 2 * slice; i < n2; i += stepi) {
                     Star<NC> s0, s1;
                     load_pair<NC, ICOL>(cols, icol, stride, i, s0, s1);
-                    term<ROT, FREE, BG, MATH>(Wk, s0, A, s_exp2);
-                    term<ROT, FREE, BG, MATH>(Wk, s1, A, s_exp2);
+                    term_pair<ROT, FREE, BG, MATH>(Wk, s0, s1, A, exp2_addr);
                     A.end_group();
                     if (++done == 64) {     // fold the running products before they can overflow
                         A.end_tile();
@@ -1084,7 +1198,7 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
                 if ((n & 1) && (n2 / 2) % slices == slice) {
                     Star<NC> s0;
                     load_one<NC, ICOL>(cols, icol, stride, n2, s0);
-                    term<ROT, FREE, BG, MATH>(Wk, s0, A, s_exp2);
+                    term<ROT, FREE, BG, MATH>(Wk, s0, A, exp2_addr);
                     A.end_group();
                 }
                 A.end_tile();

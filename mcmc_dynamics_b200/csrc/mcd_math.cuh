@@ -266,6 +266,79 @@ __device__ __forceinline__ void exp_neg_half_table(double w, const double *__res
     mant = fma(t, p * r, t);
 }
 
+// ---- mixture fast path -------------------------------------------------------------------------
+// exp(-z^2/2) as ONE plain double, for u = z * kExpArgScale (kExpArgScale^2 = 32 log2(e), so that
+// -z^2/2 * log2(e) * 64 = -u^2 and the square is formed inside the two FMAs that split it into integer
+// and fraction -- no separate multiplication, and the walker constants carry the scale for free).
+// |u| is clamped to 254 on the integer pipe, i.e. the result never drops below 2^-1010 and its exponent
+// can be set by an integer addition on the high word: the caller only takes this path when the other
+// mixture component is at least 2^-480, where a member term of 2^-1010 and one of 2^-100000 are the same
+// thing.  A NaN u is clamped too (the NaN reaches the factor through y = norm^-1/2 or the walker's
+// `bad` flag).  9 FP64 + 6 integer instructions.
+constexpr double kExpArgScale = 6.7945744023041525;     // sqrt(32 / ln 2)
+constexpr int kMixFastFlag = (int)0x80000000;           // exponent-column value of a fast-path star
+constexpr int kMixComfort = 200;                        // fast path: |log2(background term)| <= this
+constexpr int kMixSlowExp = -200;                       // fitted background: both components below 2^this -> slow path
+
+#ifndef MCD_MIX_LEAN
+#define MCD_MIX_LEAN 0     // 1: 256-entry table + cubic polynomial (3.5e-13), quadratic Newton (1.3e-12)
+#endif
+#if MCD_MIX_LEAN
+constexpr int kMixTableBits = 8;
+#else
+constexpr int kMixTableBits = 6;
+#endif
+constexpr int kMixTableSize = 1 << kMixTableBits;
+
+// returns the mantissa in [0.99, 2.01); N = table-units exponent: exp(-z^2/2) = mant * 2^(N >> kMixTableBits)
+// `table` is the 32-bit shared-memory address of 2^(j / kMixTableSize), j = 0 .. kMixTableSize - 1 (a generic
+// pointer costs four uniform-datapath instructions per load to rebuild the shared window base).
+__device__ __forceinline__ double exp_neg_sq_split(double u, uint32_t table, int &N) {
+    const double kMagic = 6755399441055744.0;            // 1.5 * 2^52
+    const int hi = min(__double2hiint(u) & 0x7fffffff, 0x406fc000);      // |u| <= 254
+    const double uc = __hiloint2double(hi, __double2loint(u));
+#if MCD_MIX_LEAN
+    // table units of 1/256: -u^2 * 4
+    const double s = uc * 2.0;                            // exact
+    const double shifted = fma(-s, s, kMagic);
+    N = __double2loint(shifted);
+    const double nf = shifted - kMagic;
+    const double r = fma(-s, s, -nf);
+    double p = fma(3.3083026805413713e-09, r, 3.6655655969101062e-06);
+    p = fma(p, r, 0.0027076061740622863);
+#else
+    const double shifted = fma(-uc, uc, kMagic);
+    N = __double2loint(shifted);
+    const double nf = shifted - kMagic;
+    const double r = fma(-uc, uc, -nf);                  // exact square minus its integer part
+    double p = fma(kExp2StepCoef[4], r, kExp2StepCoef[3]);
+    p = fma(p, r, kExp2StepCoef[2]);
+    p = fma(p, r, kExp2StepCoef[1]);
+    p = fma(p, r, kExp2StepCoef[0]);
+#endif
+    double t;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(table + ((uint32_t)(N & (kMixTableSize - 1)) << 3)));
+    return fma(t, p * r, t);
+}
+
+// mant * 2^(N >> kMixTableBits) by an integer addition on the exponent field (N >= -64 * 1010: stays normal)
+__device__ __forceinline__ double scale_by_table_exponent(double mant, int N) {
+    return __hiloint2double(__double2hiint(mant) + ((N >> kMixTableBits) << 20), __double2loint(mant));
+}
+
+// x^(-1/2) for the mixture fast path: cubic Newton step, or quadratic under MCD_MIX_LEAN
+__device__ __forceinline__ double mix_rsqrt(double x) {
+#if MCD_MIX_LEAN
+    const double y0 = rsqrt_seed(x);
+    const double t = x * y0;
+    const double e = fma(-t, y0, 1.0);
+    const double h = __hiloint2double(__double2hiint(y0) - 0x00100000, __double2loint(y0));
+    return fma(h, e, y0);
+#else
+    return fast_rsqrt(x);
+#endif
+}
+
 // 2^d for d <= 0, exactly zero below 2^-960 (integer pipe only)
 __device__ __forceinline__ double pow2_flush(int d) {
     const int hi = (d + 1023) << 20;

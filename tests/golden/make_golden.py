@@ -193,6 +193,13 @@ def main():
                                     for kk, vv in kw.items()} for k, kw in sets.items()},
             'fitted_parameters': names, 'theta': theta.tolist(), 'expected': out,
         }
+        # what the INTEGRATION.md Option-B binding (tools/reference_binding.py) compiles from this REAL
+        # reference object: tests/test_binding_cpu.py checks it against the product's own packing, and
+        # tests/test_gpu_binding.py runs the binding on a stand-in with the same attribute surface
+        sys.path.insert(0, os.path.join(ROOT, 'tools'))
+        import reference_binding
+        case['binding_descriptor'] = reference_binding.summary(reference_binding.describe(model)[0])
+        case['model_parameters'] = list(model.MODEL_PARAMETERS)
         if model.lnlike_background is not None:
             lbg = model.lnlike_background
             case['lnlike_background'] = [float(x) for x in np.asarray(getattr(lbg, 'value', lbg))]

@@ -54,7 +54,8 @@ def test_c3_fixed_background_mixture_at_size():
     # prior rejection and evaluation in one call
     theta[1, model.fitted_parameters.index('sigma_max')] = -1.0
     out = model.lnprob(theta[:8])
-    assert out[1] == -np.inf and np.array_equal(out[[0, 2, 3]], got[[0, 2, 3]])
+    # (8 walkers per call use another launch geometry than 128: same values up to summation order)
+    assert out[1] == -np.inf and np.allclose(out[[0, 2, 3]], got[[0, 2, 3]], rtol=1e-12, atol=0)
 
 
 def test_c3b_fitted_gaussian_background_at_size():
@@ -77,4 +78,4 @@ def test_c4_free_centre_omega_cen_at_size():
     th[1, names.index('sigma_max')] = 100.0000001
     th[2, names.index('v_maxx')] = -100.0000001
     out = model.lnprob(th)
-    assert np.isfinite(out[0]) and out[1] == -np.inf and out[2] == -np.inf and out[3] == got[3]
+    assert np.isfinite(out[0]) and out[1] == -np.inf and out[2] == -np.inf and np.isclose(out[3], got[3], rtol=1e-12, atol=0)
