@@ -397,18 +397,28 @@ def configs_block(device_index):
         t0 = time.perf_counter()
         want = oracle.lnprob_many(theta[:n_check])
         cpu_s = (time.perf_counter() - t0) / n_check
+        # device-timed through the C ABI itself (mcd_lnprob_device on torch's current stream): the torch
+        # operator wrapper adds ~8 us of host work per call, which on C1/C2 would be timed instead of the GPU
         th_dev = torch.as_tensor(theta[:half], device='cuda:%d' % device_index)
+        out_dev = torch.empty(half, dtype=torch.float64, device=th_dev.device)
+        stream = torch.cuda.current_stream(th_dev.device).cuda_stream
+        lib = packed._lib
+
+        def launch():
+            rc = lib.mcd_lnprob_device(packed.handle, th_dev.data_ptr(), half, out_dev.data_ptr(), stream)
+            assert rc == 0, lib.mcd_last_error()
         reps = 200
         for _ in range(5):
-            model.lnprob_tensor(th_dev)
+            launch()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            model.lnprob_tensor(th_dev)
+            launch()
         e1.record()
         torch.cuda.synchronize()
         dev_s = e0.elapsed_time(e1) / reps * 1e-3
+        assert np.array_equal(out_dev.cpu().numpy(), got)
         for _ in range(5):
             model.lnprob(theta[:half])
         t0 = time.perf_counter()

@@ -95,6 +95,7 @@ class Runner(object):
         self._packed_stamps = None
         self._expression_priors_present = False
         self._derived = []
+        self._n_free = None
 
     # ------------------------------------------------------------------------------------------
     # introspection (analysis/runner.py:108-141, 662-673)
@@ -166,6 +167,7 @@ class Runner(object):
         stamps = (pack.edit_stamps(self.parameters), self.math_mode)
         if self._packed is not None and stamps == self._packed_stamps:
             return self._packed                       # nothing was assigned to any parameter since the last call
+        self._n_free = self.n_fitted_parameters
         signature = (pack.routing_signature(self.parameters, self.MODEL_PARAMETERS), self.math_mode)
         self._expression_priors_present = any(par.lnprior is not None for par in self.parameters.values())
         self._derived = pack.derived_parameters(self.parameters)
@@ -211,8 +213,11 @@ class Runner(object):
     def _as_batch(self, values):
         values = np.asarray(values, dtype=np.float64)
         scalar = values.ndim == 1
-        theta = np.atleast_2d(values)
-        assert theta.shape[1] == self.n_fitted_parameters, 'Not all parameters used.'
+        theta = values[None, :] if scalar else values
+        # number of sampled parameters: cached by pack() (refreshed whenever a parameter is edited)
+        n_free = self._n_free if self._packed_stamps is not None and self._packed_stamps[0] == pack.edit_stamps(
+            self.parameters) else self.n_fitted_parameters
+        assert theta.ndim == 2 and theta.shape[1] == n_free, 'Not all parameters used.'
         return theta, scalar
 
     def _derived_columns(self, theta):
@@ -364,13 +369,17 @@ class Runner(object):
         return initials
 
     def __call__(self, n_walkers=100, n_steps=500, n_burn=100, n_threads=1, n_out=None, pos=None, lnprob0=None,
-                 plot=False, prefix='sampler', true_values=None, sampler='host', seed=None, **kwargs):
+                 plot=False, prefix='sampler', true_values=None, sampler='auto', seed=None, **kwargs):
         """Run the ensemble sampler (``analysis/runner.py:332-443``).
 
         ``n_threads`` is accepted and ignored: the walker-parallel process pool of the reference is
         replaced by the batched launch.  ``sampler='host'`` runs an emcee-compatible stretch-move
         loop on the host that calls ``lnprob`` in vectorised mode (emcee itself is used when it is
-        importable); ``sampler='device'`` keeps the whole chain on the GPU.
+        importable); ``sampler='device'`` keeps the whole chain on the GPU (same move, counter-based
+        random numbers).  ``sampler='auto'`` (default) takes the device engine whenever it can express
+        the model -- box priors only, no per-walker ``expr`` constraints, no ``lnprob0`` handed in -- and
+        the host loop otherwise: on the small configurations a host round trip per half-step costs
+        10-20x the likelihood itself (profiles/r02_configs.md), so the drop-in default should not pay it.
         """
         if kwargs:
             if "filename" in kwargs or "plotfilename" in kwargs:
@@ -390,6 +399,12 @@ class Runner(object):
                 raise ValueError(
                     "Invalid initial guesses for walker {0}: {1}={2}".format(i, self.fitted_parameters, pos[i]))
 
+        if sampler not in ('auto', 'device', 'host'):
+            raise ValueError("sampler must be 'auto', 'device' or 'host'")
+        if sampler == 'auto':
+            self.pack()
+            box_only = not (self._expression_priors_present or self._derived)
+            sampler = 'device' if (box_only and lnprob0 is None and n_walkers <= 4096) else 'host'
         if sampler == 'device':
             packed = self.pack()
             self._require_box_priors("sampler='device'")

@@ -38,13 +38,18 @@ __device__ __forceinline__ double rsqrt_seed(double x) {
 }
 
 // Newton order of the reciprocal / reciprocal square root refinements:
-//   3 (cubic step, default): rel. error ~ d^3 with d = seed error (measured 2^-20 for both MUFU
-//                            seeds on B200) -> 2.2e-16 / 2.7e-16 measured; 3 / 5 DFMA
-//   2 (quadratic step)     : measured 9.8e-13 / 1.3e-12; 2 / 3 DFMA (+1 integer op); only 2.5 %
-//                            faster on the headline workload, so not the default
+//   2 (quadratic step, default): measured 9.8e-13 / 1.3e-12 relative (seed error 2^-20 on B200 for both
+//                            MUFU seeds); 2 / 3 FP64 instructions (+1 integer op)
+//   3 (cubic step)         : 2.2e-16 / 2.7e-16; 3 / 5 FP64 instructions
+// The tolerance of the path is 1e-9 relative on lnprob (BASELINE.json north_star); a per-term relative error
+// of 1.3e-12 ends up as < 5e-13 relative on lnprob whatever the catalogue size (it is relative, and of one
+// sign: tests/test_gpu_parity.py measures 1e-13..4e-13 against the oracle), three orders inside it.  On the
+// headline workload the quadratic step is worth 8.3 % (7.395 -> 6.827 ms per 512-walker call over 1e7 stars,
+// profiles/r02_ab_runs.md); round 1 measured 2.5 % on an earlier, less FP64-bound loop and kept the cubic
+// step.  -DMCD_NEWTON=3 restores it (A/B builds: tools/build_variant.py).
 // Measurements: tools/microbench/seeds.cu, DESIGN.md ("arithmetic").
 #ifndef MCD_NEWTON
-#define MCD_NEWTON 3
+#define MCD_NEWTON 2
 #endif
 
 // 1/x for normal positive x.  e = 1 - x*y0, 1/x = y0 (1 + e + e^2 + O(e^3)).
@@ -280,8 +285,12 @@ constexpr int kMixFastFlag = (int)0x80000000;           // exponent-column value
 constexpr int kMixComfort = 200;                        // fast path: |log2(background term)| <= this
 constexpr int kMixSlowExp = -200;                       // fitted background: both components below 2^this -> slow path
 
+// MCD_MIX_LEAN 1 (default): 256-entry table + cubic polynomial (truncation 1.4e-13) and quadratic Newton
+// steps (1.3e-12) in the mixture kernels: 28 instead of 34 FP64 instructions per term, +14 % on the 2e6-star
+// mixture workload (2.87 -> 2.51 ms), same tolerance argument as MCD_NEWTON above.  0: 64-entry table +
+// degree-5 polynomial (4e-17) and cubic Newton steps.
 #ifndef MCD_MIX_LEAN
-#define MCD_MIX_LEAN 0     // 1: 256-entry table + cubic polynomial (3.5e-13), quadratic Newton (1.3e-12)
+#define MCD_MIX_LEAN 1
 #endif
 #if MCD_MIX_LEAN
 constexpr int kMixTableBits = 8;

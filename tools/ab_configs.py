@@ -76,6 +76,8 @@ def main():
             best = min(best, e0.elapsed_time(e1) / calls * 1e-3)
         host = model.lnprob(theta)
         assert np.array_equal(host, out.cpu().numpy())
+        from oracle import harness                   # checker: three walkers against the NumPy oracle
+        err = harness.relative_error(host[:3], harness.oracle_for(model).lnprob_many(theta[:3])) if n <= 3_000_000 else float('nan')
         host_s = 1e30
         for _ in range(3):
             t0 = time.perf_counter()
@@ -84,8 +86,8 @@ def main():
             host_s = min(host_s, (time.perf_counter() - t0) / calls)
         info = packed.info()
         print('%-6s %-62s | device %8.1f us/call %.3e terms/s | host buffers %8.1f us/call %.3e terms/s | grid %d x %d, '
-              'wl %d | lnprob[0] %.9e' % (key, name, 1e6 * best, half * n / best, 1e6 * host_s, half * n / host_s,
-                                         info['last_grid_x'], info['last_grid_y'], info['last_walker_tile'], host[0]),
+              'wl %d | lnprob[0] %.9e | rel err vs oracle %.1e' % (key, name, 1e6 * best, half * n / best, 1e6 * host_s, half * n / host_s,
+                                         info['last_grid_x'], info['last_grid_y'], info['last_walker_tile'], host[0], err),
               flush=True)
         packed.close()
 

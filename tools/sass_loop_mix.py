@@ -6,7 +6,8 @@
                                                       # + profiles/r02_sass_loop_<kernel>.txt (the loop listings)
 
 For a kernel it finds every backward branch, takes the innermost loop body with the most FP64 instructions
-and counts opcodes, plus the FP64-pipe issue cycles per warp under the measured costs of
+and counts the opcodes on its hot path (rare-branch code inside the loop is skipped, see `hot_path`), plus
+the FP64-pipe issue cycles per warp under the measured costs of
 profiles/r01_microbench.md (DFMA with three distinct register operands 3, other FP64 2, MUFU.*64H 2).
 `bench.py` reads `fp64_pipe_instr_per_term` from the JSON instead of carrying literals.
 """
@@ -46,6 +47,26 @@ def function_instructions(lines, key):
     return ins
 
 
+def hot_path(body):
+    """The instructions the loop executes when no rare branch is taken: predicated forward branches inside the
+    body (the mixture kernels' jump to the extended-range code) are counted and not followed, unconditional
+    forward branches are followed (they skip that code).  Predicated non-branch instructions occupy an issue
+    slot either way and are counted."""
+    index = {a: i for i, (a, _) in enumerate(body)}
+    out, i = [], 0
+    while i < len(body):
+        addr, text = body[i]
+        out.append(body[i])
+        m = re.search(r'\bBRA\b.*?(0x[0-9a-f]+)', text)
+        if m and not re.match(r'^@', text):
+            target = int(m.group(1), 16)
+            if target > addr and target in index:
+                i = index[target]
+                continue
+        i += 1
+    return out
+
+
 def loop_mix(lines, key):
     ins = function_instructions(lines, key)
     addr_index = {a: i for i, (a, _) in enumerate(ins)}
@@ -65,6 +86,7 @@ def loop_mix(lines, key):
         if best is None or fp64 > best[0]:
             best = (fp64, body)
     _, body = best
+    body = hot_path(body)
     counts = collections.Counter()
     cycles = 0
     three_operand = 0
