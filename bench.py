@@ -355,6 +355,12 @@ def measured_samplers(args, world, device, model, like, theta_host, n_steps):
         model(n_walkers=args.walkers, n_steps=3, pos=theta_host, sampler='device', seed=1, prefix=None)
         out['device'] = n_steps / timed(lambda: model(n_walkers=args.walkers, n_steps=n_steps, pos=theta_host,
                                                       sampler='device', seed=1, prefix=None))
+        # the same engine without the per-run set-up (state upload, initial lnprob of all walkers, graph capture)
+        dev = samplers.DeviceEnsembleSampler(args.walkers, theta_host.shape[1], model.pack(), seed=1)
+        dev.run_mcmc(theta_host, 3, store=False)
+        out['device_steady_state'] = n_steps / timed(lambda: dev.run_mcmc(None, n_steps, store=False))
+        out['device_engine'] = dev.engine[0]
+        dev.close()
         model(n_walkers=args.walkers, n_steps=2, pos=theta_host, sampler='host', seed=1, prefix=None)
         out['host'] = n_steps / timed(lambda: model(n_walkers=args.walkers, n_steps=n_steps, pos=theta_host,
                                                     sampler='host', seed=1, prefix=None))

@@ -67,6 +67,10 @@ struct mcd_handle {
     // staging for the host-buffer entry points
     double *theta_dev = nullptr, *out_dev = nullptr, *theta_pin = nullptr, *out_pin = nullptr;
     size_t theta_cap = 0, out_cap = 0;
+    // inline host-buffer calls: completion flag in pinned memory, counter of finished walker groups on the device
+    unsigned long long *flag_pin = nullptr;
+    unsigned long long host_seq = 0;
+    unsigned int *done_counter = nullptr;
     double *star_dev = nullptr;    // [n] scratch of the per-star entry point
     cudaStream_t stream = nullptr;
     int sm_count = 0, blocks_per_sm = 1;
@@ -202,6 +206,8 @@ extern "C" void mcd_destroy(mcd_handle *h) {
     cudaFree(h->theta_dev);
     cudaFree(h->out_dev);
     cudaFree(h->star_dev);
+    cudaFree(h->done_counter);
+    cudaFreeHost(h->flag_pin);
     cudaFree(h->xchg_status);
     if (h->order_event) cudaEventDestroy(h->order_event);
     cudaFreeHost(h->theta_pin);
@@ -488,12 +494,12 @@ unsigned long long mcd::next_fuse_nonce(mcd_handle *h) { return ++h->fuse_nonce;
 
 static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double *out_dev, int apply_prior,
                   cudaStream_t stream, bool exchange = false, const FuseParams *fuse = nullptr,
-                  const unsigned long long *epoch_dev = nullptr) {
+                  const unsigned long long *epoch_dev = nullptr, const ThetaBlock *inline_theta = nullptr) {
     if (!h) return fail(-1, "null handle");
     if (n_walkers < 0) return fail(-1, "n_walkers < 0");
     if (n_walkers == 0) return 0;
     if (!fuse) {
-        if (!theta_dev && h->desc.n_theta > 0) return fail(-1, "null theta");
+        if (!theta_dev && !inline_theta && h->desc.n_theta > 0) return fail(-1, "null theta");
         if (!out_dev) return fail(-1, "null out");
     }
     MCD_CUDA(cudaSetDevice(h->device));
@@ -534,7 +540,14 @@ static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double 
             p.xchg_flags[r] = h->xchg_flags[r];
         }
     }
-    MCD_CUDA(launch_lnlike(h->var, p, stream));
+    if (inline_theta) {
+        // theta rides in the kernel arguments, `out_dev` is pinned host memory, completion is flagged there
+        p.theta = nullptr;
+        p.host_flag = h->flag_pin;
+        p.host_seq = h->host_seq;
+        p.done_counter = h->done_counter;
+    }
+    MCD_CUDA(launch_lnlike(h->var, p, stream, inline_theta));
     h->info.last_grid_x = p.n_chunks;
     h->info.last_grid_y = p.n_groups;
     h->info.last_block = kBlock;
@@ -569,6 +582,41 @@ static int ensure_staging(mcd_handle *h, size_t theta_doubles, size_t out_double
     return 0;
 }
 
+// Small calls: ONE kernel launch, nothing else.  theta is copied into the kernel's argument block, the kernel
+// writes the result into pinned host memory and its last walker group stores the call's sequence number into a
+// pinned flag after a system-scope fence; the host spins on that flag (a stream synchronisation costs more than
+// the kernel on these sizes) and falls back to waiting on the stream when the kernel is a long one.
+static int host_call_inline(mcd_handle *h, const double *theta_host, int n_walkers, double *out_host, int apply_prior,
+                            size_t rows, size_t nt) {
+    if (int rc = ensure_staging(h, 1, rows)) return rc;
+    if (!h->flag_pin) {
+        MCD_CUDA(cudaMallocHost(&h->flag_pin, sizeof(unsigned long long)));
+        *h->flag_pin = 0ull;
+        MCD_CUDA(cudaMalloc(&h->done_counter, sizeof(unsigned int)));
+        MCD_CUDA(cudaMemset(h->done_counter, 0, sizeof(unsigned int)));
+    }
+    ThetaBlock block;
+    if (nt) memcpy(block.v, theta_host, sizeof(double) * nt);
+    h->host_seq += 1;
+    if (int rc = launch(h, nullptr, n_walkers, h->out_pin, apply_prior, h->stream, false, nullptr, nullptr, &block)) return rc;
+    volatile unsigned long long *flag = h->flag_pin;
+    const unsigned long long want = h->host_seq;
+    bool seen = false;
+    for (int spin = 0; spin < 200000; ++spin) {            // ~100 us of polling, then block on the stream
+        if (*flag == want) { seen = true; break; }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    if (!seen) {
+        MCD_CUDA(cudaStreamSynchronize(h->stream));
+        if (*flag != want) return fail(-2, "the likelihood kernel finished without publishing its result");
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    memcpy(out_host, h->out_pin, sizeof(double) * rows);
+    return 0;
+}
+
 static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, double *out_host, int apply_prior,
                      int exchange = 0) {
     if (!h) return fail(-1, "null handle");
@@ -579,6 +627,13 @@ static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, dou
     MCD_CUDA(cudaSetDevice(h->device));
     const size_t rows = (size_t)n_walkers * h->n_segments;        // theta is [segments][walkers][theta]
     const size_t nt = rows * h->desc.n_theta;
+    if (!exchange && nt <= (size_t)kThetaInline && rows <= 4096) {
+        static const char *mode = getenv("MCD_HOST_CALL");        // "graph": always take the copy + graph path (A/B)
+        if (!(mode && mode[0] == 'g')) {
+            if (int rc = order_on_stream(h, h->stream)) return rc;
+            return host_call_inline(h, theta_host, n_walkers, out_host, apply_prior, rows, nt);
+        }
+    }
     // one word after theta carries the call's exchange epoch to the device inside the same copy, so that
     // the replayed graph (whose kernel arguments are frozen) sees a fresh tag on every call
     if (int rc = ensure_staging(h, nt + 1, rows)) return rc;

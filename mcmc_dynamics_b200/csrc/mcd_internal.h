@@ -87,6 +87,15 @@ struct ChainParams {
     double *chain_lnp;            // [n_steps][S][W] or nullptr
 };
 
+// Small host-buffer calls (C1 / C2-sized: a few hundred theta values) skip the copy nodes altogether: theta
+// travels INSIDE the kernel arguments (constant bank), the result is written straight into pinned host memory
+// and the finishing CTA raises a flag there that the host spins on -- one launch, no cudaMemcpy, no stream
+// synchronisation.  kThetaInline doubles = 3 KiB of the 32 KiB argument space.
+constexpr int kThetaInline = 384;
+struct ThetaBlock {
+    double v[kThetaInline];
+};
+
 // Kernel argument block of one lnlike / lnprob launch (passed by value, __grid_constant__).
 struct LaunchParams {
     const double *cols[kMaxCols];
@@ -113,6 +122,11 @@ struct LaunchParams {
     double *partials2;        // [n_segments][n_super][n_walkers]
     unsigned int *counters;   // [n_segments][n_groups][n_super + 1], zero between launches
     double *out;              // [n_segments][n_walkers]
+    // inline host-buffer call (theta == nullptr: read the ThetaBlock argument): `out` is pinned host memory,
+    // the last walker group to finish stores host_seq into *host_flag (pinned) after a system-scope fence
+    unsigned long long *host_flag;
+    unsigned long long host_seq;
+    unsigned int *done_counter;   // device: walker groups finished so far, zero between launches
     int slot[MCD_NPARAM];
     double fixed_scaled[MCD_NPARAM];   // fixed value already multiplied by its unit scale
     double scale[MCD_NPARAM];
@@ -140,7 +154,8 @@ bool variant_has_icol(const Variant &v);
 int variant_flops_per_term(const Variant &v);
 
 cudaError_t launch_pack(const PackParams &p, cudaStream_t stream);
-cudaError_t launch_lnlike(const Variant &v, const LaunchParams &p, cudaStream_t stream);
+// `inline_theta` (may be nullptr) is handed to the kernel by value next to `p`
+cudaError_t launch_lnlike(const Variant &v, const LaunchParams &p, cudaStream_t stream, const ThetaBlock *inline_theta = nullptr);
 // per-star lnlike (membership = 0) or membership probability (1) of walker 0 of p.theta into out[N]
 // (always PLAIN arithmetic)
 cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out, int membership, cudaStream_t stream);

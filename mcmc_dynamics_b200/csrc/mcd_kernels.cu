@@ -274,6 +274,9 @@ __device__ __forceinline__ void load_walker(const LaunchParams &P, const double 
         W.cx *= kExpArgScale;
         W.cy *= kExpArgScale;
         W.vb *= kExpArgScale;
+        // opaque to the optimiser: it would otherwise redo these multiplications inside the star loop
+        // (v - v_sys * c as an FMA with the constant rebuilt in uniform registers per pair)
+        asm volatile("" : "+d"(W.vsys), "+d"(W.vb));
         // The fast path keeps the per-star factor as a plain double and renormalises the running product
         // every four stars: it needs the background weight f_back inside a sane range.  A walker with a
         // (nearly) vanishing or non-finite f_back evaluates all its terms in extended range instead.
@@ -623,6 +626,14 @@ __device__ __forceinline__ unsigned int take_ticket(unsigned int *counter) {
 // `buffer` selects one of kXchgSlots buffers, `epoch` is the unique, never repeating tag of this call.
 // Consecutive calls must use different slots (a rank can be one call ahead of a peer that is still
 // reading): host-counted calls alternate 0/1 by epoch parity, the sampler's half-steps alternate 2/3.
+#ifdef MCD_KERNEL_PROFILE
+// [0] sums stored to every peer, [1] flags published, [2] every peer's flag seen (thread 0 of the exchanging CTA)
+__device__ unsigned long long g_xchg_stamp[3];
+#define MCD_XSTAMP(i) do { if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_xchg_stamp[i])); } while (0)
+#else
+#define MCD_XSTAMP(i) do { } while (0)
+#endif
+
 static __device__ __noinline__ double exchange_shard_sums(const LaunchParams &P, double total, int w, int group, bool owner,
                                                    int *timed_out, int buffer, unsigned long long epoch) {
     const int tid = threadIdx.x;
@@ -634,6 +645,7 @@ static __device__ __noinline__ double exchange_shard_sums(const LaunchParams &P,
         __threadfence_system();
     }
     __syncthreads();
+    MCD_XSTAMP(0);
     if (tid < P.xchg_world) {
         // publish: flag[par][my rank][group] on rank `tid` <- epoch (release, system scope)
         unsigned long long *dst = P.xchg_flags[tid] + ((size_t)par * P.xchg_world + P.xchg_rank) * kMaxXchgGroups + group;
@@ -643,6 +655,7 @@ static __device__ __noinline__ double exchange_shard_sums(const LaunchParams &P,
             P.xchg_flags[P.xchg_rank] + ((size_t)par * P.xchg_world + tid) * kMaxXchgGroups + group;
         unsigned long long seen;
         const long long t0 = clock64();
+        MCD_XSTAMP(1);
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
             // a peer that never arrives (crashed rank) must not hang the GPU: give up after ~10 s
@@ -654,6 +667,7 @@ static __device__ __noinline__ double exchange_shard_sums(const LaunchParams &P,
         } while (seen != epoch);
     }
     __syncthreads();
+    MCD_XSTAMP(2);
     if (owner) {
         double s = *timed_out ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
         for (int r = 0; r < P.xchg_world; ++r)
@@ -806,6 +820,20 @@ __device__ __noinline__ void finish_walker_group(const LaunchParams &P, int seg,
         if (owner) accept_proposal(P, seg, w, total);
     } else {
         if (owner) P.out[(size_t)seg * P.n_walkers + w] = total;
+        if (P.host_flag) {
+            // `out` is pinned host memory: order this CTA's results before the flag the host spins on.  The
+            // last walker group (of the last segment) to get here publishes it.
+            if (owner) __threadfence_system();
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned int expected = (unsigned int)(P.n_groups * max(1, P.n_segments));
+                if (atomicAdd(P.done_counter, 1u) == expected - 1u) {
+                    *P.done_counter = 0u;
+                    __threadfence_system();
+                    *reinterpret_cast<volatile unsigned long long *>(P.host_flag) = P.host_seq;
+                }
+            }
+        }
     }
 #ifdef MCD_KERNEL_PROFILE
     if (tid == 0 && stamps && group == P.n_groups - 1) {
@@ -818,6 +846,10 @@ __device__ __noinline__ void finish_walker_group(const LaunchParams &P, int seg,
                launch, gridDim.x, gridDim.y, n_chunks, n_super, blockIdx.x, stamps[0] - t0, stamps[1] - t0, stamps[2] - t0,
                stamps[3] - t0, stamps[4] - t0, stamps[5] - t0, stamps[6] - t0, stamps[7] - t0, stamps[8] - t0,
                n_super > 1 ? stamps[9] - t0 : 0ull, end - t0);
+        if (P.xchg_world > 1)
+            printf("  rank %d exchange: sums stored to peers +%llu ns | flags published +%llu | all %d ranks seen +%llu (waited %llu ns)\n",
+                   P.xchg_rank, g_xchg_stamp[0] - t0, g_xchg_stamp[1] - t0, P.xchg_world, g_xchg_stamp[2] - t0,
+                   g_xchg_stamp[2] - g_xchg_stamp[1]);
         g_kernel_start[launch & 1u] = ~0ull;
         g_kernel_launch = launch + 1u;
     }
@@ -832,7 +864,7 @@ __device__ __noinline__ void finish_walker_group(const LaunchParams &P, int seg,
 // and cost 2.8 % on the headline workload when it was a run-time branch).
 // FUSE: ensemble half-step fused in (proposal drawn in the prologue, acceptance in the finishing CTA).
 template <int ROT, int FREE, int BG, int MATH, bool SEG, bool FUSE>
-__global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : MCD_BG_MIN_BLOCKS)) lnlike_kernel(const __grid_constant__ LaunchParams P) {
+__global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : MCD_BG_MIN_BLOCKS)) lnlike_kernel(const __grid_constant__ LaunchParams P, const __grid_constant__ ThetaBlock T) {
     constexpr int NC = total_columns(ROT, FREE, BG);
     constexpr bool ICOL = has_icol(BG, MATH);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -843,7 +875,8 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
     constexpr bool EXP_TABLE = BG != MCD_BG_NONE && MATH == MCD_MATH_FAST;
     __shared__ double s_exp2[EXP_TABLE ? kMixTableSize : 1];
     if constexpr (EXP_TABLE) fill_exp2_table(s_exp2);
-    const uint32_t exp2_addr = EXP_TABLE ? smem_u32(s_exp2) : 0u;
+    uint32_t exp2_addr = EXP_TABLE ? smem_u32(s_exp2) : 0u;
+    asm volatile("" : "+r"(exp2_addr));      // keep the address in a register (rebuilt per pair from the CTA id otherwise)
 
 #ifdef MCD_KERNEL_PROFILE
     __shared__ unsigned long long s_stamp[12];
@@ -917,7 +950,9 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
             load_walker<ROT, FREE, BG, EXP_TABLE>(P, q, W);
         }
     } else {
-        if (valid) load_walker<ROT, FREE, BG, EXP_TABLE>(P, P.theta + (size_t)(seg * P.n_walkers + w) * P.n_theta, W);
+        // theta in device memory, or inside the kernel arguments (small host-buffer calls)
+        const double *theta = P.theta ? P.theta : T.v;
+        if (valid) load_walker<ROT, FREE, BG, EXP_TABLE>(P, theta + (size_t)(seg * P.n_walkers + w) * P.n_theta, W);
     }
     // a walker outside its box prior is never evaluated by the reference (runner.py:303-306)
     const bool active = valid && (W.prior_ok || !P.apply_prior);
@@ -1084,7 +1119,8 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
     constexpr bool EXP_TABLE = BG != MCD_BG_NONE && MATH == MCD_MATH_FAST;
     __shared__ double s_exp2[EXP_TABLE ? kMixTableSize : 1];          // 2^(j / kMixTableSize), see exp_neg_sq_split
     if constexpr (EXP_TABLE) fill_exp2_table(s_exp2);
-    const uint32_t exp2_addr = EXP_TABLE ? smem_u32(s_exp2) : 0u;
+    uint32_t exp2_addr = EXP_TABLE ? smem_u32(s_exp2) : 0u;
+    asm volatile("" : "+r"(exp2_addr));
     const int tid = threadIdx.x;
     const int G = C.group;
     const int seg = blockIdx.x / G;
@@ -1375,22 +1411,22 @@ __global__ void per_star_kernel(const __grid_constant__ LaunchParams P, double *
     }
 
 template <int ROT, int FREE, int BG, int MATH>
-static cudaError_t launch_one(const LaunchParams &p, cudaStream_t stream) {
+static cudaError_t launch_one(const LaunchParams &p, cudaStream_t stream, const ThetaBlock &t) {
     constexpr int NC = total_columns(ROT, FREE, BG);
     const size_t smem = (size_t)kStages * kMaxTile * (NC * 8 + (has_icol(BG, MATH) ? 4 : 0));
     dim3 grid((unsigned)p.n_chunks * (unsigned)p.n_groups, (unsigned)std::max(1, p.n_segments));
     if (p.seg_begin) {
         // segmented handles (RadialBinsFit) exist for the models without fitted background parameters
         if constexpr (BG == MCD_BG_NONE || BG == MCD_BG_FIXED_PMEMBER) {
-            if (p.fuse.enabled) lnlike_kernel<ROT, FREE, BG, MATH, true, true><<<grid, kBlock, smem, stream>>>(p);
-            else lnlike_kernel<ROT, FREE, BG, MATH, true, false><<<grid, kBlock, smem, stream>>>(p);
+            if (p.fuse.enabled) lnlike_kernel<ROT, FREE, BG, MATH, true, true><<<grid, kBlock, smem, stream>>>(p, t);
+            else lnlike_kernel<ROT, FREE, BG, MATH, true, false><<<grid, kBlock, smem, stream>>>(p, t);
         } else {
             return cudaErrorInvalidValue;
         }
     } else if (p.fuse.enabled) {
-        lnlike_kernel<ROT, FREE, BG, MATH, false, true><<<grid, kBlock, smem, stream>>>(p);
+        lnlike_kernel<ROT, FREE, BG, MATH, false, true><<<grid, kBlock, smem, stream>>>(p, t);
     } else {
-        lnlike_kernel<ROT, FREE, BG, MATH, false, false><<<grid, kBlock, smem, stream>>>(p);
+        lnlike_kernel<ROT, FREE, BG, MATH, false, false><<<grid, kBlock, smem, stream>>>(p, t);
     }
     return cudaGetLastError();
 }
@@ -1423,16 +1459,16 @@ static cudaError_t chain_one(const LaunchParams &p, const ChainParams &c, size_t
 }
 
 #if MCD_TU_PART == 1
-cudaError_t launch_lnlike_fast(const Variant &v, const LaunchParams &p, cudaStream_t stream) {
-    MCD_DISPATCH_GEO(MCD_MATH_FAST, launch_one, p, stream)
+cudaError_t launch_lnlike_fast(const Variant &v, const LaunchParams &p, cudaStream_t stream, const ThetaBlock &t) {
+    MCD_DISPATCH_GEO(MCD_MATH_FAST, launch_one, p, stream, t)
 }
 int occupancy_fast(const Variant &v) { MCD_DISPATCH_GEO(MCD_MATH_FAST, occupancy_one) }
 cudaError_t launch_chain_fast(const Variant &v, const LaunchParams &p, const ChainParams &c, size_t smem, cudaStream_t stream) {
     MCD_DISPATCH_GEO(MCD_MATH_FAST, chain_one, p, c, smem, stream)
 }
 #else
-cudaError_t launch_lnlike_plain(const Variant &v, const LaunchParams &p, cudaStream_t stream) {
-    MCD_DISPATCH_GEO(MCD_MATH_PLAIN, launch_one, p, stream)
+cudaError_t launch_lnlike_plain(const Variant &v, const LaunchParams &p, cudaStream_t stream, const ThetaBlock &t) {
+    MCD_DISPATCH_GEO(MCD_MATH_PLAIN, launch_one, p, stream, t)
 }
 int occupancy_plain(const Variant &v) { MCD_DISPATCH_GEO(MCD_MATH_PLAIN, occupancy_one) }
 cudaError_t launch_chain_plain(const Variant &v, const LaunchParams &p, const ChainParams &c, size_t smem, cudaStream_t stream) {
@@ -1455,15 +1491,17 @@ cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out
 #endif  // MCD_TU_PART != 0
 
 #if MCD_TU_PART == 0
-cudaError_t launch_lnlike_fast(const Variant &v, const LaunchParams &p, cudaStream_t stream);
-cudaError_t launch_lnlike_plain(const Variant &v, const LaunchParams &p, cudaStream_t stream);
+cudaError_t launch_lnlike_fast(const Variant &v, const LaunchParams &p, cudaStream_t stream, const ThetaBlock &t);
+cudaError_t launch_lnlike_plain(const Variant &v, const LaunchParams &p, cudaStream_t stream, const ThetaBlock &t);
 int occupancy_fast(const Variant &v);
 int occupancy_plain(const Variant &v);
 cudaError_t launch_chain_fast(const Variant &v, const LaunchParams &p, const ChainParams &c, size_t smem, cudaStream_t stream);
 cudaError_t launch_chain_plain(const Variant &v, const LaunchParams &p, const ChainParams &c, size_t smem, cudaStream_t stream);
 
-cudaError_t launch_lnlike(const Variant &v, const LaunchParams &p, cudaStream_t stream) {
-    return v.math_mode == MCD_MATH_PLAIN ? launch_lnlike_plain(v, p, stream) : launch_lnlike_fast(v, p, stream);
+cudaError_t launch_lnlike(const Variant &v, const LaunchParams &p, cudaStream_t stream, const ThetaBlock *inline_theta) {
+    static const ThetaBlock kNoTheta{};
+    const ThetaBlock &t = inline_theta ? *inline_theta : kNoTheta;
+    return v.math_mode == MCD_MATH_PLAIN ? launch_lnlike_plain(v, p, stream, t) : launch_lnlike_fast(v, p, stream, t);
 }
 
 int lnlike_blocks_per_sm(const Variant &v) {

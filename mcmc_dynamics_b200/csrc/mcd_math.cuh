@@ -42,8 +42,8 @@ __device__ __forceinline__ double rsqrt_seed(double x) {
 //                            MUFU seeds); 2 / 3 FP64 instructions (+1 integer op)
 //   3 (cubic step)         : 2.2e-16 / 2.7e-16; 3 / 5 FP64 instructions
 // The tolerance of the path is 1e-9 relative on lnprob (BASELINE.json north_star); a per-term relative error
-// of 1.3e-12 ends up as < 5e-13 relative on lnprob whatever the catalogue size (it is relative, and of one
-// sign: tests/test_gpu_parity.py measures 1e-13..4e-13 against the oracle), three orders inside it.  On the
+// of 1.3e-12 ends up far below that on lnprob whatever the catalogue size (it is relative; measured against the
+// oracle on every BASELINE configuration: 0.6e-14 .. 2.3e-14, profiles/r02_configs.md), five orders inside it.  On the
 // headline workload the quadratic step is worth 8.3 % (7.395 -> 6.827 ms per 512-walker call over 1e7 stars,
 // profiles/r02_ab_runs.md); round 1 measured 2.5 % on an earlier, less FP64-bound loop and kept the cubic
 // step.  -DMCD_NEWTON=3 restores it (A/B builds: tools/build_variant.py).
@@ -299,6 +299,9 @@ constexpr int kMixTableBits = 6;
 #endif
 constexpr int kMixTableSize = 1 << kMixTableBits;
 
+// (ln2 / 256)^k / k!, k = 1..3
+__constant__ double kExp2LeanCoef[3] = {0.0027076061740622863, 3.6655655969101062e-06, 3.3083026805413713e-09};
+
 // returns the mantissa in [0.99, 2.01); N = table-units exponent: exp(-z^2/2) = mant * 2^(N >> kMixTableBits)
 // `table` is the 32-bit shared-memory address of 2^(j / kMixTableSize), j = 0 .. kMixTableSize - 1 (a generic
 // pointer costs four uniform-datapath instructions per load to rebuild the shared window base).
@@ -313,8 +316,8 @@ __device__ __forceinline__ double exp_neg_sq_split(double u, uint32_t table, int
     N = __double2loint(shifted);
     const double nf = shifted - kMagic;
     const double r = fma(-s, s, -nf);
-    double p = fma(3.3083026805413713e-09, r, 3.6655655969101062e-06);
-    p = fma(p, r, 0.0027076061740622863);
+    double p = fma(kExp2LeanCoef[2], r, kExp2LeanCoef[1]);    // constant-bank operands: no register, no move
+    p = fma(p, r, kExp2LeanCoef[0]);
 #else
     const double shifted = fma(-uc, uc, kMagic);
     N = __double2loint(shifted);

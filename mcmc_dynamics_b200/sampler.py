@@ -130,7 +130,8 @@ def make_host_sampler(nwalkers, ndim, log_prob_fn, seed=None):
     """emcee in vectorised mode when it is installed, else :class:`HostEnsembleSampler`."""
     try:
         import emcee
-    except ImportError:
+        emcee.moves.StretchMove          # a real emcee 3.x, not an import-only stub
+    except (ImportError, AttributeError):
         return HostEnsembleSampler(nwalkers, ndim, log_prob_fn, seed=seed)
     sampler = emcee.EnsembleSampler(nwalkers, ndim, log_prob_fn, vectorize=True)
     if seed is not None:

@@ -20,9 +20,19 @@ ROOT = os.path.dirname(HERE)
 
 
 def binding_module():
-    for path in (os.path.join(HERE, 'golden', 'ref_shims'), os.path.join(ROOT, 'tools')):
-        if path not in sys.path:
-            sys.path.insert(0, path)
+    """tools/reference_binding.py with ``astropy.units`` resolved to the stand-in of tests/golden/ref_shims.  The
+    shim directory is taken off ``sys.path`` again at once: it also holds import-only stubs of emcee, pathos,
+    ... that must not shadow anything for the rest of the test session."""
+    tools = os.path.join(ROOT, 'tools')
+    if tools not in sys.path:
+        sys.path.insert(0, tools)
+    if 'astropy.units' not in sys.modules:
+        shims = os.path.join(HERE, 'golden', 'ref_shims')
+        sys.path.insert(0, shims)
+        try:
+            import astropy.units  # noqa: F401
+        finally:
+            sys.path.remove(shims)
     import reference_binding
     return reference_binding
 

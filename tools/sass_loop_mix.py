@@ -48,23 +48,37 @@ def function_instructions(lines, key):
 
 
 def hot_path(body):
-    """The instructions the loop executes when no rare branch is taken: predicated forward branches inside the
-    body (the mixture kernels' jump to the extended-range code) are counted and not followed, unconditional
-    forward branches are followed (they skip that code).  Predicated non-branch instructions occupy an issue
-    slot either way and are counted."""
+    """The instructions the loop executes when no rare branch is taken = the cheapest path from the loop head to
+    the backward branch, where every instruction costs 1 and an out-of-line CALL (the mixture kernels'
+    extended-range evaluation) costs 1000.  Predicated forward branches may or may not be taken, unconditional
+    ones are; predicated non-branch instructions occupy an issue slot either way and are counted."""
+    n = len(body)
     index = {a: i for i, (a, _) in enumerate(body)}
-    out, i = [], 0
-    while i < len(body):
+    cost = [float('inf')] * (n + 1)
+    prev = [None] * (n + 1)
+    cost[0] = 0.0
+    for i in range(n):                      # forward edges only: a topological order is the address order
+        if cost[i] == float('inf'):
+            continue
         addr, text = body[i]
-        out.append(body[i])
+        step = 1000.0 if re.search(r'\bCALL\b', text) else 1.0
         m = re.search(r'\bBRA\b.*?(0x[0-9a-f]+)', text)
-        if m and not re.match(r'^@', text):
-            target = int(m.group(1), 16)
-            if target > addr and target in index:
-                i = index[target]
-                continue
-        i += 1
-    return out
+        targets = []
+        if m and int(m.group(1), 16) > addr and int(m.group(1), 16) in index:
+            targets.append(index[int(m.group(1), 16)])
+            if re.match(r'^@', text):
+                targets.append(i + 1)
+        else:
+            targets.append(i + 1)
+        for t in targets:
+            if cost[i] + step < cost[t]:
+                cost[t] = cost[i] + step
+                prev[t] = i
+    path, i = [], n
+    while prev[i] is not None:
+        i = prev[i]
+        path.append(body[i])
+    return path[::-1]
 
 
 def loop_mix(lines, key):
