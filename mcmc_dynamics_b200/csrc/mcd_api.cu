@@ -67,6 +67,14 @@ struct mcd_handle {
     // staging for the host-buffer entry points
     double *theta_dev = nullptr, *out_dev = nullptr, *theta_pin = nullptr, *out_pin = nullptr;
     size_t theta_cap = 0, out_cap = 0;
+    // launch geometry of the most recent walker counts (the search costs ~3 us: too much to redo on every small call)
+    struct Geometry {
+        int n_walkers = -1;
+        unsigned long long generation = 0;
+        int wl, slices, n_groups, tile, n_tiles, tiles_per_chunk, n_chunks, super, n_super;
+    };
+    Geometry geometry[4];
+    int geometry_next = 0;
     // inline host-buffer calls: completion flag in pinned memory, counter of finished walker groups on the device
     unsigned long long *flag_pin = nullptr;
     unsigned long long host_seq = 0;
@@ -324,7 +332,28 @@ extern "C" int mcd_get_info(const mcd_handle *h, mcd_info *info) {
 // ------------------------------------------------------------------------------------------
 // launch geometry
 // ------------------------------------------------------------------------------------------
-static void choose_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p) {
+static void search_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p);
+
+// cached per (walker count, pack generation); MCD_GEOMETRY (experiments) always searches
+static void choose_geometry(mcd_handle *h, int n_walkers, LaunchParams &p) {
+    if (!getenv("MCD_GEOMETRY")) {
+        for (const auto &g : h->geometry)
+            if (g.n_walkers == n_walkers && g.generation == h->generation) {
+                p.wl = g.wl; p.slices = g.slices; p.n_groups = g.n_groups; p.tile = g.tile; p.n_tiles = g.n_tiles;
+                p.tiles_per_chunk = g.tiles_per_chunk; p.n_chunks = g.n_chunks; p.super = g.super; p.n_super = g.n_super;
+                return;
+            }
+    }
+    search_geometry(h, n_walkers, p);
+    if (getenv("MCD_GEOMETRY")) return;
+    mcd_handle::Geometry &g = h->geometry[h->geometry_next++ % 4];
+    g.n_walkers = n_walkers;
+    g.wl = p.wl; g.slices = p.slices; g.n_groups = p.n_groups; g.tile = p.tile; g.n_tiles = p.n_tiles;
+    g.tiles_per_chunk = p.tiles_per_chunk; g.n_chunks = p.n_chunks; g.super = p.super; g.n_super = p.n_super;
+    g.generation = h->generation;
+}
+
+static void search_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p) {
     // walkers per CTA: minimise groups / slices (CTA time ~ stars / slices, CTAs ~ groups)
     int best_g = 1, best_wl = std::max(1, std::min(n_walkers, kBlock)), best_s = 1;
     double best_cost = 1e300;
@@ -628,7 +657,7 @@ static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, dou
     const size_t rows = (size_t)n_walkers * h->n_segments;        // theta is [segments][walkers][theta]
     const size_t nt = rows * h->desc.n_theta;
     if (!exchange && nt <= (size_t)kThetaInline && rows <= 4096) {
-        static const char *mode = getenv("MCD_HOST_CALL");        // "graph": always take the copy + graph path (A/B)
+        const char *mode = getenv("MCD_HOST_CALL");               // "graph": always take the copy + graph path (A/B, tests)
         if (!(mode && mode[0] == 'g')) {
             if (int rc = order_on_stream(h, h->stream)) return rc;
             return host_call_inline(h, theta_host, n_walkers, out_host, apply_prior, rows, nt);
