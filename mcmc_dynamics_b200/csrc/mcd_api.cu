@@ -95,6 +95,8 @@ struct mcd_handle {
     unsigned long long fuse_nonce = 0;          // ensembles created on this handle so far (exchange tag of their half-steps)
     double *xchg_data[kMaxRanks] = {};
     unsigned long long *xchg_flags[kMaxRanks] = {};
+    unsigned long long *xchg_words[kMaxRanks] = {};
+    int xchg_tagged_mode = 1;                   // MCD_XCHG=flags selects the flag + fence protocol (A/B)
     int *xchg_status = nullptr;                 // device word: set to 1 by a kernel whose wait for a peer timed out
     // Everything a captured graph bakes in (scratch pointers, packed columns, routing, exchange buffers)
     // belongs to one generation; whoever replays a graph compares the generation it captured at.
@@ -285,6 +287,15 @@ extern "C" int mcd_pack_create(const mcd_pack_desc *desc, mcd_handle **out) {
         h->sm_count = prop.multiProcessorCount;
         if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(-2, "cudaStreamCreate failed"); break; }
         if (cudaEventCreateWithFlags(&h->order_event, cudaEventDisableTiming) != cudaSuccess) { rc = fail(-2, "cudaEventCreate failed"); break; }
+        {   // keep what the stream-ordered allocations (ensemble state, chains, background scratch) give back in the
+            // device's pool instead of returning it to the driver at every synchronisation
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+                unsigned long long keep = 1ull << 30;
+                (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            (void)cudaGetLastError();
+        }
         h->n = desc->n_stars;
         h->n_alloc = ((h->n + kMaxTile - 1) / kMaxTile + 1) * kMaxTile;   // full bulk copies at the tail
         h->max_segment = h->n;
@@ -564,9 +575,11 @@ static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double 
         p.xchg_epoch = (fuse || epoch_dev) ? 0 : ++h->xchg_epoch;
         p.xchg_epoch_ptr = epoch_dev;
         p.xchg_status = h->xchg_status;
+        p.xchg_tagged_mode = h->xchg_tagged_mode;
         for (int r = 0; r < h->xchg_world; ++r) {
             p.xchg_data[r] = h->xchg_data[r];
             p.xchg_flags[r] = h->xchg_flags[r];
+            p.xchg_words[r] = h->xchg_words[r];
         }
     }
     if (inline_theta) {
@@ -878,7 +891,8 @@ static size_t exchange_flag_bytes(int world) { return sizeof(unsigned long long)
 
 extern "C" int mcd_exchange_bytes(int32_t world, int32_t max_walkers, int64_t *bytes_out) {
     if (world < 2 || world > kMaxRanks || max_walkers < 1 || !bytes_out) return fail(-1, "bad exchange geometry");
-    *bytes_out = (int64_t)(exchange_flag_bytes(world) + sizeof(double) * kXchgSlots * world * (size_t)max_walkers);
+    // flags | plain sums (flag protocol) | tagged words, two per sum (tagged protocol)
+    *bytes_out = (int64_t)(exchange_flag_bytes(world) + 3 * sizeof(double) * kXchgSlots * world * (size_t)max_walkers);
     return 0;
 }
 
@@ -902,7 +916,11 @@ extern "C" int mcd_exchange_attach(mcd_handle *h, int32_t rank, int32_t world, c
         char *base = reinterpret_cast<char *>(static_cast<uintptr_t>(peer_buffers[r]));
         h->xchg_flags[r] = reinterpret_cast<unsigned long long *>(base);
         h->xchg_data[r] = reinterpret_cast<double *>(base + exchange_flag_bytes(world));
+        h->xchg_words[r] = reinterpret_cast<unsigned long long *>(
+            base + exchange_flag_bytes(world) + sizeof(double) * kXchgSlots * world * (size_t)max_walkers);
     }
+    const char *mode = getenv("MCD_XCHG");
+    h->xchg_tagged_mode = (mode && mode[0] == 'f') ? 0 : 1;
     return 0;
 }
 

@@ -141,6 +141,10 @@ struct LaunchParams {
     int *xchg_status;                              // set to 1 when the wait for a peer ran into its time limit
     double *xchg_data[kMaxRanks];                  // rank p's data region  [kXchgSlots][world][capacity]
     unsigned long long *xchg_flags[kMaxRanks];     // rank p's flag region  [kXchgSlots][world][kMaxXchgGroups]
+    // tagged exchange (xchg_tagged_mode = 1): every sum travels as two 8-byte words, each carrying half of the
+    // double and the call's 32-bit tag, so a word validates itself -- no flag, no system fence, no barrier
+    unsigned long long *xchg_words[kMaxRanks];     // rank p's tagged region [kXchgSlots][world][capacity][2]
+    int xchg_tagged_mode;
     FuseParams fuse;
 };
 

@@ -43,7 +43,7 @@
 #define MCD_BG_MIN_BLOCKS 2   // the same two knobs for the background-mixture variants
 #endif
 #ifndef MCD_BG_PAIRS
-#define MCD_BG_PAIRS 1
+#define MCD_BG_PAIRS 2        // round 2 (lean arithmetic): C3 45.1 -> 43.1 us, mixgb 4286 -> 4159 us, mix +0.9 % (r02_ab_runs.md)
 #endif
 
 // This file is compiled three times (see __graft_entry__.py), so that the template instantiations
@@ -677,6 +677,41 @@ static __device__ __noinline__ double exchange_shard_sums(const LaunchParams &P,
     return total;
 }
 
+// The same exchange with self-validating words (the LL scheme of NCCL, as the resident chain kernel uses inside
+// one GPU): the owner of walker w stores {low half | tag, high half | tag} into every rank's slot with one
+// 16-byte store, then polls its OWN rank's slots of all ranks until both tags match and adds in rank order.
+// Nothing orders the data before a separate flag, so there is no __threadfence_system (measured 4 us on two
+// GPUs: profiles/r02_exchange_timeline.md), no block barrier and no second round trip.  `tag` must differ
+// from the tag the slot carried two calls earlier and never be 0 (the buffer starts zero-filled).
+static __device__ __noinline__ double exchange_shard_sums_tagged(const LaunchParams &P, double total, int w, bool owner,
+                                                          int buffer, unsigned int tag) {
+    if (!owner) return total;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(total);
+    const unsigned long long t = (unsigned long long)tag << 32;
+    const unsigned long long lo = (bits & 0xffffffffULL) | t, hi = (bits >> 32) | t;
+    const size_t mine = (((size_t)buffer * P.xchg_world + P.xchg_rank) * P.xchg_capacity + w) * 2;
+    for (int peer = 0; peer < P.xchg_world; ++peer)
+        asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(P.xchg_words[peer] + mine), "l"(lo), "l"(hi) : "memory");
+    double s = 0.0;
+    const long long t0 = clock64();
+    for (int r = 0; r < P.xchg_world; ++r) {
+        const unsigned long long *src = P.xchg_words[P.xchg_rank] + (((size_t)buffer * P.xchg_world + r) * P.xchg_capacity + w) * 2;
+        unsigned long long a, b;
+        unsigned int polls = 0u;
+        while (true) {
+            asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
+            if ((unsigned int)(a >> 32) == tag && (unsigned int)(b >> 32) == tag) break;
+            // a peer that never arrives (crashed rank) must not hang the GPU: give up after ~10 s
+            if ((++polls & 1023u) == 0u && clock64() - t0 > 20000000000LL) {
+                if (P.xchg_status) *P.xchg_status = 1;
+                return __longlong_as_double(0x7ff8000000000000LL);
+            }
+        }
+        s += __longlong_as_double((long long)((a & 0xffffffffULL) | (b << 32)));     // rank order: bit-identical everywhere
+    }
+    return s;
+}
+
 // acceptance of the fused half-step: (P-1) ln z + lnp(q) - lnp(s) > ln u'; NaN never accepts
 static __device__ __noinline__ void accept_proposal(const LaunchParams &P, int seg, int k, double lnp_new) {
     const FuseParams &F = P.fuse;
@@ -811,7 +846,15 @@ __device__ __noinline__ void finish_walker_group(const LaunchParams &P, int seg,
             slot = 2 + P.fuse.half;
             epoch = P.fuse.tag_base | (2ull * P.fuse.step[0] + (unsigned long long)P.fuse.half);
         }
-        total = exchange_shard_sums(P, total, w, group, owner, s_last, slot, epoch);
+        if (P.xchg_tagged_mode) {
+            // 32-bit tag: host-counted calls use the epoch itself; half-steps mix the ensemble's nonce (bits
+            // 36.. of tag_base) into the top byte, so consecutive users of a slot never share a tag
+            unsigned int tag = (unsigned int)epoch;
+            if constexpr (FUSE) tag = ((unsigned int)((P.fuse.tag_base >> 36) % 255ull + 1ull) << 24) ^ ((unsigned int)epoch & 0xffffffu);
+            total = exchange_shard_sums_tagged(P, total, w, owner, slot, tag == 0u ? 1u : tag);
+        } else {
+            total = exchange_shard_sums(P, total, w, group, owner, s_last, slot, epoch);
+        }
     }
     if constexpr (FUSE) {
         // accept or reject in place.  Safe without further synchronisation: the positions of the active

@@ -14,7 +14,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <new>
 
 #include "mcd_internal.h"
@@ -93,6 +95,7 @@ struct mcd_ensemble {
     bool graph_stores = false;
     size_t chain_cap_steps = 0;
     bool have_state = false;
+    void *state = nullptr;                     // one stream-ordered allocation holding every array of E but the chain
     unsigned long long graph_generation = 0;   // handle_generation() the graph was captured at
     unsigned long long tag_base = 0;           // exchange tag of this ensemble's fused half-steps
     unsigned int steps_done = 0;     // host mirror of E.step[0]
@@ -104,15 +107,11 @@ static void free_ensemble(mcd_ensemble *e) {
     cudaSetDevice(e->device);
     if (e->exec) cudaGraphExecDestroy(e->exec);
     if (e->graph) cudaGraphDestroy(e->graph);
-    cudaFree(e->E.pos);
-    cudaFree(e->E.lnp);
-    cudaFree(e->E.lnp_q);
-    cudaFree(e->E.perm);
-    cudaFree(e->E.n_accepted);
-    cudaFree(e->E.step);
-    cudaFree(e->E.chain);
-    cudaFree(e->E.chain_lnp);
     if (e->stream) {
+        // stream-ordered frees into the device's memory pool: cudaFree synchronises the whole device and was
+        // measured at 30-130 ms per call in a process that also holds a large catalogue (profiles/r02_summary.md)
+        if (e->state) cudaFreeAsync(e->state, e->stream);
+        if (e->E.chain) cudaFreeAsync(e->E.chain, e->stream);
         cudaStreamSynchronize(e->stream);
         forget_stream(e->h, e->stream);
         cudaStreamDestroy(e->stream);
@@ -156,17 +155,29 @@ extern "C" int mcd_ensemble_create(mcd_handle *h, int32_t n_walkers, uint64_t se
     const size_t S = (size_t)E.n_segments;
     bool ok = cudaSetDevice(e->device) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaMalloc(&E.pos, sizeof(double) * S * n_walkers * P) == cudaSuccess;
-    ok = ok && cudaMalloc(&E.lnp, sizeof(double) * S * n_walkers) == cudaSuccess;
-    ok = ok && cudaMalloc(&E.lnp_q, sizeof(double) * S * E.n0) == cudaSuccess;
-    ok = ok && cudaMalloc(&E.perm, sizeof(int) * S * n_walkers) == cudaSuccess;
-    ok = ok && cudaMalloc(&E.n_accepted, sizeof(long long) * S * n_walkers) == cudaSuccess;
-    ok = ok && cudaMalloc(&E.step, sizeof(unsigned int) * 2) == cudaSuccess;
-    ok = ok && cudaMemset(E.n_accepted, 0, sizeof(long long) * S * n_walkers) == cudaSuccess;
-    ok = ok && cudaMemset(E.step, 0, sizeof(unsigned int) * 2) == cudaSuccess;
+    // one allocation from the device's memory pool (cudaMallocAsync: no device-wide synchronisation), carved up
+    // at 256-byte boundaries
+    auto round = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_pos = round(sizeof(double) * S * n_walkers * P), b_lnp = round(sizeof(double) * S * n_walkers);
+    const size_t b_q = round(sizeof(double) * S * E.n0), b_perm = round(sizeof(int) * S * n_walkers);
+    const size_t b_acc = round(sizeof(long long) * S * n_walkers), b_step = round(sizeof(unsigned int) * 2);
+    const size_t total = b_pos + b_lnp + b_q + b_perm + b_acc + b_step;
+    ok = ok && cudaMallocAsync(&e->state, total, e->stream) == cudaSuccess;
+    if (ok) {
+        char *base = static_cast<char *>(e->state);
+        E.pos = reinterpret_cast<double *>(base);
+        E.lnp = reinterpret_cast<double *>(base + b_pos);
+        E.lnp_q = reinterpret_cast<double *>(base + b_pos + b_lnp);
+        E.perm = reinterpret_cast<int *>(base + b_pos + b_lnp + b_q);
+        E.n_accepted = reinterpret_cast<long long *>(base + b_pos + b_lnp + b_q + b_perm);
+        E.step = reinterpret_cast<unsigned int *>(base + b_pos + b_lnp + b_q + b_perm + b_acc);
+        ok = cudaMemsetAsync(E.n_accepted, 0, b_acc + b_step, e->stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(e->stream) == cudaSuccess;
+    }
     if (!ok) {
+        const cudaError_t err = cudaGetLastError();
         free_ensemble(e);
-        return set_error(-2, "allocating the ensemble state failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return set_error(-2, "allocating the ensemble state failed: %s", cudaGetErrorString(err));
     }
     *out = e;
     return 0;
@@ -242,9 +253,19 @@ static int build_graph(mcd_ensemble *e) {
     return 0;
 }
 
+// MCD_TIMING=1: wall-clock of the phases of a run on stderr (diagnostics)
+static double now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e3 * ts.tv_sec + 1e-6 * ts.tv_nsec;
+}
+
 extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_host, double *lnprob_host,
                                 int64_t *n_accepted_host) {
     if (!e || n_steps < 0) return set_error(-1, "bad argument");
+    const char *timing_env = getenv("MCD_TIMING");
+    const bool timing = timing_env && timing_env[0] == '1';
+    const double t_enter = now_ms();
     if (!e->have_state) return set_error(-1, "mcd_ensemble_set_state has not been called");
     ENS_CUDA(cudaSetDevice(e->device));
     Ensemble &E = e->E;
@@ -255,12 +276,12 @@ extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_
     // chain chunks of at most 256 MiB on the device
     size_t chunk = std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, n_steps), ((size_t)256 << 20) / (per_step * 8)));
     if (store && chunk > e->chain_cap_steps) {
-        cudaFree(E.chain);
-        cudaFree(E.chain_lnp);
+        // chain [chunk][rows][P] followed by lnprob [chunk][rows], one stream-ordered allocation
+        if (E.chain) ENS_CUDA(cudaFreeAsync(E.chain, e->stream));
         E.chain = E.chain_lnp = nullptr;
         e->chain_cap_steps = 0;
-        ENS_CUDA(cudaMalloc(&E.chain, sizeof(double) * chunk * per_step));
-        ENS_CUDA(cudaMalloc(&E.chain_lnp, sizeof(double) * chunk * rows));
+        ENS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&E.chain), sizeof(double) * chunk * (per_step + rows), e->stream));
+        E.chain_lnp = E.chain + chunk * per_step;
         e->chain_cap_steps = chunk;
         if (e->exec) {   // pointers baked into the graph changed
             cudaGraphExecDestroy(e->exec);
@@ -316,6 +337,7 @@ extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_
     if (!store) E.chain = E.chain_lnp = nullptr;
     // the graph bakes in the handle's scratch buffers, packed columns, routing and exchange pointers: a
     // larger lnprob call, a re-pack or an exchange attach since the capture makes it stale
+    const double t_graph = now_ms();
     if (!e->exec || e->graph_stores != store || e->graph_generation != handle_generation(e->h)) {
         const int rc = build_graph(e);
         if (rc) {
@@ -325,6 +347,8 @@ extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_
         }
         e->graph_stores = store;
     }
+    const double t_loop = now_ms();
+    double t_queued = t_loop;
     int rc = order_on_stream(e->h, e->stream);
     for (int done = 0; done < n_steps && rc == 0;) {
         const int todo = (int)std::min<size_t>(chunk, (size_t)(n_steps - done));
@@ -332,6 +356,7 @@ extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_
         for (int s = 0; s < todo; ++s)
             if (cudaGraphLaunch(e->exec, e->stream) != cudaSuccess) { rc = -2; break; }
         if (rc) break;
+        t_queued = now_ms();
         if (chain_host && cudaMemcpyAsync(chain_host + (size_t)done * per_step, E.chain, sizeof(double) * todo * per_step,
                                           cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) rc = -2;
         if (lnprob_host && cudaMemcpyAsync(lnprob_host + (size_t)done * rows, E.chain_lnp, sizeof(double) * todo * rows,
@@ -347,6 +372,10 @@ extern "C" int mcd_ensemble_run(mcd_ensemble *e, int32_t n_steps, double *chain_
     }
     if (rc == 0 && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = -2;
     if (rc == 0) rc = exchange_status(e->h, e->stream);
+    if (timing)
+        fprintf(stderr, "mcd_ensemble_run(%d steps, store %d): set-up %.2f ms | graph (re)build %.2f ms | %d graph launches queued "
+                        "in %.2f ms | until done %.2f ms | total %.2f ms\n", n_steps, (int)store, t_graph - t_enter, t_loop - t_graph,
+                n_steps, t_queued - t_loop, now_ms() - t_queued, now_ms() - t_enter);
     return rc;
 }
 
