@@ -389,18 +389,18 @@ static void search_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p)
     // loaded SM needs for its CTAs one after the other.  Cost of a candidate, in star iterations per thread:
     //   cta   = tiles_per_chunk * (tile / slices + 3) + overhead      (3: barrier + stage hand-over per tile;
     //           overhead: walker set-up and reduction, ~24 iterations' worth of pipe time)
-    //   load  = CTAs on the most loaded SM
-    //           - grid fits one wave of resident CTAs: the hardware deals them out round-robin and nothing
-    //             rebalances, so load = ceil(CTAs / SMs); 5 % is added for the differences between SMs that
-    //             only a multi-wave grid evens out (measured on the 1e7-star workload: 8 waves beat 1), and
-    //             25 % when an SM holds a single CTA (8 warps do not keep the FP64 pipe busy: measured 18 %)
-    //           - several waves: CTAs / SMs on average, plus a third of a CTA for the ragged end
-    //   cost  = load * cta
-    // Fitted to a (tile, tiles_per_chunk) sweep of BASELINE configs C3 and C4 (profiles/r02_geometry.md):
-    // measured time / cost is constant within +-8 % over 24 geometries, where the round-1 model (whole waves
-    // of SMs x CTAs-per-SM, blind to a partly filled wave) was off by up to 35 %.
+    //   load  = ceil(CTAs / SMs): CTAs on the most loaded SM.  Equal-sized CTAs are dealt out evenly, so a grid
+    //           of 8.26 CTAs per SM costs 9 (measured: +9 %), whether or not it fits one wave of resident CTAs.
+    //           x 1.25 when an SM holds a single CTA: 8 warps do not keep the FP64 pipe busy (measured 18 %);
+    //           x 1.03 per resident slot left empty otherwise
+    //   cost  = load * cta + min(2 % of that, cta / 3): SMs differ by a per cent or two in speed; many small
+    //           CTAs even that out to within a fraction of one CTA, few large ones cannot (round 1 measured
+    //           8 waves 2.3 % ahead of 1 on the 1e7-star workload)
+    // Fitted to (tile, tiles_per_chunk) sweeps of BASELINE configs C3, C4 and of one of eight C5 shards
+    // (profiles/r02_ab_runs.md): measured time / cost is constant within +-8 % over 24 mid-size geometries and
+    // within 2 % over the 7 shard-sized ones, where the round-1 model (whole waves of SMs x CTAs-per-SM, blind
+    // to a partly filled wave) was off by up to 35 % and 9 %.
     const int sms = std::max(1, h->sm_count);
-    const int resident = sms * std::max(1, h->blocks_per_sm);
     const int problems = std::max(1, p.n_groups * h->n_segments);      // CTAs per star chunk
     const double overhead = 24.0;
     const long long n = std::max<long long>(h->max_segment, 1);     // grid sized for the largest segment
@@ -418,9 +418,12 @@ static void search_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p)
             const long long ctas = chunks * problems;
             const double cta = (double)tpc * ((double)tile / p.slices + 3.0) + overhead;
             const long long per_sm = (ctas + sms - 1) / sms;
-            const double load = ctas <= resident ? (per_sm == 1 ? 1.25 : 1.05) * (double)per_sm
-                                                 : (double)ctas / sms + 0.3;
-            const double cost = load * cta;
+            // fewer CTAs on an SM than fit: less latency hiding (1 CTA: measured; 2 of 3: 3 %, an estimate that only
+            // breaks ties between otherwise equal geometries)
+            const int room = std::max(1, h->blocks_per_sm);
+            const double thin = per_sm == 1 ? 1.25 : (per_sm < room ? 1.0 + 0.03 * (double)(room - per_sm) : 1.0);
+            const double base = thin * (double)per_sm * cta;
+            const double cost = base + std::min(0.02 * base, cta / 3.0);
             if (cost < best * (1.0 - 1e-12)) {
                 best = cost;
                 best_tile = tile;

@@ -391,10 +391,19 @@ __device__ __forceinline__ void fill_exp2_table(double *table) {
 // ------------------------------------------------------------------------------------------
 // one (walker, star) term
 // ------------------------------------------------------------------------------------------
-// ASSUME_FAST (FAST mixtures with a per-star flag): the caller has checked that this star takes the fast path
-template <int ROT, int FREE, int BG, int MATH, bool ASSUME_FAST = false>
+// Fast-path value of one mixture term: nothing is applied to the accumulators yet, so that the caller can run
+// several stars through one basic block (independent dependency chains for the scheduler) and decide afterwards.
+struct MixFast {
+    double factor;      // wm y exp(-z^2/2) + background term
+    double den;         // density + f_back (variants that normalise by it)
+    int slow;           // fitted background: both components tiny, the term needs the extended-range path
+};
+
+// FAST_VALUE (FAST mixtures): the caller has checked that this star may take the fast path; its value goes to
+// *fast and `A` is left alone.  Otherwise the term is evaluated and applied to `A` (fast or slow path as needed).
+template <int ROT, int FREE, int BG, int MATH, bool FAST_VALUE = false>
 __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(ROT, FREE, BG)> &S, Accum<BG, MATH> &A,
-                                     uint32_t exp2_table = 0) {
+                                     uint32_t exp2_table = 0, MixFast *fast = nullptr) {
     constexpr int NB = base_columns(ROT, FREE);
     constexpr bool FAST = MATH == MCD_MATH_FAST;
     // ---- geometry: numerator `num` of the rotation term, r^2 ---------------------------------
@@ -454,35 +463,37 @@ __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(R
             const double u = t * yq;
             const double y = ROT == MCD_ROT_RADIAL ? yq * D1 : yq;
             const double wm = S.c[NB];
-            bool slow = false;
-            if constexpr (!ASSUME_FAST) {
-                slow = W.slow != 0;
-                if constexpr (has_icol(BG, MATH)) slow |= (S.e != kMixFastFlag);
-            }
             int Nm, Nb = 0;
             const double em = exp_neg_sq_split(u, exp2_table, Nm);
             double bterm, yb = 0.0, ub = 0.0;
+            bool tiny = false;
             if constexpr (BG == MCD_BG_FIXED_PMEMBER) {
                 bterm = S.c[NB + 1];
             } else if constexpr (BG == MCD_BG_FIXED_DENSITY) {
                 bterm = W.fb * S.c[NB + 1];
-                A.den.mul_raw(wm + W.fb);
             } else {
                 yb = mix_rsqrt(e2 + W.sb2);
                 ub = (v - W.vb) * yb;
                 const double eb = exp_neg_sq_split(ub, exp2_table, Nb);
                 bterm = (W.fb * yb) * scale_by_table_exponent(eb, Nb);
-                A.den.mul_raw(wm + W.fb);
-                slow |= max(Nm, Nb) < kMixSlowExp * kMixTableSize;
+                tiny = max(Nm, Nb) < kMixSlowExp * kMixTableSize;
             }
-            if (!slow) {
-                A.num.mul_raw(fma(wm * y, scale_by_table_exponent(em, Nm), bterm));
+            const double factor = fma(wm * y, scale_by_table_exponent(em, Nm), bterm);
+            if constexpr (FAST_VALUE) {
+                fast->factor = factor;
+                fast->den = wm + W.fb;
+                fast->slow = tiny ? 1 : 0;
             } else {
-                const ExtFactor f = mix_term_slow<BG>(W.fb, u, y, wm, BG == MCD_BG_GAUSSIAN ? yb : S.c[NB + 1],
-                                                      BG == MCD_BG_GAUSSIAN ? 0 : S.e, ub);
-                const double m = f.m;
-                const int e = f.e;
-                A.mul_slow(m, e);
+                bool slow = W.slow != 0 || tiny;
+                if constexpr (has_icol(BG, MATH)) slow |= (S.e != kMixFastFlag);
+                if constexpr (BG != MCD_BG_FIXED_PMEMBER) A.den.mul_raw(wm + W.fb);
+                if (!slow) {
+                    A.num.mul_raw(factor);
+                } else {
+                    const ExtFactor f = mix_term_slow<BG>(W.fb, u, y, wm, BG == MCD_BG_GAUSSIAN ? yb : S.c[NB + 1],
+                                                          BG == MCD_BG_GAUSSIAN ? 0 : S.e, ub);
+                    A.mul_slow(f.m, f.e);
+                }
             }
         }
     } else {
@@ -552,24 +563,48 @@ __device__ __forceinline__ void load_one(const double *__restrict__ c, const int
     a.e = ICOL ? ci[i] : 0;
 }
 
-// two adjacent stars; the FAST mixtures decide once per pair whether both take the fast path
+// N adjacent stars (2 or 4).  The FAST mixtures decide once for the group whether all take the fast path: the
+// per-star flags of the fixed backgrounds are checked first (integer compares), the per-term condition of the
+// fitted background after the values are known; the N fast evaluations form one basic block.
+template <int ROT, int FREE, int BG, int MATH, int N>
+__device__ __forceinline__ void term_group(const Walker &W, const Star<total_columns(ROT, FREE, BG)> *const (&s)[N],
+                                           Accum<BG, MATH> &A, uint32_t exp2_table) {
+    if constexpr (MATH == MCD_MATH_FAST && BG != MCD_BG_NONE) {
+        int slow = W.slow;
+        if constexpr (has_icol(BG, MATH)) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) slow |= s[k]->e ^ kMixFastFlag;
+        }
+        if (slow == 0) {
+            MixFast f[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) term<ROT, FREE, BG, MATH, true>(W, *s[k], A, exp2_table, &f[k]);
+            if constexpr (BG == MCD_BG_GAUSSIAN) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) slow |= f[k].slow;
+            }
+            if (slow == 0) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    A.num.mul_raw(f[k].factor);
+                    if constexpr (BG != MCD_BG_FIXED_PMEMBER) A.den.mul_raw(f[k].den);
+                }
+                return;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) term<ROT, FREE, BG, MATH, false>(W, *s[k], A, exp2_table);
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) term<ROT, FREE, BG, MATH>(W, *s[k], A, exp2_table);
+    }
+}
+
 template <int ROT, int FREE, int BG, int MATH>
 __device__ __forceinline__ void term_pair(const Walker &W, const Star<total_columns(ROT, FREE, BG)> &a,
                                           const Star<total_columns(ROT, FREE, BG)> &b, Accum<BG, MATH> &A, uint32_t exp2_table) {
-    if constexpr (MATH == MCD_MATH_FAST && BG != MCD_BG_NONE) {
-        int slow = W.slow;
-        if constexpr (has_icol(BG, MATH)) slow |= (a.e ^ kMixFastFlag) | (b.e ^ kMixFastFlag);
-        if (slow == 0) {
-            term<ROT, FREE, BG, MATH, true>(W, a, A, exp2_table);
-            term<ROT, FREE, BG, MATH, true>(W, b, A, exp2_table);
-        } else {
-            term<ROT, FREE, BG, MATH, false>(W, a, A, exp2_table);
-            term<ROT, FREE, BG, MATH, false>(W, b, A, exp2_table);
-        }
-    } else {
-        term<ROT, FREE, BG, MATH>(W, a, A, exp2_table);
-        term<ROT, FREE, BG, MATH>(W, b, A, exp2_table);
-    }
+    const Star<total_columns(ROT, FREE, BG)> *const group[2] = {&a, &b};
+    term_group<ROT, FREE, BG, MATH, 2>(W, group, A, exp2_table);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1025,9 +1060,15 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
                 Star<NC> s0, s1, s2, s3;
                 load_pair<NC, ICOL>(c, ci, TS, i, s0, s1);
                 load_pair<NC, ICOL>(c, ci, TS, i + step, s2, s3);
-                term_pair<ROT, FREE, BG, MATH>(W, s0, s1, A, exp2_addr);
-                if constexpr (EXP_TABLE == false) A.end_group();       // FAST mixtures fold every four stars
-                term_pair<ROT, FREE, BG, MATH>(W, s2, s3, A, exp2_addr);
+                if constexpr (EXP_TABLE) {
+                    // FAST mixtures: four stars through one basic block, exponent folded every four stars
+                    const Star<NC> *const group[4] = {&s0, &s1, &s2, &s3};
+                    term_group<ROT, FREE, BG, MATH, 4>(W, group, A, exp2_addr);
+                } else {
+                    term_pair<ROT, FREE, BG, MATH>(W, s0, s1, A, exp2_addr);
+                    A.end_group();
+                    term_pair<ROT, FREE, BG, MATH>(W, s2, s3, A, exp2_addr);
+                }
                 A.end_group();
             }
             for (; i < n2; i += step) {

@@ -1,14 +1,19 @@
-# round 2, multi-GPU call: N = number of GPUs of the box (argument 1)
+# round 2, multi-GPU call: N = number of GPUs of the box (argument 1); "quick" as argument 2 = one bench line only
 N=${1:-2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-echo "== check_fused_allreduce ($N ranks)"
-timeout 300 $TR --master-port 29511 tools/check_fused_allreduce.py > gpurun_out/r2_check_fused_n$N.log 2>&1; echo "rc=$?"; grep -v "Missing units" gpurun_out/r2_check_fused_n$N.log | tail -16
-echo "== bench fused"
-timeout 600 $TR --master-port 29512 bench.py --gpus $N --steps 40 --warmup 3 > gpurun_out/r2_bench_n${N}_fused.json 2> gpurun_out/r2_bench_n${N}_fused.err; echo "rc=$?"; tail -3 gpurun_out/r2_bench_n${N}_fused.err; head -c 1800 gpurun_out/r2_bench_n${N}_fused.json; echo
+echo "== bench fused (tagged-word exchange)"
+timeout 600 $TR --master-port 29512 bench.py --gpus $N --steps 60 --warmup 3 > gpurun_out/r2_bench_n${N}_fused.json 2> gpurun_out/r2_bench_n${N}_fused.err; echo "rc=$?"; tail -2 gpurun_out/r2_bench_n${N}_fused.err; python tools/bench_digest.py gpurun_out/r2_bench_n${N}_fused.json
+if [ "$2" = "quick" ]; then exit 0; fi
+echo "== check_fused_allreduce ($N ranks, tagged-word exchange)"
+timeout 300 $TR --master-port 29511 tools/check_fused_allreduce.py > gpurun_out/r2_check_fused_n$N.log 2>&1; echo "rc=$?"; grep -v "Missing units\|OMP_NUM\|\*\*\*" gpurun_out/r2_check_fused_n$N.log | tail -15
+echo "== check_fused_allreduce ($N ranks, flag + fence exchange)"
+MCD_XCHG=flags timeout 300 $TR --master-port 29516 tools/check_fused_allreduce.py > gpurun_out/r2_check_fused_flags_n$N.log 2>&1; echo "rc=$?"; grep -v "Missing units\|OMP_NUM\|\*\*\*" gpurun_out/r2_check_fused_flags_n$N.log | tail -5
+echo "== bench fused (flag + fence exchange of round 1)"
+MCD_XCHG=flags timeout 600 $TR --master-port 29517 bench.py --gpus $N --steps 60 --warmup 3 --no-samplers > gpurun_out/r2_bench_n${N}_fused_flags.json 2> gpurun_out/r2_bench_n${N}_fused_flags.err; echo "rc=$?"; python tools/bench_digest.py gpurun_out/r2_bench_n${N}_fused_flags.json
 echo "== bench nccl"
-MCD_COLLECTIVE=nccl timeout 600 $TR --master-port 29513 bench.py --gpus $N --steps 40 --warmup 3 > gpurun_out/r2_bench_n${N}_nccl.json 2> gpurun_out/r2_bench_n${N}_nccl.err; echo "rc=$?"; tail -3 gpurun_out/r2_bench_n${N}_nccl.err; head -c 600 gpurun_out/r2_bench_n${N}_nccl.json; echo
-echo "== exchange timeline"
-MCD_B200_LIB=scratch_ab/profile/libmcd_b200.so timeout 300 $TR --master-port 29514 tools/probe/exchange_timeline.py > gpurun_out/r2_exchange_timeline_n$N.log 2>&1; echo "rc=$?"; grep -A1 "^launch" gpurun_out/r2_exchange_timeline_n$N.log | tail -24
-echo "== ncu on rank 0 (nccl mode; after the same command ran plainly above)"
-MCD_COLLECTIVE=nccl NCU_OUT=gpurun_out/r02_lnlike_n${N}_ncu.csv timeout 600 $TR --master-port 29515 --no-python bash tools/ncu_rank0.sh --gpus $N --steps 6 --warmup 3 --no-samplers > gpurun_out/r2_ncu_n${N}.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/r2_ncu_n${N}.log; tail -8 gpurun_out/r02_lnlike_n${N}_ncu.csv | cut -c1-300
+MCD_COLLECTIVE=nccl timeout 600 $TR --master-port 29513 bench.py --gpus $N --steps 60 --warmup 3 --no-samplers > gpurun_out/r2_bench_n${N}_nccl.json 2> gpurun_out/r2_bench_n${N}_nccl.err; echo "rc=$?"; python tools/bench_digest.py gpurun_out/r2_bench_n${N}_nccl.json
+echo "== exchange timeline (tagged, then flags)"
+MCD_B200_LIB=scratch_ab/profile/libmcd_b200.so timeout 300 $TR --master-port 29514 tools/probe/exchange_timeline.py > gpurun_out/r2_exchange_timeline_n$N.log 2>&1; echo "rc=$?"
+MCD_XCHG=flags MCD_B200_LIB=scratch_ab/profile/libmcd_b200.so timeout 300 $TR --master-port 29518 tools/probe/exchange_timeline.py > gpurun_out/r2_exchange_timeline_flags_n$N.log 2>&1; echo "rc=$?"
+grep -c "^launch" gpurun_out/r2_exchange_timeline_n$N.log gpurun_out/r2_exchange_timeline_flags_n$N.log

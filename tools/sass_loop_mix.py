@@ -29,10 +29,10 @@ KERNELS = {
     'lnlike<RADIAL,FIXED,BG_NONE,FAST>': ('ILi1ELi0ELi0ELi0ELb0ELb0E', 4),
     'lnlike<RADIAL,FREE,BG_NONE,FAST>': ('ILi1ELi1ELi0ELi0ELb0ELb0E', 4),
     'lnlike<CONSTANT,FIXED,BG_NONE,FAST>': ('ILi0ELi0ELi0ELi0ELb0ELb0E', 4),
-    'lnlike<RADIAL,FIXED,BG_FIXED_PMEMBER,FAST>': ('ILi1ELi0ELi1ELi0ELb0ELb0E', 2),
-    'lnlike<RADIAL,FIXED,BG_FIXED_DENSITY,FAST>': ('ILi1ELi0ELi2ELi0ELb0ELb0E', 2),
-    'lnlike<RADIAL,FIXED,BG_GAUSSIAN,FAST>': ('ILi1ELi0ELi3ELi0ELb0ELb0E', 2),
-    'lnlike<CONSTANT,FIXED,BG_FIXED_PMEMBER,FAST>': ('ILi0ELi0ELi1ELi0ELb0ELb0E', 2),
+    'lnlike<RADIAL,FIXED,BG_FIXED_PMEMBER,FAST>': ('ILi1ELi0ELi1ELi0ELb0ELb0E', 4),
+    'lnlike<RADIAL,FIXED,BG_FIXED_DENSITY,FAST>': ('ILi1ELi0ELi2ELi0ELb0ELb0E', 4),
+    'lnlike<RADIAL,FIXED,BG_GAUSSIAN,FAST>': ('ILi1ELi0ELi3ELi0ELb0ELb0E', 4),
+    'lnlike<CONSTANT,FIXED,BG_FIXED_PMEMBER,FAST>': ('ILi0ELi0ELi1ELi0ELb0ELb0E', 4),
 }
 
 
