@@ -100,7 +100,10 @@ def test_fused_in_kernel_allreduce_two_gpus():
     """tools/check_fused_allreduce.py under torchrun on two GPUs: fused == NCCL == whole catalogue,
     bit-identical across ranks."""
     import subprocess
-    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
-           '127.0.0.1', '--master-port', str(_free_port()), os.path.join(ROOT, 'tools', 'check_fused_allreduce.py')]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=280, env=dict(os.environ, N_STARS='100000'))
+    for attempt in range(2):           # a rendezvous port just released by another job can fail the first try
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+               '127.0.0.1', '--master-port', str(_free_port()), os.path.join(ROOT, 'tools', 'check_fused_allreduce.py')]
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=140, env=dict(os.environ, N_STARS='100000'))
+        if res.returncode == 0 or 'RESULT FAIL' in res.stdout:
+            break
     assert res.returncode == 0 and 'RESULT PASS' in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
