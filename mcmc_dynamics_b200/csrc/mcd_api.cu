@@ -537,7 +537,8 @@ unsigned long long mcd::next_fuse_nonce(mcd_handle *h) { return ++h->fuse_nonce;
 
 static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double *out_dev, int apply_prior,
                   cudaStream_t stream, bool exchange = false, const FuseParams *fuse = nullptr,
-                  const unsigned long long *epoch_dev = nullptr, const ThetaBlock *inline_theta = nullptr) {
+                  const unsigned long long *epoch_dev = nullptr, const ThetaBlock *inline_theta = nullptr,
+                  const unsigned long long *host_seq_dev = nullptr) {
     if (!h) return fail(-1, "null handle");
     if (n_walkers < 0) return fail(-1, "n_walkers < 0");
     if (n_walkers == 0) return 0;
@@ -592,6 +593,12 @@ static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double 
         p.host_seq = h->host_seq;
         p.done_counter = h->done_counter;
     }
+    if (host_seq_dev) {
+        // graph-replayed host call: `out_dev` is pinned host memory, the sequence number arrives with theta
+        p.host_flag = h->flag_pin;
+        p.host_seq_ptr = host_seq_dev;
+        p.done_counter = h->done_counter;
+    }
     MCD_CUDA(launch_lnlike(h->var, p, stream, inline_theta));
     h->info.last_grid_x = p.n_chunks;
     h->info.last_grid_y = p.n_groups;
@@ -631,21 +638,19 @@ static int ensure_staging(mcd_handle *h, size_t theta_doubles, size_t out_double
 // writes the result into pinned host memory and its last walker group stores the call's sequence number into a
 // pinned flag after a system-scope fence; the host spins on that flag (a stream synchronisation costs more than
 // the kernel on these sizes) and falls back to waiting on the stream when the kernel is a long one.
-static int host_call_inline(mcd_handle *h, const double *theta_host, int n_walkers, double *out_host, int apply_prior,
-                            size_t rows, size_t nt) {
-    if (int rc = ensure_staging(h, 1, rows)) return rc;
+static int ensure_flag(mcd_handle *h) {
     if (!h->flag_pin) {
         MCD_CUDA(cudaMallocHost(&h->flag_pin, sizeof(unsigned long long)));
         *h->flag_pin = 0ull;
         MCD_CUDA(cudaMalloc(&h->done_counter, sizeof(unsigned int)));
         MCD_CUDA(cudaMemset(h->done_counter, 0, sizeof(unsigned int)));
     }
-    ThetaBlock block;
-    if (nt) memcpy(block.v, theta_host, sizeof(double) * nt);
-    h->host_seq += 1;
-    if (int rc = launch(h, nullptr, n_walkers, h->out_pin, apply_prior, h->stream, false, nullptr, nullptr, &block)) return rc;
+    return 0;
+}
+
+// spin on the pinned completion flag until the kernel of call `want` has published its result
+static int wait_for_flag(mcd_handle *h, unsigned long long want) {
     volatile unsigned long long *flag = h->flag_pin;
-    const unsigned long long want = h->host_seq;
     bool seen = false;
     for (int spin = 0; spin < 200000; ++spin) {            // ~100 us of polling, then block on the stream
         if (*flag == want) { seen = true; break; }
@@ -658,6 +663,18 @@ static int host_call_inline(mcd_handle *h, const double *theta_host, int n_walke
         if (*flag != want) return fail(-2, "the likelihood kernel finished without publishing its result");
     }
     __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    return 0;
+}
+
+static int host_call_inline(mcd_handle *h, const double *theta_host, int n_walkers, double *out_host, int apply_prior,
+                            size_t rows, size_t nt) {
+    if (int rc = ensure_staging(h, 1, rows)) return rc;
+    if (int rc = ensure_flag(h)) return rc;
+    ThetaBlock block;
+    if (nt) memcpy(block.v, theta_host, sizeof(double) * nt);
+    h->host_seq += 1;
+    if (int rc = launch(h, nullptr, n_walkers, h->out_pin, apply_prior, h->stream, false, nullptr, nullptr, &block)) return rc;
+    if (int rc = wait_for_flag(h, h->host_seq)) return rc;
     memcpy(out_host, h->out_pin, sizeof(double) * rows);
     return 0;
 }
@@ -673,45 +690,60 @@ static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, dou
     const size_t rows = (size_t)n_walkers * h->n_segments;        // theta is [segments][walkers][theta]
     const size_t nt = rows * h->desc.n_theta;
     if (!exchange && nt <= (size_t)kThetaInline && rows <= 4096) {
-        const char *mode = getenv("MCD_HOST_CALL");               // "graph": always take the copy + graph path (A/B, tests)
-        if (!(mode && mode[0] == 'g')) {
+        const char *mode = getenv("MCD_HOST_CALL");               // "graph" / "sync": take the staged graph path (A/B, tests)
+        if (!(mode && (mode[0] == 'g' || mode[0] == 's'))) {
             if (int rc = order_on_stream(h, h->stream)) return rc;
             return host_call_inline(h, theta_host, n_walkers, out_host, apply_prior, rows, nt);
         }
     }
-    // one word after theta carries the call's exchange epoch to the device inside the same copy, so that
-    // the replayed graph (whose kernel arguments are frozen) sees a fresh tag on every call
-    if (int rc = ensure_staging(h, nt + 1, rows)) return rc;
+    // Two words after theta travel to the device inside the same copy, so that the replayed graph (whose kernel
+    // arguments are frozen) sees fresh values on every call: the exchange epoch (identical on all ranks) and
+    // this handle's call sequence number, which the kernel stores into the pinned completion flag once its
+    // result -- written straight into pinned host memory -- is complete.  The graph is copy-in -> kernel: no
+    // copy-out node, no stream synchronisation (MCD_HOST_CALL=sync keeps both, for A/B).
+    const char *mode = getenv("MCD_HOST_CALL");
+    const bool flagged = !(mode && mode[0] == 's') && h->n_segments == 1;
+    if (int rc = ensure_staging(h, nt + 2, rows)) return rc;
+    if (flagged)
+        if (int rc = ensure_flag(h)) return rc;
     if (nt) memcpy(h->theta_pin, theta_host, sizeof(double) * nt);
-    const unsigned long long *epoch_dev = nullptr;
+    const unsigned long long *epoch_dev = nullptr, *seq_dev = nullptr;
+    unsigned long long words[2] = {0ull, 0ull};
     if (exchange) {
-        const unsigned long long epoch = ++h->xchg_epoch;
-        memcpy(h->theta_pin + nt, &epoch, sizeof(epoch));
+        words[0] = ++h->xchg_epoch;
         epoch_dev = reinterpret_cast<const unsigned long long *>(h->theta_dev + nt);
     }
-    const size_t n_copy = nt + (exchange ? 1 : 0);
+    if (flagged) {
+        words[1] = ++h->host_seq;
+        seq_dev = reinterpret_cast<const unsigned long long *>(h->theta_dev + nt + 1);
+    }
+    memcpy(h->theta_pin + nt, words, sizeof(words));
+    const size_t n_copy = nt + 2;
 
     // A sampler calls with the same shape thousands of times: from the third call of a shape on, the
-    // copy-in / kernel / copy-out sequence is one graph launch (the first call sizes the scratch
+    // copy-in / kernel (/ copy-out) sequence is one graph launch (the first call sizes the scratch
     // buffers, the second captures).
     mcd_handle::HostGraph *slot = nullptr;
+    const int kind = exchange | (flagged ? 2 : 0);
     for (auto &g : h->host_graphs)
-        if (g.seen && g.n_walkers == n_walkers && g.apply_prior == apply_prior && g.exchange == exchange) slot = &g;
+        if (g.seen && g.n_walkers == n_walkers && g.apply_prior == apply_prior && g.exchange == kind) slot = &g;
     if (!slot) {
         for (auto &g : h->host_graphs)
             if (!g.seen && !slot) slot = &g;
         if (slot) {
             slot->n_walkers = n_walkers;
             slot->apply_prior = apply_prior;
-            slot->exchange = exchange;
+            slot->exchange = kind;
         }
     }
     if (int rc = order_on_stream(h, h->stream)) return rc;
     auto enqueue = [&]() -> int {
-        if (n_copy) MCD_CUDA(cudaMemcpyAsync(h->theta_dev, h->theta_pin, sizeof(double) * n_copy, cudaMemcpyHostToDevice, h->stream));
-        if (int rc = launch(h, h->theta_dev, n_walkers, h->out_dev, apply_prior, h->stream, exchange != 0, nullptr, epoch_dev))
+        MCD_CUDA(cudaMemcpyAsync(h->theta_dev, h->theta_pin, sizeof(double) * n_copy, cudaMemcpyHostToDevice, h->stream));
+        if (int rc = launch(h, h->theta_dev, n_walkers, flagged ? h->out_pin : h->out_dev, apply_prior, h->stream, exchange != 0,
+                            nullptr, epoch_dev, nullptr, seq_dev))
             return rc;
-        MCD_CUDA(cudaMemcpyAsync(h->out_pin, h->out_dev, sizeof(double) * rows, cudaMemcpyDeviceToHost, h->stream));
+        if (!flagged)
+            MCD_CUDA(cudaMemcpyAsync(h->out_pin, h->out_dev, sizeof(double) * rows, cudaMemcpyDeviceToHost, h->stream));
         return 0;
     };
     if (slot && slot->exec) {
@@ -737,12 +769,19 @@ static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, dou
         if (int rc = enqueue()) return rc;
     }
     if (slot) slot->seen += slot->seen < 2 ? 1 : 0;
-    MCD_CUDA(cudaStreamSynchronize(h->stream));
+    if (flagged) {
+        if (int rc = wait_for_flag(h, words[1])) return rc;
+    } else {
+        MCD_CUDA(cudaStreamSynchronize(h->stream));
+    }
     memcpy(out_host, h->out_pin, sizeof(double) * rows);
     if (exchange) {
         // a peer that never published turns the sums into NaN after the kernel's time limit: say so
         for (size_t i = 0; i < rows; ++i)
-            if (out_host[i] != out_host[i]) return exchange_status(h, h->stream);
+            if (out_host[i] != out_host[i]) {
+                MCD_CUDA(cudaStreamSynchronize(h->stream));
+                return exchange_status(h, h->stream);
+            }
     }
     return 0;
 }

@@ -126,6 +126,7 @@ struct LaunchParams {
     // the last walker group to finish stores host_seq into *host_flag (pinned) after a system-scope fence
     unsigned long long *host_flag;
     unsigned long long host_seq;
+    const unsigned long long *host_seq_ptr;   // non-null: the sequence number is read from device memory (graph replays)
     unsigned int *done_counter;   // device: walker groups finished so far, zero between launches
     int slot[MCD_NPARAM];
     double fixed_scaled[MCD_NPARAM];   // fixed value already multiplied by its unit scale

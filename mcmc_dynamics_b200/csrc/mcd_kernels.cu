@@ -725,8 +725,10 @@ static __device__ __noinline__ double exchange_shard_sums_tagged(const LaunchPar
     const unsigned long long t = (unsigned long long)tag << 32;
     const unsigned long long lo = (bits & 0xffffffffULL) | t, hi = (bits >> 32) | t;
     const size_t mine = (((size_t)buffer * P.xchg_world + P.xchg_rank) * P.xchg_capacity + w) * 2;
+    MCD_XSTAMP(0);
     for (int peer = 0; peer < P.xchg_world; ++peer)
         asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(P.xchg_words[peer] + mine), "l"(lo), "l"(hi) : "memory");
+    MCD_XSTAMP(1);
     double s = 0.0;
     const long long t0 = clock64();
     for (int r = 0; r < P.xchg_world; ++r) {
@@ -744,6 +746,7 @@ static __device__ __noinline__ double exchange_shard_sums_tagged(const LaunchPar
         }
         s += __longlong_as_double((long long)((a & 0xffffffffULL) | (b << 32)));     // rank order: bit-identical everywhere
     }
+    MCD_XSTAMP(2);
     return s;
 }
 
@@ -908,7 +911,8 @@ __device__ __noinline__ void finish_walker_group(const LaunchParams &P, int seg,
                 if (atomicAdd(P.done_counter, 1u) == expected - 1u) {
                     *P.done_counter = 0u;
                     __threadfence_system();
-                    *reinterpret_cast<volatile unsigned long long *>(P.host_flag) = P.host_seq;
+                    *reinterpret_cast<volatile unsigned long long *>(P.host_flag) =
+                        P.host_seq_ptr ? *P.host_seq_ptr : P.host_seq;
                 }
             }
         }
@@ -925,7 +929,7 @@ __device__ __noinline__ void finish_walker_group(const LaunchParams &P, int seg,
                stamps[3] - t0, stamps[4] - t0, stamps[5] - t0, stamps[6] - t0, stamps[7] - t0, stamps[8] - t0,
                n_super > 1 ? stamps[9] - t0 : 0ull, end - t0);
         if (P.xchg_world > 1)
-            printf("  rank %d exchange: sums stored to peers +%llu ns | flags published +%llu | all %d ranks seen +%llu (waited %llu ns)\n",
+            printf("  rank %d exchange: begin / sums stored to peers +%llu ns | stores issued / flags published +%llu | all %d ranks seen +%llu (waited %llu ns)\n",
                    P.xchg_rank, g_xchg_stamp[0] - t0, g_xchg_stamp[1] - t0, P.xchg_world, g_xchg_stamp[2] - t0,
                    g_xchg_stamp[2] - g_xchg_stamp[1]);
         g_kernel_start[launch & 1u] = ~0ull;

@@ -183,11 +183,13 @@ def test_inline_and_graph_host_calls_agree(monkeypatch):
         monkeypatch.delenv('MCD_HOST_CALL', raising=False)
         inline = [model.lnprob(th) for _ in range(4)]
         lnlike_inline = model.lnlike(th)
-        monkeypatch.setenv('MCD_HOST_CALL', 'graph')
+        monkeypatch.setenv('MCD_HOST_CALL', 'graph')       # staged copy-in -> kernel graph, result + flag in pinned memory
         graph = [model.lnprob(th) for _ in range(4)]
         lnlike_graph = model.lnlike(th)
-        for a, b in zip(inline, graph):
-            assert np.array_equal(a, b) and np.array_equal(a, inline[0])
+        monkeypatch.setenv('MCD_HOST_CALL', 'sync')        # copy-in -> kernel -> copy-out graph, stream synchronisation
+        sync = [model.lnprob(th) for _ in range(4)]
+        for a, b, c in zip(inline, graph, sync):
+            assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, inline[0])
         assert np.array_equal(lnlike_inline, lnlike_graph)
         if n_walkers > 2:
             assert inline[0][2] == -np.inf and np.isfinite(lnlike_inline[2])
