@@ -381,7 +381,16 @@ static __device__ __noinline__ ExtFactor mix_term_slow(double fb, double u, doub
 // 2^(j / kMixTableSize) into shared memory (called by the first kMixTableSize threads' worth of a CTA before
 // its first barrier)
 __device__ __forceinline__ void fill_exp2_table(double *table) {
-#if MCD_MIX_LEAN
+#if MCD_MIX_LEAN == 2
+    // one library exp2 per four entries, the other three by a multiplication (1.5 ulp)
+    for (int j = threadIdx.x; j < kMixTableSize / 4; j += blockDim.x) {
+        const double e = exp2((double)j * (4.0 / kMixTableSize));
+        table[4 * j] = e;
+        table[4 * j + 1] = e * 1.0006771306930664;      // 2^(1/1024)
+        table[4 * j + 2] = e * 1.0013547198921082;      // 2^(2/1024)
+        table[4 * j + 3] = e * 1.002032767907594;       // 2^(3/1024)
+    }
+#elif MCD_MIX_LEAN
     for (int j = threadIdx.x; j < kMixTableSize; j += blockDim.x) table[j] = exp2((double)j * (1.0 / kMixTableSize));
 #else
     if (threadIdx.x < 64) table[threadIdx.x] = kExp2Table[threadIdx.x];

@@ -272,44 +272,60 @@ __device__ __forceinline__ void exp_neg_half_table(double w, const double *__res
 }
 
 // ---- mixture fast path -------------------------------------------------------------------------
-// exp(-z^2/2) as ONE plain double, for u = z * kExpArgScale (kExpArgScale^2 = 32 log2(e), so that
-// -z^2/2 * log2(e) * 64 = -u^2 and the square is formed inside the two FMAs that split it into integer
-// and fraction -- no separate multiplication, and the walker constants carry the scale for free).
-// |u| is clamped to 254 on the integer pipe, i.e. the result never drops below 2^-1010 and its exponent
+// exp(-z^2/2) as ONE plain double, for u = z * kExpArgScale (kExpArgScale^2 = T log2(e) / 2 for a table of T
+// entries, so that -z^2/2 * log2(e) * T = -u^2 and the square is formed inside the two FMAs that split it
+// into integer and fraction -- no separate multiplication, and the walker constants carry the scale for free).
+// |u| is clamped on the integer pipe (kMixClampHi), i.e. the result never drops below 2^-1010 and its exponent
 // can be set by an integer addition on the high word: the caller only takes this path when the other
 // mixture component is at least 2^-480, where a member term of 2^-1010 and one of 2^-100000 are the same
 // thing.  A NaN u is clamped too (the NaN reaches the factor through y = norm^-1/2 or the walker's
-// `bad` flag).  9 FP64 + 6 integer instructions.
+// `bad` flag).
+// MCD_MIX_LEAN selects the arithmetic of the mixture kernels (same tolerance argument as MCD_NEWTON above):
+//   2 (default): 1024-entry table + quadratic polynomial (truncation 6.5e-12, zero-mean) and quadratic Newton
+//      steps (1.3e-12); the table unit is folded into kExpArgScale, so the argument needs no rescaling:
+//      26 FP64 instructions per term of the fixed-background mixture, 42 with the fitted Gaussian background.
+//   1: 256-entry table + cubic polynomial (1.4e-13), the argument doubled in the loop (28 / 46; round 2's
+//      first version: +14 % over 0 on the 2e6-star mixture workload, 2.87 -> 2.51 ms).
+//   0: 64-entry table + degree-5 polynomial (4e-17) and cubic Newton steps (34 / 59).
+#ifndef MCD_MIX_LEAN
+#define MCD_MIX_LEAN 2
+#endif
+#if MCD_MIX_LEAN == 2
+constexpr int kMixTableBits = 10;
+constexpr double kExpArgScale = 27.17829760921661;      // sqrt(512 / ln 2): -z^2/2 log2(e) 1024 = -u^2
+constexpr int kMixClampHi = 0x408fc000;                 // |u| <= 1016: the result never drops below 2^-1008.1
+#elif MCD_MIX_LEAN
+constexpr int kMixTableBits = 8;
+constexpr double kExpArgScale = 6.7945744023041525;     // sqrt(32 / ln 2), doubled in exp_neg_sq_split
+constexpr int kMixClampHi = 0x406fc000;                 // |u| <= 254
+#else
+constexpr int kMixTableBits = 6;
 constexpr double kExpArgScale = 6.7945744023041525;     // sqrt(32 / ln 2)
+constexpr int kMixClampHi = 0x406fc000;                 // |u| <= 254
+#endif
+constexpr int kMixTableSize = 1 << kMixTableBits;
 constexpr int kMixFastFlag = (int)0x80000000;           // exponent-column value of a fast-path star
 constexpr int kMixComfort = 200;                        // fast path: |log2(background term)| <= this
 constexpr int kMixSlowExp = -200;                       // fitted background: both components below 2^this -> slow path
 
-// MCD_MIX_LEAN 1 (default): 256-entry table + cubic polynomial (truncation 1.4e-13) and quadratic Newton
-// steps (1.3e-12) in the mixture kernels: 28 instead of 34 FP64 instructions per term, +14 % on the 2e6-star
-// mixture workload (2.87 -> 2.51 ms), same tolerance argument as MCD_NEWTON above.  0: 64-entry table +
-// degree-5 polynomial (4e-17) and cubic Newton steps.
-#ifndef MCD_MIX_LEAN
-#define MCD_MIX_LEAN 1
-#endif
-#if MCD_MIX_LEAN
-constexpr int kMixTableBits = 8;
-#else
-constexpr int kMixTableBits = 6;
-#endif
-constexpr int kMixTableSize = 1 << kMixTableBits;
-
-// (ln2 / 256)^k / k!, k = 1..3
+// (ln2 / 256)^k / k!, k = 1..3, and (ln2 / 1024)^k / k!, k = 1..2
 __constant__ double kExp2LeanCoef[3] = {0.0027076061740622863, 3.6655655969101062e-06, 3.3083026805413713e-09};
+__constant__ double kExp2Lean2Coef[2] = {0.0006769015435155716, 2.290978498068816e-07};
 
 // returns the mantissa in [0.99, 2.01); N = table-units exponent: exp(-z^2/2) = mant * 2^(N >> kMixTableBits)
 // `table` is the 32-bit shared-memory address of 2^(j / kMixTableSize), j = 0 .. kMixTableSize - 1 (a generic
 // pointer costs four uniform-datapath instructions per load to rebuild the shared window base).
 __device__ __forceinline__ double exp_neg_sq_split(double u, uint32_t table, int &N) {
     const double kMagic = 6755399441055744.0;            // 1.5 * 2^52
-    const int hi = min(__double2hiint(u) & 0x7fffffff, 0x406fc000);      // |u| <= 254
+    const int hi = min(__double2hiint(u) & 0x7fffffff, kMixClampHi);
     const double uc = __hiloint2double(hi, __double2loint(u));
-#if MCD_MIX_LEAN
+#if MCD_MIX_LEAN == 2
+    const double shifted = fma(-uc, uc, kMagic);
+    N = __double2loint(shifted);
+    const double nf = shifted - kMagic;
+    const double r = fma(-uc, uc, -nf);                  // exact square minus its integer part, |r| <= 1/2
+    const double p = fma(kExp2Lean2Coef[1], r, kExp2Lean2Coef[0]);
+#elif MCD_MIX_LEAN
     // table units of 1/256: -u^2 * 4
     const double s = uc * 2.0;                            // exact
     const double shifted = fma(-s, s, kMagic);
