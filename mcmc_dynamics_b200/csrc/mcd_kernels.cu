@@ -42,6 +42,9 @@
 #ifndef MCD_BG_MIN_BLOCKS
 #define MCD_BG_MIN_BLOCKS 2   // the same two knobs for the background-mixture variants
 #endif
+#ifndef MCD_FLAG_LATE
+#define MCD_FLAG_LATE 1       // fixed-background mixtures: per-star fast-path flags checked after the fast evaluation
+#endif
 #ifndef MCD_BG_PAIRS
 #define MCD_BG_PAIRS 2        // round 2 (lean arithmetic): C3 45.1 -> 43.1 us, mixgb 4286 -> 4159 us, mix +0.9 % (r02_ab_runs.md)
 #endif
@@ -188,6 +191,7 @@ cudaError_t launch_pack(const PackParams &p, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------
 struct Walker {
     double vsys, s2;            // systemic velocity, sigma_max^2
+    double s2h;                 // sigma_max^2 / 2 (pairs with rsqrt_twice in the FAST radial variants)
     double cx, cy;              // rotation: v_rot numerator = x*cx + y*cy
     double ip2, ia2;            // 1/r_peak^2, 1/a^2 in units of the stored coordinates
     double sb, cb, cdc;         // free centre: sin/cos(ra_c - ra0), cos(dec_c)
@@ -240,6 +244,7 @@ __device__ __forceinline__ void load_walker(const LaunchParams &P, const double 
     W.prior_ok = ok;
     W.vsys = par[MCD_P_V_SYS];
     W.s2 = par[MCD_P_SIGMA_MAX] * par[MCD_P_SIGMA_MAX];
+    W.s2h = 0.5 * W.s2;
     const double vmx = par[MCD_P_V_MAXX], vmy = par[MCD_P_V_MAXY];
     if constexpr (ROT == MCD_ROT_CONSTANT) {
         // v_max sin(theta_i - theta_0) = sin(theta_i) v_maxx - cos(theta_i) v_maxy (constant.py:109-111)
@@ -449,7 +454,10 @@ __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(R
             D1 = fma(r2, W.ip2, 1.0);
             const double D2 = fma(r2, W.ia2, 1.0);
             // sigma_max^2 / sqrt(1 + r^2/a^2) + verr^2
-            norm = fma(W.s2, BG == MCD_BG_NONE ? fast_rsqrt(D2) : mix_rsqrt(D2), e2);
+            if constexpr (MCD_NEWTON == 2 && (BG == MCD_BG_NONE || MCD_MIX_LEAN != 0))
+                norm = fma(W.s2h, rsqrt_twice(D2), e2);
+            else
+                norm = fma(W.s2, BG == MCD_BG_NONE ? fast_rsqrt(D2) : mix_rsqrt(D2), e2);
         } else {
             norm = e2 + W.s2;
         }
@@ -580,14 +588,24 @@ __device__ __forceinline__ void term_group(const Walker &W, const Star<total_col
                                            Accum<BG, MATH> &A, uint32_t exp2_table) {
     if constexpr (MATH == MCD_MATH_FAST && BG != MCD_BG_NONE) {
         int slow = W.slow;
+#if !MCD_FLAG_LATE
         if constexpr (has_icol(BG, MATH)) {
 #pragma unroll
             for (int k = 0; k < N; ++k) slow |= s[k]->e ^ kMixFastFlag;
         }
+#endif
         if (slow == 0) {
             MixFast f[N];
 #pragma unroll
             for (int k = 0; k < N; ++k) term<ROT, FREE, BG, MATH, true>(W, *s[k], A, exp2_table, &f[k]);
+#if MCD_FLAG_LATE
+            // the per-star flags are looked at after the (harmless) fast evaluation: the first instructions of
+            // the block then wait for the star columns only, not for a flag load, compare and branch
+            if constexpr (has_icol(BG, MATH)) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) slow |= s[k]->e ^ kMixFastFlag;
+            }
+#endif
             if constexpr (BG == MCD_BG_GAUSSIAN) {
 #pragma unroll
                 for (int k = 0; k < N; ++k) slow |= f[k].slow;

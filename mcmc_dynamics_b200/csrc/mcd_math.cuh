@@ -81,6 +81,24 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
 #endif
 }
 
+// 2 x^(-1/2) for normal positive x: the quadratic Newton step in the form y0 (3 - x y0^2), which needs no halved
+// seed (no integer-pipe work); the caller folds the factor 2 into a constant.  Same error as fast_rsqrt with
+// MCD_NEWTON 2 (3/8 e^2, e = the seed's relative error 2^-20).
+#ifndef MCD_RSQRT3
+#define MCD_RSQRT3 1
+#endif
+__device__ __forceinline__ double rsqrt_twice(double x) {
+#if MCD_RSQRT3
+    const double y0 = rsqrt_seed(x);
+    const double t = x * y0;
+    const double g = fma(-t, y0, 3.0);
+    return y0 * g;
+#else
+    const double y = fast_rsqrt(x);
+    return y + y;
+#endif
+}
+
 // 2^d for integer d <= 0; exact, flushed to zero below the normal range.
 __device__ __forceinline__ double pow2_nonpos(int d) {
     const int hi = (d + 1023) << 20;
