@@ -994,7 +994,11 @@ static int per_star(mcd_handle *h, const double *theta_dev, double *out_dev, int
     const int nb = variant_columns(h->var) - (h->var.background == MCD_BG_NONE ? 0 : (h->var.background == MCD_BG_GAUSSIAN ? 1 : 2));
     if (h->var.background == MCD_BG_FIXED_PMEMBER || h->var.background == MCD_BG_FIXED_DENSITY) p.cols[nb + 1] = h->raw[RAW_LBG];
     // ... and the velocity itself where the FAST mixture packing keeps it in units of 1 / kExpArgScale
-    if (h->var.background != MCD_BG_NONE && h->var.math_mode == MCD_MATH_FAST) p.cols[nb - 2] = h->raw[RAW_V];
+    p.verr2_unscale = 1.0;
+    if (h->var.background != MCD_BG_NONE && h->var.math_mode == MCD_MATH_FAST) {
+        p.cols[nb - 2] = h->raw[RAW_V];
+        p.verr2_unscale = 1.0 / mix_var_scale();      // ... and verr^2 times kMixVarScale
+    }
     if (membership && h->var.background == MCD_BG_NONE) return fail(-1, "membership probabilities need a background component");
     if (h->n_segments > 1) return fail(-1, "per-star entry points are not available for segmented handles");
     MCD_CUDA(launch_per_star(h->var, p, out_dev, membership, stream));

@@ -115,6 +115,7 @@ struct LaunchParams {
     int n_theta;
     int apply_prior;          // 1: lnprob (box prior fused), 0: lnlike
     int fixed_prior_ok;
+    double verr2_unscale;         // per-star kernel: factor that takes the packed verr^2 column back to verr^2
     const double *theta;      // [n_segments][n_walkers][n_theta]
     int super;                // chunks per super-chunk (level 1 of the cross-CTA reduction)
     int n_super;              // super-chunks per walker group
@@ -158,6 +159,7 @@ int variant_columns(const Variant &v);
 bool variant_has_icol(const Variant &v);
 int variant_flops_per_term(const Variant &v);
 
+double mix_var_scale();      // factor carried by the packed verr^2 column of the FAST mixture variants (mcd_math.cuh)
 cudaError_t launch_pack(const PackParams &p, cudaStream_t stream);
 // `inline_theta` (may be nullptr) is handed to the kernel by value next to `p`
 cudaError_t launch_lnlike(const Variant &v, const LaunchParams &p, cudaStream_t stream, const ThetaBlock *inline_theta = nullptr);

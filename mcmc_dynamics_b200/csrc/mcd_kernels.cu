@@ -147,7 +147,8 @@ __global__ void pack_kernel(const PackParams P) {
     // FAST mixture kernels take the velocity in units of 1 / kExpArgScale (see `term`)
     const bool scaled = P.math_mode == MCD_MATH_FAST && P.background != MCD_BG_NONE;
     P.cols[c++][o] = scaled ? v * kExpArgScale : v;
-    P.cols[c++][o] = e2;
+    // ... and verr^2 times kMixVarScale (a power of two: exact)
+    P.cols[c++][o] = scaled ? e2 * kMixVarScale : e2;
     if (P.background == MCD_BG_FIXED_PMEMBER || P.background == MCD_BG_FIXED_DENSITY) {
         const double w = P.background == MCD_BG_FIXED_PMEMBER ? P.raw.pmember[i] : P.raw.density[i];
         const double lbg = P.raw.lbg[i];
@@ -175,6 +176,8 @@ __global__ void pack_kernel(const PackParams P) {
     }
 }
 
+double mix_var_scale() { return kMixVarScale; }
+
 cudaError_t launch_pack(const PackParams &p, cudaStream_t stream) {
     if (p.n_stars <= 0) return cudaSuccess;
     const int block = 256;
@@ -200,7 +203,8 @@ struct Walker {
     int prior_ok;
     int slow;                   // FAST mixtures: every term of this walker takes the extended-range path
     // FAST mixture kernels (SCALED): vsys, cx, cy, vb are multiplied by kExpArgScale, so that residuals come
-    // out as u = z * kExpArgScale, the argument of exp_neg_sq_split
+    // out as u = z * kExpArgScale, the argument of exp_neg_sq_split; s2, s2h, sb2 by kMixVarScale like the
+    // packed verr^2 column
 };
 
 // stretch-move proposal of active walker k of segment `seg` (emcee RedBlueMove/StretchMove):
@@ -279,6 +283,9 @@ __device__ __forceinline__ void load_walker(const LaunchParams &P, const double 
         W.cx *= kExpArgScale;
         W.cy *= kExpArgScale;
         W.vb *= kExpArgScale;
+        W.s2 *= kMixVarScale;
+        W.s2h *= kMixVarScale;
+        W.sb2 *= kMixVarScale;
         // opaque to the optimiser: it would otherwise redo these multiplications inside the star loop
         // (v - v_sys * c as an FMA with the constant rebuilt in uniform registers per pair)
         asm volatile("" : "+d"(W.vsys), "+d"(W.vb));
@@ -454,6 +461,7 @@ __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(R
             D1 = fma(r2, W.ip2, 1.0);
             const double D2 = fma(r2, W.ia2, 1.0);
             // sigma_max^2 / sqrt(1 + r^2/a^2) + verr^2
+            // (mixtures: W.s2h, W.s2 and e2 carry kMixVarScale, see load_walker)
             if constexpr (MCD_NEWTON == 2 && (BG == MCD_BG_NONE || MCD_MIX_LEAN != 0))
                 norm = fma(W.s2h, rsqrt_twice(D2), e2);
             else
@@ -476,7 +484,7 @@ __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(R
             // fixed backgrounds, checked per term for the fitted one); everything else -- weights of exactly
             // 0 or 1, components hundreds of sigma out, the reference's -inf corner of runner.py:280-286 --
             // goes through the (mantissa, exponent) arithmetic below, which cannot underflow.
-            const double yq = mix_rsqrt(q);
+            const double yq = mix_var_rsqrt(q);
             const double u = t * yq;
             const double y = ROT == MCD_ROT_RADIAL ? yq * D1 : yq;
             const double wm = S.c[NB];
@@ -489,7 +497,7 @@ __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(R
             } else if constexpr (BG == MCD_BG_FIXED_DENSITY) {
                 bterm = W.fb * S.c[NB + 1];
             } else {
-                yb = mix_rsqrt(e2 + W.sb2);
+                yb = mix_var_rsqrt(e2 + W.sb2);
                 ub = (v - W.vb) * yb;
                 const double eb = exp_neg_sq_split(ub, exp2_table, Nb);
                 bterm = (W.fb * yb) * scale_by_table_exponent(eb, Nb);
@@ -1498,6 +1506,7 @@ __global__ void per_star_kernel(const __grid_constant__ LaunchParams P, double *
     Star<NC> S;
 #pragma unroll
     for (int k = 0; k < NC; ++k) S.c[k] = P.cols[k][i];
+    S.c[base_columns(ROT, FREE) - 1] *= P.verr2_unscale;      // 1, or 1 / kMixVarScale for a FAST mixture packing (exact)
     S.e = 0;
     Accum<BG, MCD_MATH_PLAIN> A;
     A.reset();

@@ -99,6 +99,15 @@ __device__ __forceinline__ double rsqrt_twice(double x) {
 #endif
 }
 
+// FAST mixture variants: the packed verr^2 column and the walker's sigma^2 constants carry this factor, so that
+// every reciprocal square root of the mixture term is rsqrt_twice of four times its argument -- no halved seed
+// anywhere in the loop.  (1: round-2 arithmetic with mix_rsqrt; A/B builds.)
+#if MCD_RSQRT3 && MCD_NEWTON == 2
+constexpr double kMixVarScale = 4.0;
+#else
+constexpr double kMixVarScale = 1.0;
+#endif
+
 // 2^d for integer d <= 0; exact, flushed to zero below the normal range.
 __device__ __forceinline__ double pow2_nonpos(int d) {
     const int hi = (d + 1023) << 20;
@@ -383,6 +392,12 @@ __device__ __forceinline__ double mix_rsqrt(double x) {
 #else
     return fast_rsqrt(x);
 #endif
+}
+
+// x^(-1/2) of a variance that carries kMixVarScale
+__device__ __forceinline__ double mix_var_rsqrt(double x_scaled) {
+    if constexpr (kMixVarScale == 4.0 && MCD_MIX_LEAN != 0) return rsqrt_twice(x_scaled);
+    else return mix_rsqrt(x_scaled * (1.0 / kMixVarScale));
 }
 
 // 2^d for d <= 0, exactly zero below 2^-960 (integer pipe only)
