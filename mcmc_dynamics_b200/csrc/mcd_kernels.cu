@@ -42,6 +42,9 @@
 #ifndef MCD_BG_MIN_BLOCKS
 #define MCD_BG_MIN_BLOCKS 2   // the same two knobs for the background-mixture variants
 #endif
+#ifndef MCD_GROUP4
+#define MCD_GROUP4 1          // no-background variants: exponent of the variance product folded every four stars (0: two)
+#endif
 #ifndef MCD_FLAG_LATE
 #define MCD_FLAG_LATE 1       // fixed-background mixtures: per-star fast-path flags checked after the fast evaluation
 #endif
@@ -307,10 +310,14 @@ struct Accum<MCD_BG_NONE, MCD_MATH_FAST> {
     double chi;
     LogProduct norm;
     __device__ __forceinline__ void reset() { chi = 0.0; norm.reset(); }
-    // called after every group of at most kGroup factors multiplied in with mul_raw()
-    __device__ __forceinline__ void end_group() { norm.renormalise_checked(); }
-    __device__ __forceinline__ void end_tile() {}
-    __device__ __forceinline__ double value() { return -0.5 * (chi + norm.ln()); }
+    // called after every group of at most four factors multiplied in with mul_raw(): variances within
+    // 2^+-250 (1e-75 .. 1e75 km^2/s^2) keep the product of four a normal number; anything else raises `bad`
+    __device__ __forceinline__ void end_group() { norm.renormalise_light(); }
+    __device__ __forceinline__ void end_tile() { norm.fold(); }
+    __device__ __forceinline__ double value() {
+        norm.fold();
+        return -0.5 * (chi + norm.ln());
+    }
 };
 template <int BG>
 struct Accum<BG, MCD_MATH_FAST> {
@@ -319,6 +326,8 @@ struct Accum<BG, MCD_MATH_FAST> {
     __device__ __forceinline__ void reset() { num.reset(); den.reset(); dead = 0; }
     // Called after at most four stars.  Fast-path factors lie within 2^+-(kMixComfort + a few), so the
     // product of four stays a normal number; anything else (NaN, inf, zero, negative) raises `bad`.
+    // (renormalise_light() is 1.2 - 1.6 % slower here: these kernels are latency-, not issue-bound, and the two
+    // extra accumulator registers cost more than the five integer instructions, profiles/r02_ab_runs.md)
     __device__ __forceinline__ void end_group() {
         num.renormalise_checked();
         if (BG != MCD_BG_FIXED_PMEMBER) den.renormalise_checked();
@@ -1105,7 +1114,7 @@ __global__ void __launch_bounds__(kBlock, (BG == MCD_BG_NONE ? MCD_MIN_BLOCKS : 
                     term_group<ROT, FREE, BG, MATH, 4>(W, group, A, exp2_addr);
                 } else {
                     term_pair<ROT, FREE, BG, MATH>(W, s0, s1, A, exp2_addr);
-                    A.end_group();
+                    if constexpr (MCD_GROUP4 == 0) A.end_group();
                     term_pair<ROT, FREE, BG, MATH>(W, s2, s3, A, exp2_addr);
                 }
                 A.end_group();

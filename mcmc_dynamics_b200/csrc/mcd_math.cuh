@@ -121,8 +121,11 @@ struct LogProduct {
     long long expo;     // sum of the factors' unbiased exponents
     int bad;            // a factor of mul()/renormalise_checked() left the normal positive range (result: NaN)
     int signs;          // OR of the high words of the mul_ext() factors: sign bit set = a negative factor
+    int expo32;         // renormalise_light(): exponents since the last fold() (32-bit: one add per group)
+    unsigned range;     // renormalise_light(): largest (high word - 0x00100000) seen, as unsigned: >= 0x7fe00000
+                        // means some group product left the normal positive range (result: NaN)
 
-    __device__ __forceinline__ void reset() { mant = 1.0; expo = 0; bad = 0; signs = 0; }
+    __device__ __forceinline__ void reset() { mant = 1.0; expo = 0; bad = 0; signs = 0; expo32 = 0; range = 0u; }
 
     // multiply by x, a normal positive double
     __device__ __forceinline__ void mul(double x) {
@@ -172,6 +175,21 @@ struct LogProduct {
         bad |= ((unsigned)(hi - 0x00100000) >= 0x7fe00000u);
         expo += (hi >> 20) - 1023;
         mant = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(mant));
+    }
+
+    // The hot-loop form of renormalise_checked(): the exponent goes into a 32-bit sum and the range check into
+    // a running maximum (6 integer instructions instead of 11); fold() moves both into `expo` / `bad` and must
+    // be called at least every 2^20 calls and before ln().
+    __device__ __forceinline__ void renormalise_light() {
+        const int hi = __double2hiint(mant);
+        range = max(range, (unsigned)(hi - 0x00100000));
+        expo32 += (hi >> 20) - 1023;
+        mant = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(mant));
+    }
+    __device__ __forceinline__ void fold() {
+        expo += expo32;
+        expo32 = 0;
+        bad |= range >= 0x7fe00000u;
     }
 
     // ln of the product: -inf if it is exactly zero, NaN if a factor was bad or negative or the

@@ -202,3 +202,27 @@ def test_inline_and_graph_host_calls_agree(monkeypatch):
     for _ in range(3):
         assert harness.relative_error(model.lnprob(small), want_small) < RTOL
         assert harness.relative_error(model.lnprob(big), want_big) < RTOL
+
+
+@pytest.mark.parametrize('variant', ['ModelFit', 'ConstantFit'])
+def test_extreme_variances_are_right_or_nan(variant):
+    """The FAST no-background kernels multiply the variances of four stars before folding the exponent
+    (csrc/mcd_kernels.cu: Accum<BG_NONE, FAST>::end_group): variances within 2^+-250 are exact business as
+    usual; beyond that the product may leave the normal range, which must surface as NaN -- never as a wrong
+    finite number.  PLAIN arithmetic (the reference's formulas, runner.py:261-271) has no such limit."""
+    from common import build
+    model, oracle, theta, truth = build(variant, n_stars=1003)
+    plain, _, _, _ = build(variant, n_stars=1003, math_mode='plain')
+    names = model.fitted_parameters
+    th = theta(6, seed=11)
+    for row, sigma in enumerate([1e-30, 1e-20, 1e20, 1e35, 1e60, 1e-60]):
+        th[row, names.index('sigma_max')] = sigma
+    for m in (model, plain):       # the default bounds of sigma_max do not reach that far
+        m.parameters['sigma_max'].set(min=0.0, max=1e80)
+    want = oracle.lnlike_many(th)
+    got = model.lnlike(th)
+    assert harness.relative_error(plain.lnlike(th), want) < RTOL
+    for g, w in zip(got, want):
+        assert np.isnan(g) or abs(g - w) <= RTOL * abs(w)
+    # sigma_max = 1e20, 1e35 are inside the documented range (variance 1e40, 1e70 < 2^250 = 1.8e75): exact
+    assert np.all(np.isfinite(got[2:4])) and harness.relative_error(got[2:4], want[2:4]) < RTOL
