@@ -388,21 +388,21 @@ static void search_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p)
     // kernel is FP64-pipe bound, so co-resident CTAs share the pipe and the launch takes as long as the most
     // loaded SM needs for its CTAs one after the other.  Cost of a candidate, in star iterations per thread:
     //   cta   = tiles_per_chunk * (tile / slices + 3) + overhead      (3: barrier + stage hand-over per tile;
-    //           overhead: walker set-up and reduction, ~24 iterations' worth of pipe time)
+    //           overhead: walker set-up and reduction, ~16 iterations' worth of pipe time)
     //   load  = ceil(CTAs / SMs): CTAs on the most loaded SM.  Equal-sized CTAs are dealt out evenly, so a grid
     //           of 8.26 CTAs per SM costs 9 (measured: +9 %), whether or not it fits one wave of resident CTAs.
-    //           x 1.25 when an SM holds a single CTA: 8 warps do not keep the FP64 pipe busy (measured 18 %);
-    //           x 1.03 per resident slot left empty otherwise
-    //   cost  = load * cta + min(2 % of that, cta / 3): SMs differ by a per cent or two in speed; many small
-    //           CTAs even that out to within a fraction of one CTA, few large ones cannot (round 1 measured
-    //           8 waves 2.3 % ahead of 1 on the 1e7-star workload)
+    //           A partly filled last round of resident CTAs costs extra (see below).
+    //   cost  = load * cta * (1 + 2 % / waves^1.5): SMs differ by a per cent or two in speed; several waves of
+    //           CTAs even that out, one wave cannot.  Measured on star shards of C5 with the round-2 kernel
+    //           (gpurun_out/r2r_geometry.log): 5e6 stars, one wave 3121 us, two 3074, four 3056, eight 3053;
+    //           1.25e6 stars, one wave 788.6 us, two 779.3, 3.7 waves 778.2
     // Fitted to (tile, tiles_per_chunk) sweeps of BASELINE configs C3, C4 and of one of eight C5 shards
     // (profiles/r02_ab_runs.md): measured time / cost is constant within +-8 % over 24 mid-size geometries and
     // within 2 % over the 7 shard-sized ones, where the round-1 model (whole waves of SMs x CTAs-per-SM, blind
     // to a partly filled wave) was off by up to 35 % and 9 %.
     const int sms = std::max(1, h->sm_count);
     const int problems = std::max(1, p.n_groups * h->n_segments);      // CTAs per star chunk
-    const double overhead = 24.0;
+    const double overhead = 16.0;      // 24 before the round-2 kernels; 1e7 stars: 24 CTAs per SM 6056 us, 12 per SM 6084 us
     const long long n = std::max<long long>(h->max_segment, 1);     // grid sized for the largest segment
     int min_tile = ((2 * p.slices + 15) / 16) * 16;
     min_tile = std::min(std::max(min_tile, 16), kMaxTile);
@@ -418,12 +418,15 @@ static void search_geometry(const mcd_handle *h, int n_walkers, LaunchParams &p)
             const long long ctas = chunks * problems;
             const double cta = (double)tpc * ((double)tile / p.slices + 3.0) + overhead;
             const long long per_sm = (ctas + sms - 1) / sms;
-            // fewer CTAs on an SM than fit: less latency hiding (1 CTA: measured; 2 of 3: 3 %, an estimate that only
-            // breaks ties between otherwise equal geometries)
+            // An SM works through its CTAs `room` at a time.  A last, partly filled round hides less latency: one
+            // CTA alone on an SM runs 25 % slower per term (measured: 8 warps do not fill the FP64 pipe), 2 of 3
+            // about 3 % (an estimate that only breaks ties between otherwise equal geometries).
             const int room = std::max(1, h->blocks_per_sm);
-            const double thin = per_sm == 1 ? 1.25 : (per_sm < room ? 1.0 + 0.03 * (double)(room - per_sm) : 1.0);
-            const double base = thin * (double)per_sm * cta;
-            const double cost = base + std::min(0.02 * base, cta / 3.0);
+            const long long full = per_sm / room, rem = per_sm % room;
+            const double rem_cost = rem == 0 ? 0.0 : (rem == 1 ? 1.25 : (double)rem * (1.0 + 0.03 * (double)(room - rem)));
+            const double base = ((double)(full * room) + rem_cost) * cta;
+            const double waves = std::max(1.0, (double)per_sm / (double)room);
+            const double cost = base * (1.0 + 0.02 / (waves * std::sqrt(waves)));
             if (cost < best * (1.0 - 1e-12)) {
                 best = cost;
                 best_tile = tile;

@@ -41,6 +41,7 @@ BUILDERS = {'c1': configs.config_c1, 'c2': configs.config_c2, 'c3': configs.conf
             'c4': configs.config_c4, 'c5': configs.config_c5, 'c5free': lambda: configs.config_c5(free=True),
             # one of eight star shards of C5: what each rank runs at N = 8
             'c5s': lambda: configs.config_c5(n_stars=1_250_000),
+            'c5q': lambda: configs.config_c5(n_stars=2_500_000), 'c5h': lambda: configs.config_c5(n_stars=5_000_000),
             'mix': lambda: mixture_large(False), 'mixgb': lambda: mixture_large(True)}
 
 

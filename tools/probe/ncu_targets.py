@@ -21,7 +21,10 @@ else:
     name, model, truth, nw = ab_configs.BUILDERS[what]()
     th = synthetic.initial_ball(truth, model.fitted_parameters, nw, seed=5, scale=0.05)[:nw // 2]
     tdev = torch.as_tensor(th, device='cuda:0')
-    for _ in range(6):
+    n_calls = int(sys.argv[2]) if len(sys.argv) > 2 else 6       # a large count keeps a GPU busy as background load
+    for k in range(n_calls):
         out = model.lnprob_tensor(tdev)
+        if k % 64 == 63:
+            torch.cuda.synchronize()
     torch.cuda.synchronize()
     print(name, float(out[0]))
