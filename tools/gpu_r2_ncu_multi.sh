@@ -1,4 +1,4 @@
-# round 2: counters at N GPUs (argument 1).  (A) rank 0 of the bench under ncu, NCCL collective; (B) shard under load.
+# round 2: bench line and hardware counters at N GPUs (argument 1): (B) one star shard under ncu while the other GPUs run the same shard workload.
 N=${1:-2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
@@ -7,6 +7,5 @@ timeout 300 $TR --master-port 29512 bench.py --gpus $N --steps 60 --warmup 3 > g
 echo "== (B) shard under load"
 bash tools/ncu_shard_under_load.sh $N gpurun_out/r02_lnlike_shard_n${N}_ncu.csv 2>&1 | tail -3
 grep -c lnlike_kernel gpurun_out/r02_lnlike_shard_n${N}_ncu.csv
-echo "== (A) rank 0 of the bench under ncu (NCCL collective)"
-MCD_COLLECTIVE=nccl NCU_OUT=gpurun_out/r02_lnlike_n${N}_ncu.csv timeout -k 10 150 $TR --master-port 29519 --no-python bash tools/ncu_rank0.sh --gpus $N --steps 12 --warmup 3 --no-samplers --no-configs --no-cpu-baseline > gpurun_out/r2q_ncu_n${N}.log 2>&1; echo "rc=$?"
-grep -c lnlike_kernel gpurun_out/r02_lnlike_n${N}_ncu.csv; tail -3 gpurun_out/r2q_ncu_n${N}.log | cut -c1-200
+# (A) rank 0 of the bench under ncu with the NCCL collective (tools/ncu_rank0.sh) stalls after NCCL's start-up at
+# N = 2 (twice, killed by timeout: gpurun_out/r2_ncu_n2.log, r2q_ncu_n2.log), so the counters come from (B).
