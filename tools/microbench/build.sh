@@ -7,3 +7,4 @@ nvcc -O3 -std=c++17 $ARCH -o dispatch dispatch.cu
 nvcc -O3 -std=c++17 $ARCH -o operands operands.cu
 nvcc -O3 -std=c++17 $ARCH -DNEWTON=2 -o seeds2 seeds.cu
 nvcc -O3 -std=c++17 $ARCH -DNEWTON=3 -o seeds3 seeds.cu
+nvcc -O3 -std=c++17 $ARCH -o dmma dmma.cu
