@@ -58,10 +58,16 @@ enum {
 #define MCD_MAX_THETA 16       /* free parameters per walker (the largest shipped config has 11) */
 
 /* Arithmetic variant of the kernels.
- *   FAST : division-free restructuring, MUFU-seeded Newton reciprocals, logs taken of running
- *          products; FP64 throughout (default).
- *   PLAIN: the same per-star formulas with the compiler's div / sqrt / log / exp; kept to
- *          A/B the restructuring on the device. */
+ *   FAST : division-free restructuring, MUFU-seeded Newton reciprocals (quadratic steps, 1.3e-12
+ *          per term), logs taken of running products, table-driven exponentials in the mixture
+ *          variants (6.5e-12 per term, zero mean); FP64 throughout (default).  lnprob agrees with
+ *          the reference's formulas to ~2e-14 relative on the BASELINE configurations (tolerance of
+ *          the path: 1e-9).  Range: the combined variance verr^2 + sigma^2 of every star must lie
+ *          within 2^+-250 (1e-75 .. 1e75 km^2/s^2) -- the kernels multiply four of them before
+ *          folding the exponent; beyond that the result is NaN (never a wrong finite number).
+ *   PLAIN: the same per-star formulas with the compiler's div / sqrt / log / exp, no range limit
+ *          beyond the reference's own; kept to A/B the restructuring on the device and for the
+ *          per-star entry points. */
 enum { MCD_MATH_FAST = 0, MCD_MATH_PLAIN = 1 };
 
 /* What mcd_pack_create() compiles: a model, its parameter routing and the star columns.
@@ -138,7 +144,14 @@ int mcd_lnlike(mcd_handle *h, const double *theta_host, int32_t n_walkers, doubl
 int mcd_lnlike_device(mcd_handle *h, const double *theta_dev, int32_t n_walkers, double *out_dev, void *stream);
 
 /* lnprob = box prior + lnlike with exact -inf for rejected walkers: Runner.lnprob
- * (analysis/runner.py:288-306) with Runner.lnprior (runner.py:182-217) fused in. */
+ * (analysis/runner.py:288-306) with Runner.lnprior (runner.py:182-217) fused in.
+ * Host-buffer entry points block until the result is in out_host.  Calls of <= 384 theta values carry
+ * theta inside the kernel arguments; larger ones stage it through pinned memory and replay copy-in ->
+ * kernel as one CUDA graph from the third call of a shape on.  Either way the kernel writes the result
+ * and a completion flag straight into pinned memory (no copy-out, no stream synchronisation).
+ * Environment overrides for tests and A/B runs: MCD_HOST_CALL=graph (always the staged path) | sync
+ * (staged path with copy-out node and stream synchronisation), MCD_GEOMETRY=<tile>,<tiles per CTA>,
+ * MCD_XCHG=flags (cross-GPU exchange with flags + fences instead of self-validating words). */
 int mcd_lnprob(mcd_handle *h, const double *theta_host, int32_t n_walkers, double *out_host);
 int mcd_lnprob_device(mcd_handle *h, const double *theta_dev, int32_t n_walkers, double *out_dev, void *stream);
 
