@@ -369,6 +369,9 @@ def measured_samplers(args, world, device, model, like, theta_host, n_steps):
         if like.fused:
             dev = like.device_sampler(args.walkers, seed=1)
             dev.run_mcmc(theta_host, 3, store=False)
+            # the engine alone (graph captured, nothing stored), then a run as a user makes it: chain stored,
+            # which allocates the chain and re-captures the graph once
+            out['device_steady_state'] = n_steps / timed(lambda: dev.run_mcmc(None, n_steps, store=False))
             out['device'] = n_steps / timed(lambda: dev.run_mcmc(None, n_steps))
             dev.close()
         host = samplers.HostEnsembleSampler(args.walkers, theta_host.shape[1], like.lnprob, seed=1)
