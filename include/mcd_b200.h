@@ -147,8 +147,9 @@ int mcd_lnlike_device(mcd_handle *h, const double *theta_dev, int32_t n_walkers,
  * (analysis/runner.py:288-306) with Runner.lnprior (runner.py:182-217) fused in.
  * Host-buffer entry points block until the result is in out_host.  Calls of <= 384 theta values carry
  * theta inside the kernel arguments; larger ones stage it through pinned memory and replay copy-in ->
- * kernel as one CUDA graph from the third call of a shape on.  Either way the kernel writes the result
- * and a completion flag straight into pinned memory (no copy-out, no stream synchronisation).
+ * kernel as one CUDA graph from the third call of a shape on.  Either way the kernel writes every walker's
+ * result straight into pinned memory as two self-validating words (half of the double + the call's tag
+ * each), which the host polls: no copy-out, no fence or flag on the device, no stream synchronisation.
  * Environment overrides for tests and A/B runs: MCD_HOST_CALL=graph (always the staged path) | sync
  * (staged path with copy-out node and stream synchronisation), MCD_GEOMETRY=<tile>,<tiles per CTA>,
  * MCD_XCHG=flags (cross-GPU exchange with flags + fences instead of self-validating words). */

@@ -76,9 +76,7 @@ struct mcd_handle {
     Geometry geometry[4];
     int geometry_next = 0;
     // inline host-buffer calls: completion flag in pinned memory, counter of finished walker groups on the device
-    unsigned long long *flag_pin = nullptr;
-    unsigned long long host_seq = 0;
-    unsigned int *done_counter = nullptr;
+    unsigned long long host_seq = 0;            // host-buffer calls: sequence number, its low 32 bits tag the result words
     double *star_dev = nullptr;    // [n] scratch of the per-star entry point
     cudaStream_t stream = nullptr;
     int sm_count = 0, blocks_per_sm = 1;
@@ -216,8 +214,6 @@ extern "C" void mcd_destroy(mcd_handle *h) {
     cudaFree(h->theta_dev);
     cudaFree(h->out_dev);
     cudaFree(h->star_dev);
-    cudaFree(h->done_counter);
-    cudaFreeHost(h->flag_pin);
     cudaFree(h->xchg_status);
     if (h->order_event) cudaEventDestroy(h->order_event);
     cudaFreeHost(h->theta_pin);
@@ -590,17 +586,15 @@ static int launch(mcd_handle *h, const double *theta_dev, int n_walkers, double 
         }
     }
     if (inline_theta) {
-        // theta rides in the kernel arguments, `out_dev` is pinned host memory, completion is flagged there
+        // theta rides in the kernel arguments, the result goes into pinned host memory as tagged words
         p.theta = nullptr;
-        p.host_flag = h->flag_pin;
-        p.host_seq = h->host_seq;
-        p.done_counter = h->done_counter;
+        p.host_words = reinterpret_cast<unsigned long long *>(h->out_pin);
+        p.host_tag = (unsigned int)h->host_seq;
     }
     if (host_seq_dev) {
-        // graph-replayed host call: `out_dev` is pinned host memory, the sequence number arrives with theta
-        p.host_flag = h->flag_pin;
+        // graph-replayed host call: the same, with the sequence number arriving in device memory beside theta
+        p.host_words = reinterpret_cast<unsigned long long *>(h->out_pin);
         p.host_seq_ptr = host_seq_dev;
-        p.done_counter = h->done_counter;
     }
     MCD_CUDA(launch_lnlike(h->var, p, stream, inline_theta));
     h->info.last_grid_x = p.n_chunks;
@@ -631,55 +625,62 @@ static int ensure_staging(mcd_handle *h, size_t theta_doubles, size_t out_double
         h->out_cap = 0;
         const size_t cap = std::max<size_t>(out_doubles, 1024);
         MCD_CUDA(cudaMalloc(&h->out_dev, sizeof(double) * cap));
-        MCD_CUDA(cudaMallocHost(&h->out_pin, sizeof(double) * cap));
+        // pinned: [0, 2 cap) tagged result words of the flagged paths, [2 cap, 3 cap) plain doubles of the copy-out path
+        MCD_CUDA(cudaMallocHost(&h->out_pin, sizeof(double) * 3 * cap));
+        memset(h->out_pin, 0, sizeof(double) * 3 * cap);
         h->out_cap = cap;
     }
     return 0;
 }
 
-// Small calls: ONE kernel launch, nothing else.  theta is copied into the kernel's argument block, the kernel
-// writes the result into pinned host memory and its last walker group stores the call's sequence number into a
-// pinned flag after a system-scope fence; the host spins on that flag (a stream synchronisation costs more than
-// the kernel on these sizes) and falls back to waiting on the stream when the kernel is a long one.
-static int ensure_flag(mcd_handle *h) {
-    if (!h->flag_pin) {
-        MCD_CUDA(cudaMallocHost(&h->flag_pin, sizeof(unsigned long long)));
-        *h->flag_pin = 0ull;
-        MCD_CUDA(cudaMalloc(&h->done_counter, sizeof(unsigned int)));
-        MCD_CUDA(cudaMemset(h->done_counter, 0, sizeof(unsigned int)));
-    }
-    return 0;
+// Small calls: ONE kernel launch, nothing else.  theta is copied into the kernel's argument block and the kernel
+// writes every walker's result into pinned host memory as two self-validating words (half of the double plus the
+// call's 32-bit tag each, one 16-byte store): no fence, no counter, no flag on the device.  The host polls the rows
+// (a stream synchronisation costs more than the kernel on these sizes) and falls back to waiting on the stream
+// when the kernel is a long one.
+static unsigned long long next_host_seq(mcd_handle *h) {
+    h->host_seq += 1;
+    if ((unsigned int)h->host_seq == 0u) h->host_seq += 1;       // tag 0 is what a fresh buffer holds
+    return h->host_seq;
 }
 
-// spin on the pinned completion flag until the kernel of call `want` has published its result
-static int wait_for_flag(mcd_handle *h, unsigned long long want) {
-    volatile unsigned long long *flag = h->flag_pin;
-    bool seen = false;
-    for (int spin = 0; spin < 200000; ++spin) {            // ~100 us of polling, then block on the stream
-        if (*flag == want) { seen = true; break; }
+// collect the rows of call `seq` from the tagged words into out_host
+static int wait_for_words(mcd_handle *h, unsigned long long seq, size_t rows, double *out_host) {
+    const volatile unsigned long long *w = reinterpret_cast<const volatile unsigned long long *>(h->out_pin);
+    const unsigned long long tag = (unsigned long long)(unsigned int)seq;
+    long long budget = 200000;                             // ~100 us of polling, then block on the stream
+    bool synced = false;
+    for (size_t i = 0; i < rows; ++i) {
+        unsigned long long a, b;
+        while (true) {
+            a = w[2 * i];
+            b = w[2 * i + 1];
+            if ((a >> 32) == tag && (b >> 32) == tag) break;
+            if (--budget > 0) {
 #if defined(__x86_64__)
-        __builtin_ia32_pause();
+                __builtin_ia32_pause();
 #endif
+                continue;
+            }
+            if (synced) return fail(-2, "the likelihood kernel finished without publishing its result");
+            MCD_CUDA(cudaStreamSynchronize(h->stream));
+            synced = true;
+            budget = 1000;
+        }
+        const unsigned long long bits = (a & 0xffffffffULL) | (b << 32);
+        memcpy(&out_host[i], &bits, sizeof(double));
     }
-    if (!seen) {
-        MCD_CUDA(cudaStreamSynchronize(h->stream));
-        if (*flag != want) return fail(-2, "the likelihood kernel finished without publishing its result");
-    }
-    __atomic_thread_fence(__ATOMIC_ACQUIRE);
     return 0;
 }
 
 static int host_call_inline(mcd_handle *h, const double *theta_host, int n_walkers, double *out_host, int apply_prior,
                             size_t rows, size_t nt) {
     if (int rc = ensure_staging(h, 1, rows)) return rc;
-    if (int rc = ensure_flag(h)) return rc;
     ThetaBlock block;
     if (nt) memcpy(block.v, theta_host, sizeof(double) * nt);
-    h->host_seq += 1;
-    if (int rc = launch(h, nullptr, n_walkers, h->out_pin, apply_prior, h->stream, false, nullptr, nullptr, &block)) return rc;
-    if (int rc = wait_for_flag(h, h->host_seq)) return rc;
-    memcpy(out_host, h->out_pin, sizeof(double) * rows);
-    return 0;
+    const unsigned long long seq = next_host_seq(h);
+    if (int rc = launch(h, nullptr, n_walkers, h->out_dev, apply_prior, h->stream, false, nullptr, nullptr, &block)) return rc;
+    return wait_for_words(h, seq, rows, out_host);
 }
 
 static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, double *out_host, int apply_prior,
@@ -701,14 +702,12 @@ static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, dou
     }
     // Two words after theta travel to the device inside the same copy, so that the replayed graph (whose kernel
     // arguments are frozen) sees fresh values on every call: the exchange epoch (identical on all ranks) and
-    // this handle's call sequence number, which the kernel stores into the pinned completion flag once its
-    // result -- written straight into pinned host memory -- is complete.  The graph is copy-in -> kernel: no
-    // copy-out node, no stream synchronisation (MCD_HOST_CALL=sync keeps both, for A/B).
+    // this handle's call sequence number, whose low 32 bits tag the result words the kernel writes straight into
+    // pinned host memory.  The graph is copy-in -> kernel: no copy-out node, no stream synchronisation
+    // (MCD_HOST_CALL=sync keeps both, for A/B).
     const char *mode = getenv("MCD_HOST_CALL");
-    const bool flagged = !(mode && mode[0] == 's') && h->n_segments == 1;
+    const bool flagged = !(mode && mode[0] == 's');
     if (int rc = ensure_staging(h, nt + 2, rows)) return rc;
-    if (flagged)
-        if (int rc = ensure_flag(h)) return rc;
     if (nt) memcpy(h->theta_pin, theta_host, sizeof(double) * nt);
     const unsigned long long *epoch_dev = nullptr, *seq_dev = nullptr;
     unsigned long long words[2] = {0ull, 0ull};
@@ -717,7 +716,7 @@ static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, dou
         epoch_dev = reinterpret_cast<const unsigned long long *>(h->theta_dev + nt);
     }
     if (flagged) {
-        words[1] = ++h->host_seq;
+        words[1] = next_host_seq(h);
         seq_dev = reinterpret_cast<const unsigned long long *>(h->theta_dev + nt + 1);
     }
     memcpy(h->theta_pin + nt, words, sizeof(words));
@@ -742,11 +741,11 @@ static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, dou
     if (int rc = order_on_stream(h, h->stream)) return rc;
     auto enqueue = [&]() -> int {
         MCD_CUDA(cudaMemcpyAsync(h->theta_dev, h->theta_pin, sizeof(double) * n_copy, cudaMemcpyHostToDevice, h->stream));
-        if (int rc = launch(h, h->theta_dev, n_walkers, flagged ? h->out_pin : h->out_dev, apply_prior, h->stream, exchange != 0,
-                            nullptr, epoch_dev, nullptr, seq_dev))
+        if (int rc = launch(h, h->theta_dev, n_walkers, h->out_dev, apply_prior, h->stream, exchange != 0, nullptr, epoch_dev,
+                            nullptr, seq_dev))
             return rc;
         if (!flagged)
-            MCD_CUDA(cudaMemcpyAsync(h->out_pin, h->out_dev, sizeof(double) * rows, cudaMemcpyDeviceToHost, h->stream));
+            MCD_CUDA(cudaMemcpyAsync(h->out_pin + 2 * h->out_cap, h->out_dev, sizeof(double) * rows, cudaMemcpyDeviceToHost, h->stream));
         return 0;
     };
     if (slot && slot->exec) {
@@ -773,11 +772,11 @@ static int host_call(mcd_handle *h, const double *theta_host, int n_walkers, dou
     }
     if (slot) slot->seen += slot->seen < 2 ? 1 : 0;
     if (flagged) {
-        if (int rc = wait_for_flag(h, words[1])) return rc;
+        if (int rc = wait_for_words(h, words[1], rows, out_host)) return rc;
     } else {
         MCD_CUDA(cudaStreamSynchronize(h->stream));
+        memcpy(out_host, h->out_pin + 2 * h->out_cap, sizeof(double) * rows);
     }
-    memcpy(out_host, h->out_pin, sizeof(double) * rows);
     if (exchange) {
         // a peer that never published turns the sums into NaN after the kernel's time limit: say so
         for (size_t i = 0; i < rows; ++i)

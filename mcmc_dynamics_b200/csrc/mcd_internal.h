@@ -123,12 +123,12 @@ struct LaunchParams {
     double *partials2;        // [n_segments][n_super][n_walkers]
     unsigned int *counters;   // [n_segments][n_groups][n_super + 1], zero between launches
     double *out;              // [n_segments][n_walkers]
-    // inline host-buffer call (theta == nullptr: read the ThetaBlock argument): `out` is pinned host memory,
-    // the last walker group to finish stores host_seq into *host_flag (pinned) after a system-scope fence
-    unsigned long long *host_flag;
-    unsigned long long host_seq;
+    // Host-buffer calls: the result goes straight into pinned host memory as self-validating words -- row r is
+    // {low half | tag << 32, high half | tag << 32} at host_words[2 r], one 16-byte store per walker, no fence,
+    // no counter, no flag: the host polls the rows until both tags of each carry the call's tag.
+    unsigned long long *host_words;           // non-null: host-buffer call (`out` is not written)
+    unsigned int host_tag;                    // low 32 bits of the call's sequence number, never 0
     const unsigned long long *host_seq_ptr;   // non-null: the sequence number is read from device memory (graph replays)
-    unsigned int *done_counter;   // device: walker groups finished so far, zero between launches
     int slot[MCD_NPARAM];
     double fixed_scaled[MCD_NPARAM];   // fixed value already multiplied by its unit scale
     double scale[MCD_NPARAM];

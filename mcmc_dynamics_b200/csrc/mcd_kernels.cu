@@ -897,6 +897,10 @@ __device__ __noinline__ void finish_walker_group(const LaunchParams &P, int seg,
     __syncthreads();
     MCD_KSTAMP(stamps, 7);
     if (!*s_last) return;
+    // words of a graph-replayed call that live in device memory (refreshed by the copy that brought theta): asked
+    // for here, so that their round trip to L2 overlaps the gathers instead of following them
+    const unsigned long long epoch_word = (P.xchg_world > 1 && P.xchg_epoch_ptr) ? *P.xchg_epoch_ptr : P.xchg_epoch;
+    const unsigned int host_tag = (P.host_words && P.host_seq_ptr) ? (unsigned int)*P.host_seq_ptr : P.host_tag;
     const double level1 = gather_rows(P.partials + (size_t)seg * P.n_chunks * P.n_walkers, c_begin, c_end, P, w, red);
     if (tid == 0) cnt[sup] = 0u;
     MCD_KSTAMP(stamps, 8);
@@ -921,7 +925,7 @@ __device__ __noinline__ void finish_walker_group(const LaunchParams &P, int seg,
     if (P.xchg_world > 1) {
         // host-counted calls: the epoch is a kernel argument, or -- when the launch is replayed from a
         // CUDA graph -- a word in device memory refreshed by the copy that brought theta
-        unsigned long long epoch = P.xchg_epoch_ptr ? *P.xchg_epoch_ptr : P.xchg_epoch;
+        unsigned long long epoch = epoch_word;
         int slot = (int)(epoch & 1ull);
         if constexpr (FUSE) {
             // sampler half-steps: the tag comes from the device-side step counter plus the ensemble's
@@ -945,21 +949,18 @@ __device__ __noinline__ void finish_walker_group(const LaunchParams &P, int seg,
         // and the other half is read-only during this half-step.
         if (owner) accept_proposal(P, seg, w, total);
     } else {
-        if (owner) P.out[(size_t)seg * P.n_walkers + w] = total;
-        if (P.host_flag) {
-            // `out` is pinned host memory: order this CTA's results before the flag the host spins on.  The
-            // last walker group (of the last segment) to get here publishes it.
-            if (owner) __threadfence_system();
-            __syncthreads();
-            if (tid == 0) {
-                const unsigned int expected = (unsigned int)(P.n_groups * max(1, P.n_segments));
-                if (atomicAdd(P.done_counter, 1u) == expected - 1u) {
-                    *P.done_counter = 0u;
-                    __threadfence_system();
-                    *reinterpret_cast<volatile unsigned long long *>(P.host_flag) =
-                        P.host_seq_ptr ? *P.host_seq_ptr : P.host_seq;
-                }
+        if (P.host_words) {
+            // pinned host memory, self-validating words (see LaunchParams): nothing to order, nothing to count
+            if (owner) {
+                const unsigned int tag = host_tag;
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(total);
+                const unsigned long long t = (unsigned long long)tag << 32;
+                asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(P.host_words + 2 * ((size_t)seg * P.n_walkers + w)),
+                             "l"((bits & 0xffffffffULL) | t), "l"((bits >> 32) | t)
+                             : "memory");
             }
+        } else if (owner) {
+            P.out[(size_t)seg * P.n_walkers + w] = total;
         }
     }
 #ifdef MCD_KERNEL_PROFILE
