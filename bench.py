@@ -653,8 +653,8 @@ def gpu_run(args):
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(2 * half * info['n_theta'] * 8),
                 'd2h_bytes_per_step': int(2 * half * 8), 'ms_per_step': 1e3 * e2e_s / args.steps,
                 'api': 'ModelFit.lnprob(theta ndarray) -> C ABI mcd_lnprob (host buffers)' if world == 1 else
-                       ('ShardedLikelihood.lnprob(theta ndarray) -> C ABI mcd_lnprob_allreduce (host buffers; copy-in, '
-                        'shard kernel + in-kernel exchange, copy-out as one CUDA graph)' if like.fused else
+                       ('ShardedLikelihood.lnprob(theta ndarray) -> C ABI mcd_lnprob_allreduce (host buffers; copy-in -> '
+                        'shard kernel + in-kernel exchange as one CUDA graph, results polled in pinned memory)' if like.fused else
                         'ShardedLikelihood.lnprob(theta ndarray): pinned H2D, shard kernel, NCCL all_reduce, D2H')},
         'gpu_launches': int(launches),
         'clocks': clock_summary,

@@ -173,9 +173,10 @@ int mcd_exchange_bytes(int32_t world, int32_t max_walkers, int64_t *bytes_out);
 int mcd_exchange_attach(mcd_handle *h, int32_t rank, int32_t world, const uint64_t *peer_buffers, int32_t max_walkers);
 int mcd_lnprob_allreduce_device(mcd_handle *h, const double *theta_dev, int32_t n_walkers, double *out_dev, void *stream);
 /* The same with HOST buffers -- what a host sampler calls per half-ensemble on every rank (the
- * vectorised log_prob_fn of analysis/runner.py:403 on a star-sharded catalogue): pinned copy-in, shard
- * kernel with the exchange in its tail, copy-out, replayed as ONE CUDA graph from the third call of a
- * shape on (the call's exchange tag travels to the device inside the theta copy).  Returns -5 if a peer
+ * vectorised log_prob_fn of analysis/runner.py:403 on a star-sharded catalogue): pinned copy-in and the
+ * shard kernel with the exchange in its tail, replayed as ONE CUDA graph from the third call of a shape on
+ * (the call's exchange tag travels to the device inside the theta copy); the kernel writes the results
+ * into pinned memory as self-validating words, which the host polls.  Returns -5 if a peer
  * never published its sums (the values are NaN then). */
 int mcd_lnprob_allreduce(mcd_handle *h, const double *theta_host, int32_t n_walkers, double *out_host);
 /* After the caller synchronised its stream: 0, or -5 (and a message) if a kernel launched through one of

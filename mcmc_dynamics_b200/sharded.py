@@ -118,8 +118,8 @@ class ShardedLikelihood(object):
 
     def lnprob(self, theta):
         """Host array in, host array out (what a host sampler calls on every rank).  Fused mode: ONE C-ABI
-        call, ``mcd_lnprob_allreduce`` -- pinned copy-in, shard kernel with the cross-GPU exchange in its
-        tail, copy-out, replayed as one CUDA graph.  NCCL mode: pinned staging, H2D, shard kernel,
+        call, ``mcd_lnprob_allreduce`` -- pinned copy-in and the shard kernel with the cross-GPU exchange in its
+        tail replayed as one CUDA graph, results written by the kernel into pinned memory.  NCCL mode: pinned staging, H2D, shard kernel,
         ``all_reduce``, D2H through torch."""
         torch = self._torch
         theta = np.ascontiguousarray(theta, dtype=np.float64)
