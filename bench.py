@@ -155,13 +155,14 @@ def cpu_reference_run(args, steps, warmup):
         from oracle import c_port as cport
         if cport.available():
             co = cport.COracle(_CPU_ORACLE)
+            c_threads = cport.set_threads(cores)           # torchrun exports OMP_NUM_THREADS=1
             co.lnprob_many(theta[:cores])
             t0 = time.perf_counter()
             co.lnprob_many(theta)
             c_all = per_step * n_sample / (time.perf_counter() - t0)
             t0 = time.perf_counter()
             co.lnprob_many(theta[:1])
-            c_port = {'value': c_all, 'unit': UNIT, 'threads': cores,
+            c_port = {'value': c_all, 'unit': UNIT, 'threads': c_threads,
                       'one_walker_call_value': n_sample / (time.perf_counter() - t0),
                       'what': 'oracle/oracle_c.c (gcc -O2 -fopenmp), literal C restatement incl. per-call geometry'}
     except Exception as exc:                                # the C port is optional

@@ -37,8 +37,15 @@ def load():
         lib.oracle_gaussian_background.argtypes = [ctypes.c_long, dp, dp, ctypes.c_double, ctypes.c_double, dp]
         lib.oracle_single_stars_background.restype = None
         lib.oracle_single_stars_background.argtypes = [ctypes.c_long, dp, ctypes.c_long, dp, dp, ctypes.c_double, dp]
+        lib.oracle_set_threads.restype = ctypes.c_int
+        lib.oracle_set_threads.argtypes = [ctypes.c_int]
         _lib = lib
     return _lib
+
+
+def set_threads(n):
+    """OpenMP threads of the walker loops (0: leave as is); returns the number in force."""
+    return int(load().oracle_set_threads(int(n)))
 
 
 def _ptr(arr):

@@ -15,6 +15,21 @@
  */
 #include <math.h>
 #include <stddef.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* threads of the walker loops; returns what is in force (torchrun exports OMP_NUM_THREADS=1, bench.py
+ * asks for the cores it reports) */
+int oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 #define TWO_PI 6.283185307179586476925286766559
 #define DEG (3.14159265358979323846264338327950288 / 180.0)
