@@ -13,6 +13,7 @@ uses (``run_mcmc``, ``chain``, ``lnprobability``, ``iteration``, ``acceptance_fr
   accept/reject on the GPU (``csrc/mcd_sampler.cu``), one CUDA graph launch per step.
 """
 import ctypes
+import math
 
 import numpy as np
 
@@ -72,7 +73,10 @@ class HostEnsembleSampler(object):
     # -- sampling -----------------------------------------------------------------------------
     def compute_log_prob(self, coords):
         coords = np.asarray(coords, dtype=np.float64)
-        if not np.isfinite(coords).all():             # one pass in the common case, emcee's messages otherwise
+        # one dot product in the common case (a finite sum of squares proves every entry finite), emcee's
+        # checks and messages otherwise
+        flat = coords.reshape(-1)
+        if not math.isfinite(np.dot(flat, flat)) and not np.isfinite(coords).all():
             if np.any(np.isinf(coords)):
                 raise ValueError("At least one parameter value was infinite")
             raise ValueError("At least one parameter value was NaN")
@@ -81,7 +85,8 @@ class HostEnsembleSampler(object):
             log_prob = np.asarray(self.log_prob_fn(coords), dtype=np.float64)
         else:
             log_prob = np.array([float(self.log_prob_fn(row)) for row in coords], dtype=np.float64)
-        if np.isnan(log_prob).any():
+        norm = np.dot(log_prob, log_prob)                 # -inf entries are legal and give +inf; only NaN gives NaN
+        if norm != norm and np.isnan(log_prob).any():
             raise ValueError("Probability function returned NaN")
         return log_prob
 
@@ -98,31 +103,53 @@ class HostEnsembleSampler(object):
         if np.any(np.isnan(log_prob)):
             raise ValueError("The initial log_prob was NaN")
 
+        # emcee's RedBlueMove / StretchMove(a): shuffle the red/blue labels, then per half draw z, a partner from
+        # the other half, and the acceptance threshold.  Written with index arrays, in-place arithmetic and masked
+        # copies instead of boolean-mask indexing: on the small configurations the NumPy calls of this loop, not
+        # the likelihood launches, set the pace (profiles/r02_configs.md).  The partner index is
+        # floor(u * n_other) of one uniform draw rather than RandomState.randint (4 us instead of 9 per half).
         rng = self._random
-        for _ in range(int(nsteps)):
-            inds = np.arange(self.nwalkers) % 2
-            rng.shuffle(inds)
-            for split in range(2):
-                s_mask = inds == split
-                s = coords[s_mask]
-                c = coords[~s_mask]
-                ns, nc = len(s), len(c)
-                zz = ((self.a - 1.0) * rng.rand(ns) + 1) ** 2.0 / self.a
-                factors = (self.ndim - 1.0) * np.log(zz)
-                rint = rng.randint(nc, size=(ns,))
-                q = c[rint] - (c[rint] - s) * zz[:, None]
-                new_log_prob = self.compute_log_prob(q)
-                with np.errstate(invalid='ignore'):
-                    lnpdiff = factors + new_log_prob - log_prob[s_mask]
-                accepted = lnpdiff > np.log(rng.rand(ns))
-                idx = np.flatnonzero(s_mask)[accepted]
-                coords[idx] = q[accepted]
-                log_prob[idx] = new_log_prob[accepted]
-                self.naccepted[idx] += 1
-            self.iteration += 1
-            if store:
-                self._chain.append(coords.copy())
-                self._lnprob.append(log_prob.copy())
+        a_minus_1, inv_a, dim_minus_1 = self.a - 1.0, 1.0 / self.a, self.ndim - 1.0
+        parity = np.arange(self.nwalkers) % 2
+        naccepted = self.naccepted
+        compute, uniform = self.compute_log_prob, rng.random_sample
+        log, nonzero, take, copyto, intp = np.log, np.flatnonzero, np.take, np.copyto, np.intp
+        with np.errstate(invalid='ignore', divide='ignore'):
+            for _ in range(int(nsteps)):
+                inds = parity.copy()
+                rng.shuffle(inds)
+                halves = (nonzero(inds == 0), nonzero(inds))
+                for split in (0, 1):
+                    i_s, i_c = halves[split], halves[1 - split]
+                    ns = i_s.size
+                    s = take(coords, i_s, axis=0)
+                    zz = uniform(ns)
+                    zz *= a_minus_1
+                    zz += 1.0
+                    zz *= zz
+                    zz *= inv_a
+                    pick = uniform(ns)
+                    pick *= i_c.size
+                    partner = take(coords, take(i_c, pick.astype(intp)), axis=0)
+                    q = partner - s
+                    q *= zz[:, None]
+                    np.subtract(partner, q, out=q)                     # c_j - (c_j - s) z
+                    new_log_prob = compute(q)
+                    old_log_prob = take(log_prob, i_s)
+                    lnpdiff = log(zz)
+                    lnpdiff *= dim_minus_1
+                    lnpdiff += new_log_prob
+                    lnpdiff -= old_log_prob
+                    accepted = lnpdiff > log(uniform(ns))
+                    copyto(s, q, where=accepted[:, None])
+                    copyto(old_log_prob, new_log_prob, where=accepted)
+                    coords[i_s] = s
+                    log_prob[i_s] = old_log_prob
+                    naccepted[i_s] += accepted
+                self.iteration += 1
+                if store:
+                    self._chain.append(coords.copy())
+                    self._lnprob.append(log_prob.copy())
         return coords, log_prob, rng.get_state()
 
 

@@ -253,6 +253,52 @@ def test_host_sampler_recovers_a_gaussian():
         s.compute_log_prob(np.full((2, 3), np.nan))
 
 
+def test_host_sampler_error_semantics_and_resume():
+    """emcee's contract as ``analysis/runner.py:416-419`` relies on it: ``-inf`` is a legal value (never
+    accepted), NaN raises, non-finite coordinates raise with emcee's messages, and a run continued with the
+    returned ``(pos, log_prob, random_state)`` equals one uninterrupted run."""
+    def lnprob(theta):
+        out = -0.5 * np.sum(theta ** 2, axis=1)
+        out[theta[:, 0] > 1.0] = -np.inf                          # hard wall: proposals beyond it are rejected
+        return out
+    start = 0.3 * np.random.default_rng(1).standard_normal((12, 2)) - 0.5
+    whole = sampler.HostEnsembleSampler(12, 2, lnprob, seed=5)
+    whole.run_mcmc(start, 400)
+    assert whole.chain[:, :, 0].max() <= 1.0 and np.isfinite(whole.lnprobability).all()
+    assert whole.naccepted.sum() > 0 and np.all(whole.naccepted <= 400)
+
+    parts = sampler.HostEnsembleSampler(12, 2, lnprob, seed=5)
+    pos, lnp, state = parts.run_mcmc(start, 150)
+    parts.run_mcmc(pos, 250, log_prob0=lnp, rstate0=state)
+    assert np.array_equal(parts.chain, whole.chain) and np.array_equal(parts.lnprobability, whole.lnprobability)
+    assert np.array_equal(parts.naccepted, whole.naccepted)
+    assert parts.n_log_prob_calls == whole.n_log_prob_calls == 1 + 2 * 400
+
+    odd = sampler.HostEnsembleSampler(13, 2, lnprob, seed=5)     # halves of 7 and 6 walkers
+    odd.run_mcmc(np.vstack([start, [[-0.2, 0.1]]]), 50)
+    assert odd.chain.shape == (13, 50, 2)
+
+    def sometimes_nan(theta):
+        out = lnprob(theta)
+        if sometimes_nan.armed:
+            out[-1] = np.nan
+        return out
+    sometimes_nan.armed = False
+    bad = sampler.HostEnsembleSampler(12, 2, sometimes_nan, seed=5)
+    bad.run_mcmc(start, 3)
+    sometimes_nan.armed = True
+    with pytest.raises(ValueError, match='returned NaN'):
+        bad.run_mcmc(start, 3)
+    with pytest.raises(ValueError, match='infinite'):
+        whole.compute_log_prob(np.array([[0.0, np.inf]]))
+    with pytest.raises(ValueError, match='NaN'):
+        whole.compute_log_prob(np.array([[0.0, np.nan]]))
+    huge = np.array([[1e200, -1e200]])                            # squares overflow, the entries are finite: accepted
+    assert whole.compute_log_prob(huge).shape == (1,)
+    with pytest.raises(ValueError, match='initial log_prob was NaN'):
+        sampler.HostEnsembleSampler(12, 2, lnprob, seed=5).run_mcmc(start, 1, log_prob0=np.full(12, np.nan))
+
+
 def test_radial_bins_partition():
     data, truth = synthetic.mock_cluster(600, seed=2)
     data.make_radial_bins(truth['ra_center'], truth['dec_center'], nstars=50, dlogr=0.1)
