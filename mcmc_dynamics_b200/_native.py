@@ -149,5 +149,17 @@ def as_double_ptr(array):
     return array.ctypes.data_as(_c_double_p)
 
 
+_addressof, _c_char = ctypes.addressof, ctypes.c_char
+
+
+def address(array):
+    """Address of a C-contiguous ndarray's data for the raw-address entry points: through the buffer protocol
+    (0.7 us) where the array is writable and not empty, ``ndarray.ctypes.data`` (2 us) otherwise."""
+    try:
+        return _addressof(_c_char.from_buffer(array))
+    except (TypeError, ValueError):
+        return array.ctypes.data
+
+
 def contiguous(values):
     return np.ascontiguousarray(values, dtype=np.float64)

@@ -210,13 +210,13 @@ class Runner(object):
         assert i == len(values), 'Not all parameters used.'
         return current_parameters
 
-    def _as_batch(self, values):
+    def _as_batch(self, values, packed=False):
+        """One vector or a batch -> ``([n, n_free] float64, was_one_vector)``.  ``packed=True``: ``pack()`` has
+        just run, so its cached count of sampled parameters is current (no second look at the edit stamps)."""
         values = np.asarray(values, dtype=np.float64)
         scalar = values.ndim == 1
         theta = values[None, :] if scalar else values
-        # number of sampled parameters: cached by pack() (refreshed whenever a parameter is edited)
-        n_free = self._n_free if self._packed_stamps is not None and self._packed_stamps[0] == pack.edit_stamps(
-            self.parameters) else self.n_fitted_parameters
+        n_free = self._n_free if packed else self.n_fitted_parameters
         assert theta.ndim == 2 and theta.shape[1] == n_free, 'Not all parameters used.'
         return theta, scalar
 
@@ -316,16 +316,16 @@ class Runner(object):
     def lnlike(self, values):
         """Log-likelihood without priors (``constant.py:113-154``, ``model.py:182-223`` and the
         background variants), for one parameter vector or a batch."""
-        theta, scalar = self._as_batch(values)
         packed = self.pack()
+        theta, scalar = self._as_batch(values, packed=True)
         out = packed.lnlike(self._device_theta(theta))
         return float(out[0]) if scalar else out
 
     def lnprob(self, values):
         """``analysis/runner.py:288-306``: box prior fused into the kernel; walkers outside the prior
         come back as exactly ``-inf`` without being evaluated."""
-        theta, scalar = self._as_batch(values)
         packed = self.pack()
+        theta, scalar = self._as_batch(values, packed=True)
         out = packed.lnprob(self._device_theta(theta))
         if self._expression_priors_present:           # refreshed by pack() whenever a parameter was edited
             extra = self._lnprior_batch(theta)

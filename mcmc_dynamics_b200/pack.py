@@ -210,7 +210,7 @@ class PackedModel(object):
         """Host buffers in, host buffer out: copy, one kernel launch, copy, synchronise."""
         theta, n_walkers, shape = self._theta(theta)
         out = np.empty(shape, dtype=np.float64)
-        rc = self._lib.mcd_lnprob(self.handle, theta.ctypes.data, n_walkers, out.ctypes.data)
+        rc = self._lib.mcd_lnprob(self.handle, _native.address(theta), n_walkers, _native.address(out))
         if rc != 0:
             _native.check(rc)
         return out
@@ -218,7 +218,7 @@ class PackedModel(object):
     def lnlike(self, theta):
         theta, n_walkers, shape = self._theta(theta)
         out = np.empty(shape, dtype=np.float64)
-        rc = self._lib.mcd_lnlike(self.handle, theta.ctypes.data, n_walkers, out.ctypes.data)
+        rc = self._lib.mcd_lnlike(self.handle, _native.address(theta), n_walkers, _native.address(out))
         if rc != 0:
             _native.check(rc)
         return out

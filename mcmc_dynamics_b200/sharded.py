@@ -129,7 +129,7 @@ class ShardedLikelihood(object):
             if p != packed.n_theta:
                 raise ValueError('theta must have shape (n_walkers, {0}), got {1}'.format(packed.n_theta, theta.shape))
             out = np.empty(n, dtype=np.float64)
-            rc = packed._lib.mcd_lnprob_allreduce(packed.handle, theta.ctypes.data, n, out.ctypes.data)
+            rc = packed._lib.mcd_lnprob_allreduce(packed.handle, _native.address(theta), n, _native.address(out))
             if rc != 0:
                 _native.check(rc)
             return out
