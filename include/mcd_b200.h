@@ -193,6 +193,15 @@ int mcd_lnlike_per_star_device(mcd_handle *h, const double *theta_dev, double *o
 int mcd_membership_per_star(mcd_handle *h, const double *theta_host, double *out_host /* [N] */);
 int mcd_membership_per_star_device(mcd_handle *h, const double *theta_dev, double *out_dev, void *stream);
 
+/* The model curves at the stars for ONE parameter vector: v_los[N] and sigma_los[N] in km/s, i.e. what
+ * <Model>.rotation_model / <Model>.dispersion_model return (constant.py:52-74,76-111; model.py:93-128,130-180),
+ * evaluated with library division / sqrt exactly as the per-star likelihood does.  theta as for mcd_lnlike
+ * (the free parameters of ONE walker); either output may be NULL. */
+int mcd_model_per_star(mcd_handle *h, const double *theta_host, double *v_los_host /* [N] */,
+                       double *sigma_los_host /* [N] */);
+int mcd_model_per_star_device(mcd_handle *h, const double *theta_dev, double *v_los_dev, double *sigma_los_dev,
+                              void *stream);
+
 /* Background precompute: SingleStars.__call__ (background/single_stars.py:42-77) without the
  * M x N intermediate.  v_bg[M], v[N], verr[N] are HOST arrays; out[N]. */
 int mcd_single_stars_lnlike(int32_t device, const double *v_bg, int64_t m, const double *v, const double *verr,

@@ -5,6 +5,7 @@
 background in velocity and the density prior ``m = density / (density + f_back)``.
 The arithmetic lives in ``csrc/mcd_kernels.cu``; these classes only choose the kernel variant.
 """
+import inspect
 import logging
 
 import numpy as np
@@ -33,6 +34,21 @@ class ConstantFit(Runner):
         if parameters is None:
             parameters = Parameters().load(self.parameters_file)
         super(ConstantFit, self).__init__(data=data, parameters=parameters, **kwargs)
+        # which parameters each curve takes (constant.py:49-50, model.py:90-91)
+        self.rotation_parameters = inspect.signature(self.rotation_model).parameters
+        self.dispersion_parameters = inspect.signature(self.dispersion_model).parameters
+
+    def dispersion_model(self, sigma_max, **kwargs):
+        """``constant.py:52-74``: the (constant) model dispersion at every star, km/s.  Evaluated on the GPU by
+        the per-star kernel, like everything else that touches the star columns."""
+        self._no_kwargs(self.__class__.__name__, 'dispersion_model', kwargs)
+        return self._model_curves('dispersion_model', {'sigma_max': sigma_max})[1]
+
+    def rotation_model(self, v_sys, v_maxx, v_maxy, ra_center, dec_center, **kwargs):
+        """``constant.py:76-111``: ``v_sys + v_max sin(theta_i - theta_0)`` at every star, km/s."""
+        self._no_kwargs(self.__class__.__name__, 'rotation_model', kwargs)
+        return self._model_curves('rotation_model', {'v_sys': v_sys, 'v_maxx': v_maxx, 'v_maxy': v_maxy,
+                                                     'ra_center': ra_center, 'dec_center': dec_center})[0]
 
 
 class ConstantFitGB(ConstantFit):

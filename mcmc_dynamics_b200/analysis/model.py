@@ -7,6 +7,7 @@ dispersion profile ``sigma_los = sigma_max / (1 + r^2 / a^2)^(1/4)`` (``model.py
 ``ModelFitConstantBackground`` (``model.py:513-687``) a fixed background likelihood column with the
 fitted fraction ``f_back``.
 """
+import inspect
 import logging
 
 import numpy as np
@@ -35,6 +36,28 @@ class ModelFit(Runner):
         if parameters is None:
             parameters = Parameters().load(self.parameters_file)
         super(ModelFit, self).__init__(data=data, parameters=parameters, **kwargs)
+        # which parameters each curve takes (constant.py:49-50, model.py:90-91)
+        self.rotation_parameters = inspect.signature(self.rotation_model).parameters
+        self.dispersion_parameters = inspect.signature(self.dispersion_model).parameters
+
+    def dispersion_model(self, sigma_max, ra_center, dec_center, a=1, **kwargs):
+        """``model.py:93-128``: ``sigma_max / (1 + r^2 / a^2)^(1/4)`` at every star, km/s (GPU, per-star kernel).
+        `a` without a unit is taken to be in the unit of the ``a`` parameter."""
+        self._no_kwargs(self.__class__.__name__, 'dispersion_model', kwargs)
+        return self._model_curves('dispersion_model', {'sigma_max': sigma_max, 'ra_center': ra_center,
+                                                       'dec_center': dec_center, 'a': a})[1]
+
+    def rotation_model(self, v_sys, v_maxx, v_maxy, ra_center, dec_center, r_peak=None, **kwargs):
+        """``model.py:130-180``: ``v_sys + 2 (v_max / r_peak) x_pa / (1 + (r / r_peak)^2)`` at every star, km/s.
+        ``r_peak=None`` takes the median distance of the stars from the centre, as the reference does
+        (``model.py:172-173``)."""
+        self._no_kwargs(self.__class__.__name__, 'rotation_model', kwargs)
+        if r_peak is None:
+            r_peak = self.data.compute_distances(ra_center, dec_center)
+            r_peak = u.Quantity(np.median(r_peak.value), r_peak.unit)
+        return self._model_curves('rotation_model', {'v_sys': v_sys, 'v_maxx': v_maxx, 'v_maxy': v_maxy,
+                                                     'ra_center': ra_center, 'dec_center': dec_center,
+                                                     'r_peak': r_peak})[0]
 
     def create_profiles(self, chains, n_burn, radii=None, filename=None):
         """Radial profiles of the rotation amplitude and the velocity dispersion implied by the

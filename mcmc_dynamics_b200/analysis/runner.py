@@ -11,6 +11,7 @@ There is no CPU implementation of the likelihood in this package.
 """
 import logging
 import pickle
+import warnings
 
 import numpy as np
 
@@ -333,6 +334,42 @@ class Runner(object):
                 out = np.where(np.isfinite(extra), out + extra, -np.inf)
         return float(out[0]) if scalar else out
 
+    def _model_curves(self, who, given):
+        """``(v_los, sigma_los)`` of every star in km/s for the parameter values handed to ``rotation_model`` /
+        ``dispersion_model``: one launch of the per-star kernel (``mcd_model_per_star``).  `given` maps
+        parameter names to quantities or plain numbers (taken to be in the parameter's own unit, as the
+        reference takes them); sampled parameters that the curve does not depend on keep their current value.
+        A parameter that is FIXED in this model lives in the packed columns (a fixed centre is folded into the
+        stored tangent-plane coordinates), so a value that differs from it cannot be honoured."""
+        packed = self.pack()
+        theta = np.empty(self._n_free, dtype=np.float64)
+        j = 0
+        for name, par in self.parameters.items():
+            value = given.get(name)
+            if value is not None:
+                value = float(u.strip(value, par.unit))
+            if par.fixed:
+                if name in self._derived or value is None or name not in self.MODEL_PARAMETERS:
+                    continue
+                if abs(value - par.value) > 1e-12 * max(1.0, abs(par.value)):
+                    raise ValueError(
+                        "{0}.{1}: '{2}' is fixed at {3} in this model and part of the packed star columns; free the "
+                        "parameter (or change its value in .parameters) to evaluate the model at {4}".format(
+                            self.__class__.__name__, who, name, par.value, value))
+            else:
+                if value is None:           # the requested curve does not depend on it: any sane number
+                    value = float(par.value) if par.value not in (None, 0) else 1.0
+                theta[j] = value
+                j += 1
+        v_los, sigma_los = packed.model_per_star(self._device_theta(theta[None, :])[0])
+        return u.Quantity(v_los, u.km_s), u.Quantity(sigma_los, u.km_s)
+
+    @staticmethod
+    def _no_kwargs(cls_name, who, kwargs):
+        if kwargs:              # constant.py:70-72,102-104; model.py:121-123,164-166
+            raise IOError('Unknown keyword argument(s) "{0}" for method {1}.{2}.'.format(
+                ', '.join(kwargs.keys()), cls_name, who))
+
     def _has_expression_priors(self):
         return any(par.lnprior is not None for par in self.parameters.values())
 
@@ -442,6 +479,26 @@ class Runner(object):
             pickle.dump(sampler.chain, f)
         with open("{0}_lnprob.pkl".format(prefix), "wb") as f:
             pickle.dump(sampler.lnprobability, f)
+
+    @staticmethod
+    def save_chain(sampler, filename="samplerchain.pkl"):
+        """Deprecated in the reference too (``analysis/runner.py:445-455``): forwards to
+        :meth:`save_current_status` with the prefix derived from `filename`."""
+        warnings.warn('Method Runner.save_chain() is deprecated. Use Runner.save_current_status() instead.',
+                      DeprecationWarning)
+        prefix = filename.split('.')[0]
+        if len(prefix) > 5 and prefix[-5:] == 'chain':
+            prefix = prefix[:-5]
+        Runner.save_current_status(sampler, prefix=prefix)
+
+    def sample_chain(self, chain, n_burn, n_samples=1):
+        """``analysis/runner.py:820-850``: `n_samples` parameter sets drawn at random (NumPy's global generator,
+        seeded by the constructor's `seed`) from the post-burn-in part of `chain`, each as the dictionary
+        :meth:`fetch_parameter_values` returns."""
+        chain = np.asarray(chain)
+        _parameters = np.reshape(chain[:, n_burn:], (-1, chain.shape[-1]))
+        indices = np.random.randint(0, _parameters.shape[0], (n_samples,))
+        return [self.fetch_parameter_values(row) for row in _parameters[indices]]
 
     @staticmethod
     def read_chain(filename):

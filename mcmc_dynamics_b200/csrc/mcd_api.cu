@@ -986,7 +986,9 @@ extern "C" int mcd_exchange_status(mcd_handle *h) {
 // ------------------------------------------------------------------------------------------
 // per-star lnlike (no_sum)
 // ------------------------------------------------------------------------------------------
-static int per_star(mcd_handle *h, const double *theta_dev, double *out_dev, int membership, cudaStream_t stream) {
+static int per_star(mcd_handle *h, const double *theta_dev, double *out_dev, int mode, cudaStream_t stream,
+                    double *out2_dev = nullptr) {
+    const int membership = mode == kPerStarMembership;
     LaunchParams p{};
     fill_params(h, p);
     p.n_walkers = 1;
@@ -1003,7 +1005,8 @@ static int per_star(mcd_handle *h, const double *theta_dev, double *out_dev, int
     }
     if (membership && h->var.background == MCD_BG_NONE) return fail(-1, "membership probabilities need a background component");
     if (h->n_segments > 1) return fail(-1, "per-star entry points are not available for segmented handles");
-    MCD_CUDA(launch_per_star(h->var, p, out_dev, membership, stream));
+    if (!theta_dev && h->desc.n_theta > 0) return fail(-1, "null theta");
+    MCD_CUDA(launch_per_star(h->var, p, out_dev, out2_dev, mode, stream));
     h->info.launches += 1;
     return 0;
 }
@@ -1011,34 +1014,51 @@ static int per_star(mcd_handle *h, const double *theta_dev, double *out_dev, int
 extern "C" int mcd_lnlike_per_star_device(mcd_handle *h, const double *theta_dev, double *out_dev, void *stream) {
     if (!h || !out_dev) return fail(-1, "null argument");
     MCD_CUDA(cudaSetDevice(h->device));
-    return per_star(h, theta_dev, out_dev, 0, static_cast<cudaStream_t>(stream));
+    return per_star(h, theta_dev, out_dev, kPerStarLnlike, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mcd_membership_per_star_device(mcd_handle *h, const double *theta_dev, double *out_dev, void *stream) {
     if (!h || !out_dev) return fail(-1, "null argument");
     MCD_CUDA(cudaSetDevice(h->device));
-    return per_star(h, theta_dev, out_dev, 1, static_cast<cudaStream_t>(stream));
+    return per_star(h, theta_dev, out_dev, kPerStarMembership, static_cast<cudaStream_t>(stream));
 }
 
-static int per_star_host(mcd_handle *h, const double *theta_host, double *out_host, int membership) {
-    if (!h || !out_host) return fail(-1, "null argument");
+extern "C" int mcd_model_per_star_device(mcd_handle *h, const double *theta_dev, double *v_los_dev, double *sigma_los_dev,
+                                         void *stream) {
+    if (!h) return fail(-1, "null argument");
+    if (!v_los_dev && !sigma_los_dev) return 0;
+    MCD_CUDA(cudaSetDevice(h->device));
+    return per_star(h, theta_dev, v_los_dev, kPerStarModel, static_cast<cudaStream_t>(stream), sigma_los_dev);
+}
+
+static int per_star_host(mcd_handle *h, const double *theta_host, double *out_host, int mode, double *out2_host = nullptr) {
+    if (!h || (!out_host && !out2_host)) return fail(-1, "null argument");
+    if (!theta_host && h->desc.n_theta > 0) return fail(-1, "null theta");
     MCD_CUDA(cudaSetDevice(h->device));
     if (h->n == 0) return 0;
     if (int rc = ensure_staging(h, (size_t)h->desc.n_theta, 1)) return rc;
-    if (!h->star_dev) MCD_CUDA(cudaMalloc(&h->star_dev, sizeof(double) * h->n));
+    if (!h->star_dev) MCD_CUDA(cudaMalloc(&h->star_dev, sizeof(double) * 2 * h->n));      // [n] values (+ [n] second curve)
     if (h->desc.n_theta) {
         memcpy(h->theta_pin, theta_host, sizeof(double) * h->desc.n_theta);
         MCD_CUDA(cudaMemcpyAsync(h->theta_dev, h->theta_pin, sizeof(double) * h->desc.n_theta, cudaMemcpyHostToDevice, h->stream));
     }
-    if (int rc = per_star(h, h->theta_dev, h->star_dev, membership, h->stream)) return rc;
-    MCD_CUDA(cudaMemcpyAsync(out_host, h->star_dev, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
+    double *first = out_host ? h->star_dev : nullptr, *second = out2_host ? h->star_dev + h->n : nullptr;
+    if (int rc = per_star(h, h->theta_dev, first, mode, h->stream, second)) return rc;
+    if (out_host) MCD_CUDA(cudaMemcpyAsync(out_host, first, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
+    if (out2_host) MCD_CUDA(cudaMemcpyAsync(out2_host, second, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
     MCD_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
 extern "C" int mcd_lnlike_per_star(mcd_handle *h, const double *theta_host, double *out_host) {
-    return per_star_host(h, theta_host, out_host, 0);
+    if (!out_host) return fail(-1, "null argument");
+    return per_star_host(h, theta_host, out_host, kPerStarLnlike);
 }
 extern "C" int mcd_membership_per_star(mcd_handle *h, const double *theta_host, double *out_host) {
-    return per_star_host(h, theta_host, out_host, 1);
+    if (!out_host) return fail(-1, "null argument");
+    return per_star_host(h, theta_host, out_host, kPerStarMembership);
+}
+extern "C" int mcd_model_per_star(mcd_handle *h, const double *theta_host, double *v_los_host, double *sigma_los_host) {
+    if (h && !v_los_host && !sigma_los_host) return 0;
+    return per_star_host(h, theta_host, v_los_host, kPerStarModel, sigma_los_host);
 }

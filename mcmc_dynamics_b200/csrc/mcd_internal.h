@@ -165,7 +165,10 @@ cudaError_t launch_pack(const PackParams &p, cudaStream_t stream);
 cudaError_t launch_lnlike(const Variant &v, const LaunchParams &p, cudaStream_t stream, const ThetaBlock *inline_theta = nullptr);
 // per-star lnlike (membership = 0) or membership probability (1) of walker 0 of p.theta into out[N]
 // (always PLAIN arithmetic)
-cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out, int membership, cudaStream_t stream);
+// what the per-star kernel writes: lnlike (no_sum), membership probability, or the model curves (v_los, sigma_los)
+enum { kPerStarLnlike = 0, kPerStarMembership = 1, kPerStarModel = 2 };
+cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out, double *out2, int mode,
+                            cudaStream_t stream);
 // resident-chain kernel: shared memory it needs for this problem, or 0 if the problem does not fit
 size_t chain_shared_bytes(const Variant &v, long long stars_per_cta, int n_walkers, int n_theta);
 cudaError_t launch_chain(const Variant &v, const LaunchParams &p, const ChainParams &c, size_t smem, cudaStream_t stream);

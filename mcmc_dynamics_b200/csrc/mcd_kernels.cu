@@ -354,7 +354,8 @@ template <int BG>
 struct Accum<BG, MCD_MATH_PLAIN> {
     double sum;
     double pmember;     // a-posteriori membership of the last star (per-star kernel only; dead elsewhere)
-    __device__ __forceinline__ void reset() { sum = 0.0; pmember = 1.0; }
+    double vlos, sig2;  // model velocity and squared model dispersion of the last star (per-star kernel only)
+    __device__ __forceinline__ void reset() { sum = 0.0; pmember = 1.0; vlos = 0.0; sig2 = 0.0; }
     __device__ __forceinline__ void end_group() {}
     __device__ __forceinline__ void end_tile() {}
     __device__ __forceinline__ double value() { return sum; }
@@ -540,6 +541,8 @@ __device__ __forceinline__ void term(const Walker &W, const Star<total_columns(R
             vlos = W.vsys + num;                                      // constant.py:111
             sig2 = W.s2;                                              // constant.py:74
         }
+        A.vlos = vlos;
+        A.sig2 = sig2;
         const double norm = e2 + sig2;                                // runner.py:261
         const double resid = v - vlos;
         const double lm = -0.5 * log(kTwoPi * norm) + (-0.5 * (resid * resid) / norm);   // runner.py:262-271
@@ -1502,12 +1505,15 @@ __global__ void __launch_bounds__(kChainBlock) chain_kernel(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------
-// per-star lnlike of one parameter vector (`no_sum=True`, model.py:565,620-621) or, with
-// `membership`, the a-posteriori membership probability of every star at that parameter vector
-// (constant.py:366-374, model.py:458-510,625-687)
+// per-star lnlike of one parameter vector (`no_sum=True`, model.py:565,620-621); with mode
+// kPerStarMembership the a-posteriori membership probability of every star at that parameter vector
+// (constant.py:366-374, model.py:458-510,625-687); with mode kPerStarModel the model curves themselves,
+// v_los into `out` and sigma_los into `out2` (rotation_model / dispersion_model, constant.py:52-111,
+// model.py:93-180; either pointer may be null)
 // ------------------------------------------------------------------------------------------
 template <int ROT, int FREE, int BG>
-__global__ void per_star_kernel(const __grid_constant__ LaunchParams P, double *__restrict__ out, int membership) {
+__global__ void per_star_kernel(const __grid_constant__ LaunchParams P, double *__restrict__ out,
+                                double *__restrict__ out2, int mode) {
     constexpr int NC = total_columns(ROT, FREE, BG);
     __shared__ Walker Ws;
     if (threadIdx.x == 0) load_walker<ROT, FREE, BG>(P, P.theta, Ws);
@@ -1523,7 +1529,17 @@ __global__ void per_star_kernel(const __grid_constant__ LaunchParams P, double *
     A.reset();
     const Walker W = Ws;
     term<ROT, FREE, BG, MCD_MATH_PLAIN>(W, S, A);
-    out[i] = membership ? A.pmember : A.value();
+    if (mode == kPerStarModel) {
+        if (out) out[i] = A.vlos;
+        if (out2) {
+            // the curves carry the sign of sigma_max (constant.py:74, model.py:128); the walker constants keep its square
+            const int slot = P.slot[MCD_P_SIGMA_MAX];
+            const double sigma_max = slot >= 0 ? P.theta[slot] * P.scale[MCD_P_SIGMA_MAX] : P.fixed_scaled[MCD_P_SIGMA_MAX];
+            out2[i] = copysign(sqrt(A.sig2), sigma_max);
+        }
+    } else {
+        out[i] = mode == kPerStarMembership ? A.pmember : A.value();
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1611,16 +1627,17 @@ cudaError_t launch_chain_plain(const Variant &v, const LaunchParams &p, const Ch
 }
 
 template <int ROT, int FREE, int BG, int MATH_UNUSED>
-static cudaError_t per_star_one(const LaunchParams &p, double *out, int membership, cudaStream_t stream) {
+static cudaError_t per_star_one(const LaunchParams &p, double *out, double *out2, int mode, cudaStream_t stream) {
     if (p.n_stars <= 0) return cudaSuccess;
     const int block = 256;
     const long long grid = (p.n_stars + block - 1) / block;
-    per_star_kernel<ROT, FREE, BG><<<(unsigned)grid, block, 0, stream>>>(p, out, membership);
+    per_star_kernel<ROT, FREE, BG><<<(unsigned)grid, block, 0, stream>>>(p, out, out2, mode);
     return cudaGetLastError();
 }
 
-cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out, int membership, cudaStream_t stream) {
-    MCD_DISPATCH_GEO(MCD_MATH_PLAIN, per_star_one, p, out, membership, stream)
+cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out, double *out2, int mode,
+                            cudaStream_t stream) {
+    MCD_DISPATCH_GEO(MCD_MATH_PLAIN, per_star_one, p, out, out2, mode, stream)
 }
 #endif
 #endif  // MCD_TU_PART != 0

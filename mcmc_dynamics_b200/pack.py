@@ -241,6 +241,17 @@ class PackedModel(object):
                                                         _native.as_double_ptr(out)))
         return out
 
+    def model_per_star(self, theta):
+        """``(v_los, sigma_los)`` of every star in km/s for ONE parameter vector (``mcd_model_per_star``)."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1)
+        if theta.size != self.n_theta:
+            raise ValueError('theta must have {0} entries'.format(self.n_theta))
+        v_los = np.empty(self.n_stars, dtype=np.float64)
+        sigma_los = np.empty(self.n_stars, dtype=np.float64)
+        _native.check(self._lib.mcd_model_per_star(self.handle, _native.as_double_ptr(theta),
+                                                   _native.as_double_ptr(v_los), _native.as_double_ptr(sigma_los)))
+        return v_los, sigma_los
+
     # ---- device tensors (torch operator library; current CUDA stream) ----------------------
     def lnprob_tensor(self, theta):
         return _native.load_torch_ops().lnprob(self.handle.value, theta)

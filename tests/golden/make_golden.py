@@ -154,6 +154,17 @@ def main():
         theta = thetas(truth, names, n_theta, seed=len(cases) + 1)
         for (row, pname, value) in (theta_edits or []):
             theta[row, names.index(pname)] = value
+        # the model curves themselves at theta[0], routed exactly as <Model>.lnlike routes them; evaluated first
+        # because fetch_parameter_values writes the values into model.parameters (analysis/runner.py:163-176)
+        # and the descriptor recorded below must see the state the likelihood calls leave behind
+        # (constant.py:137-151, model.py:205-220)
+        par0 = model.fetch_parameter_values(theta[0])
+        with np.errstate(all='ignore'):
+            v_curve = model.rotation_model(**{k: v for k, v in par0.items() if k in model.rotation_parameters.keys()})
+            s_curve = model.dispersion_model(**{k: v for k, v in par0.items() if k in model.dispersion_parameters.keys()})
+        kms = u.km / u.s
+        curves = {'v_los': [float(x) for x in np.asarray(u.Quantity(v_curve).to(kms).value)],
+                  'sigma_los': [float(x) for x in np.asarray(u.Quantity(s_curve).to(kms).value)]}
         out = {'lnprior': [], 'lnlike': [], 'lnprob': []}
         with np.errstate(all='ignore'):
             for row in theta:
@@ -200,6 +211,7 @@ def main():
         import reference_binding
         case['binding_descriptor'] = reference_binding.summary(reference_binding.describe(model)[0])
         case['model_parameters'] = list(model.MODEL_PARAMETERS)
+        case['model_curves_theta0'] = curves
         if model.lnlike_background is not None:
             lbg = model.lnlike_background
             case['lnlike_background'] = [float(x) for x in np.asarray(getattr(lbg, 'value', lbg))]

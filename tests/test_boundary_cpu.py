@@ -299,6 +299,37 @@ def test_host_sampler_error_semantics_and_resume():
         sampler.HostEnsembleSampler(12, 2, lnprob, seed=5).run_mcmc(start, 1, log_prob0=np.full(12, np.nan))
 
 
+def test_chain_helpers_follow_the_reference(tmp_path):
+    """``sample_chain`` (analysis/runner.py:820-850), the deprecated ``save_chain`` (:445-455) and the curve
+    signatures the reference keeps on its model objects (constant.py:49-50, model.py:90-91): host-side only."""
+    data, truth = synthetic.mock_cluster(40, seed=3)
+    model = ModelFit(data, seed=7)
+    model.parameters['ra_center'].set(value=truth['ra_center'], fixed=True)
+    model.parameters['dec_center'].set(value=truth['dec_center'], fixed=True)
+    assert list(model.rotation_parameters) == ['v_sys', 'v_maxx', 'v_maxy', 'ra_center', 'dec_center', 'r_peak', 'kwargs']
+    assert list(model.dispersion_parameters) == ['sigma_max', 'ra_center', 'dec_center', 'a', 'kwargs']
+    assert list(ConstantFit(data).rotation_parameters) == ['v_sys', 'v_maxx', 'v_maxy', 'ra_center', 'dec_center', 'kwargs']
+    n_free = model.n_fitted_parameters
+    chain = np.arange(5 * 9 * n_free, dtype=np.float64).reshape(5, 9, n_free)        # [walkers, steps, free]
+    np.random.seed(11)
+    samples = model.sample_chain(chain, n_burn=4, n_samples=6)
+    np.random.seed(11)
+    rows = chain[:, 4:].reshape(-1, n_free)[np.random.randint(0, 25, (6,))]
+    assert len(samples) == 6
+    for sample, row in zip(samples, rows):
+        assert list(sample) == list(model.parameters)
+        assert [sample[name].value for name in model.fitted_parameters] == list(row)
+        assert sample['ra_center'].value == truth['ra_center'] and str(sample['a'].unit) == 'arcsec'
+
+    class Stub(object):
+        chain = np.zeros((2, 3, n_free))
+        lnprobability = np.ones((2, 3))
+    with pytest.warns(DeprecationWarning):
+        model.save_chain(Stub(), filename=str(tmp_path / 'runchain.pkl'))
+    assert np.array_equal(model.read_chain(str(tmp_path / 'run_chain.pkl')), Stub.chain)
+    assert np.array_equal(model.read_chain(str(tmp_path / 'run_lnprob.pkl')), Stub.lnprobability)
+
+
 def test_radial_bins_partition():
     data, truth = synthetic.mock_cluster(600, seed=2)
     data.make_radial_bins(truth['ra_center'], truth['dec_center'], nstars=50, dlogr=0.1)

@@ -38,6 +38,18 @@ def test_oracle_reproduces_reference_outputs(case):
             assert np.allclose(oracle.membership(theta[0]), case['membership_theta0'], rtol=1e-11, atol=1e-15)
 
 
+@pytest.mark.parametrize('case', GOLDEN['cases'], ids=[c['name'] for c in GOLDEN['cases']])
+def test_oracle_model_curves_match_the_reference(case):
+    """rotation_model / dispersion_model of the reference's own classes at theta[0] (constant.py:52-111,
+    model.py:93-180), km/s per star."""
+    oracle = golden_util.oracle_for_case(case)
+    v_los, sigma_los = oracle._models(oracle.fetch_parameter_values(np.asarray(case['theta'][0])))
+    want = case['model_curves_theta0']
+    assert len(want['v_los']) == len(want['sigma_los']) == oracle.n_data
+    assert np.allclose(v_los, want['v_los'], rtol=1e-12, atol=1e-13)
+    assert np.allclose(sigma_los, want['sigma_los'], rtol=1e-12, atol=0)
+
+
 def test_membership_vectors_cover_the_three_classes_that_define_them():
     have = {c['class'] for c in GOLDEN['cases'] if 'membership_theta0' in c}
     assert have == {'ConstantFitGB', 'ModelFitGB', 'ModelFitConstantBackground'}

@@ -38,3 +38,38 @@ def test_cuda_reproduces_reference_outputs(case, math_mode):
         got = model.calculate_membership_probabilities(chain, n_burn=1)
         assert np.allclose(got, case['membership_theta0'], rtol=1e-9, atol=1e-13)
         assert np.all((got >= 0) & (got <= 1))
+
+
+def _curve_kwargs(model, row):
+    """name -> value for rotation_model / dispersion_model, routed as <Model>.lnlike routes them
+    (constant.py:137-147): sampled parameters from `row`, fixed ones at their value, each with its unit."""
+    par = model.fetch_parameter_values(row)
+    rot = {k: v for k, v in par.items() if k in model.rotation_parameters}
+    disp = {k: v for k, v in par.items() if k in model.dispersion_parameters}
+    return rot, disp
+
+
+@pytest.mark.parametrize('math_mode', ['fast', 'plain'])
+@pytest.mark.parametrize('case', GOLDEN['cases'], ids=[c['name'] for c in GOLDEN['cases']])
+def test_model_curves_reproduce_the_reference(case, math_mode):
+    """`rotation_model` / `dispersion_model` (per-star kernel, `mcd_model_per_star`) against the curves the
+    reference's own classes return for theta[0]."""
+    model = golden_util.product_for_case(case, math_mode)
+    rot, disp = _curve_kwargs(model, np.asarray(case['theta'][0]))
+    want = case['model_curves_theta0']
+    v_los = model.rotation_model(**rot)
+    sigma_los = model.dispersion_model(**disp)
+    assert str(v_los.unit) == str(sigma_los.unit) == 'km / s'
+    assert np.allclose(v_los.value, want['v_los'], rtol=1e-9, atol=1e-11)
+    assert np.allclose(sigma_los.value, want['sigma_los'], rtol=1e-9, atol=0)
+    # plain numbers are taken to be in the parameter's own unit, as the reference takes them
+    bare = {k: getattr(v, 'value', v) for k, v in rot.items()}
+    assert np.array_equal(model.rotation_model(**bare).value, v_los.value)
+    with pytest.raises(IOError, match='Unknown keyword argument'):
+        model.rotation_model(nonsense=1.0, **rot)
+    with pytest.raises(IOError, match='Unknown keyword argument'):
+        model.dispersion_model(nonsense=1.0, **disp)
+    if not case['free_centre']:
+        moved = dict(rot, ra_center=getattr(rot['ra_center'], 'value', rot['ra_center']) + 0.01)
+        with pytest.raises(ValueError, match='is fixed at'):
+            model.rotation_model(**moved)
