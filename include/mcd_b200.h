@@ -202,6 +202,13 @@ int mcd_model_per_star(mcd_handle *h, const double *theta_host, double *v_los_ho
 int mcd_model_per_star_device(mcd_handle *h, const double *theta_dev, double *v_los_dev, double *sigma_los_dev,
                               void *stream);
 
+/* Runner._calculate_lnlike(v_los, sigma_los) (analysis/runner.py:240-286) for model curves the CALLER computed,
+ * e.g. a user-defined model class on top of Runner: the Gaussian sum (runner.py:264-271) or, when the handle was
+ * packed with pmember and lnlike_background (MCD_BG_FIXED_PMEMBER), the max-shifted mixture (runner.py:272-286).
+ * v_los[N], sigma_los[N] in km/s, HOST arrays; out_host: one double.  Not available for the classes with a fitted
+ * background fraction (they do not go through _calculate_lnlike in the reference either). */
+int mcd_calculate_lnlike(mcd_handle *h, const double *v_los_host, const double *sigma_los_host, double *out_host);
+
 /* Background precompute: SingleStars.__call__ (background/single_stars.py:42-77) without the
  * M x N intermediate.  v_bg[M], v[N], verr[N] are HOST arrays; out[N]. */
 int mcd_single_stars_lnlike(int32_t device, const double *v_bg, int64_t m, const double *v, const double *verr,

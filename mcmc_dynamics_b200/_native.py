@@ -83,6 +83,7 @@ SYMBOLS = {
     'mcd_membership_per_star_device': (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     'mcd_model_per_star': (ctypes.c_int, [_vp, _c_double_p, _c_double_p, _c_double_p]),
     'mcd_model_per_star_device': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    'mcd_calculate_lnlike': (ctypes.c_int, [_vp, _c_double_p, _c_double_p, _c_double_p]),
     'mcd_single_stars_lnlike': (ctypes.c_int, [ctypes.c_int32, _c_double_p, ctypes.c_int64, _c_double_p, _c_double_p,
                                                ctypes.c_int64, ctypes.c_double, _c_double_p]),
     'mcd_single_stars_lnlike_device': (ctypes.c_int, [ctypes.c_int32, _vp, ctypes.c_int64, _vp, _vp, ctypes.c_int64,

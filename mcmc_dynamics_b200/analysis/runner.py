@@ -370,6 +370,16 @@ class Runner(object):
             raise IOError('Unknown keyword argument(s) "{0}" for method {1}.{2}.'.format(
                 ', '.join(kwargs.keys()), cls_name, who))
 
+    def _calculate_lnlike(self, v_los, sigma_los):
+        """``analysis/runner.py:240-286``: the log-likelihood of the data for model curves computed by the caller
+        (the hook a user-defined model class builds its ``lnlike`` on): Gaussian sum, or the mixture with the
+        fixed background column when a ``background=`` object was given.  `v_los`, `sigma_los`: one value per
+        star, quantities or plain numbers in km/s.  One reduction launch over the resident ``v`` / ``verr``
+        (/ ``pmember`` / ``lnlike_background``) columns; the model classes of this package never call it --
+        their curves are evaluated inside the fused kernel."""
+        packed = self.pack()
+        return packed.calculate_lnlike(u.strip(v_los, u.km_s), u.strip(sigma_los, u.km_s))
+
     def _has_expression_priors(self):
         return any(par.lnprior is not None for par in self.parameters.values())
 

@@ -1050,6 +1050,40 @@ static int per_star_host(mcd_handle *h, const double *theta_host, double *out_ho
     return 0;
 }
 
+// Runner._calculate_lnlike(v_los, sigma_los) for curves computed by the caller (analysis/runner.py:240-286)
+extern "C" int mcd_calculate_lnlike(mcd_handle *h, const double *v_los_host, const double *sigma_los_host, double *out_host) {
+    if (!h || !out_host) return fail(-1, "null argument");
+    if (h->n > 0 && (!v_los_host || !sigma_los_host)) return fail(-1, "null model curve");
+    if (h->n_segments > 1) return fail(-1, "mcd_calculate_lnlike is not available for segmented handles");
+    const int bg = h->var.background;
+    if (bg == MCD_BG_FIXED_DENSITY || bg == MCD_BG_GAUSSIAN)
+        return fail(-1, "the classes with a fitted background fraction do not use _calculate_lnlike (model.py:565-623, "
+                        "constant.py:326-364)");
+    MCD_CUDA(cudaSetDevice(h->device));
+    if (h->n == 0) {            // np.sum over nothing
+        *out_host = 0.0;
+        return 0;
+    }
+    if (int rc = order_on_stream(h, h->stream)) return rc;
+    const int blocks = curve_lnlike_blocks(h->n, h->sm_count);
+    double *buf = nullptr;      // [n] v_los | [n] sigma_los | [blocks] partial sums | result
+    const size_t count = 2 * (size_t)h->n + (size_t)blocks + 1;
+    MCD_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&buf), sizeof(double) * count, h->stream));
+    double *v_los = buf, *sigma_los = buf + h->n, *partial = buf + 2 * h->n, *out = partial + blocks;
+    cudaError_t err = cudaMemcpyAsync(v_los, v_los_host, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(sigma_los, sigma_los_host, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream);
+    const bool mixture = bg == MCD_BG_FIXED_PMEMBER;
+    if (err == cudaSuccess)
+        err = launch_curve_lnlike(h->raw[RAW_V], h->raw[RAW_VERR], mixture ? h->raw[RAW_PMEMBER] : nullptr,
+                                  mixture ? h->raw[RAW_LBG] : nullptr, v_los, sigma_los, h->n, partial, out, h->sm_count, h->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(out_host, out, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    cudaFreeAsync(buf, h->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(h->stream);
+    if (err != cudaSuccess) return fail(-2, "mcd_calculate_lnlike: %s", cudaGetErrorString(err));
+    h->info.launches += 2;
+    return 0;
+}
+
 extern "C" int mcd_lnlike_per_star(mcd_handle *h, const double *theta_host, double *out_host) {
     if (!out_host) return fail(-1, "null argument");
     return per_star_host(h, theta_host, out_host, kPerStarLnlike);

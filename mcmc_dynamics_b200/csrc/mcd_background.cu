@@ -96,6 +96,55 @@ __global__ void gaussian_kernel(const double *__restrict__ v, const double *__re
     out[i] = -0.5 * log(2. * M_PI * norm) + exponent;                 // gaussian.py:28
 }
 
+// Runner._calculate_lnlike (analysis/runner.py:240-286): the log-likelihood of the catalogue for model curves
+// v_los[N], sigma_los[N] that the CALLER computed (a user-defined model on top of Runner): Gaussian sum, or the
+// max-shifted two-component mixture when the model carries a fixed background column.  Library log / exp /
+// division as in the reference; per-thread grid-stride sums, a fixed-order block reduction, per-block partials
+// added by one block -- the result does not depend on scheduling.
+constexpr int kCurveBlock = 256;
+
+__device__ __forceinline__ double block_sum(double x, double *red) {
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+    __syncthreads();
+    double total = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < kCurveBlock / 32; ++w) total += red[w];
+    return total;            // valid in thread 0
+}
+
+__global__ void __launch_bounds__(kCurveBlock) curve_lnlike_kernel(
+    const double *__restrict__ v, const double *__restrict__ verr, const double *__restrict__ pmember,
+    const double *__restrict__ lbg, const double *__restrict__ v_los, const double *__restrict__ sigma_los, long long n,
+    double *__restrict__ partial) {
+    __shared__ double red[kCurveBlock / 32];
+    double sum = 0.0;
+    for (long long i = (long long)blockIdx.x * kCurveBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kCurveBlock) {
+        const double norm = verr[i] * verr[i] + sigma_los[i] * sigma_los[i];      // runner.py:261
+        const double d = v[i] - v_los[i];
+        const double exponent = -0.5 * (d * d) / norm;                            // runner.py:262
+        const double lm = -0.5 * log(mcd::kTwoPi * norm) + exponent;              // runner.py:269-270,280
+        if (!lbg) {
+            sum += lm;
+        } else {
+            const double lb = lbg[i], m = pmember[i];
+            const double mx = fmax(lm, lb);                                       // runner.py:282
+            sum += mx + log(m * exp(lm - mx) + (1.0 - m) * exp(lb - mx));         // runner.py:283-284
+        }
+    }
+    const double total = block_sum(sum, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kCurveBlock) curve_sum_kernel(const double *__restrict__ partial, int count,
+                                                                double *__restrict__ out) {
+    __shared__ double red[kCurveBlock / 32];
+    double sum = 0.0;
+    for (int i = threadIdx.x; i < count; i += kCurveBlock) sum += partial[i];
+    const double total = block_sum(sum, red);
+    if (threadIdx.x == 0) out[0] = total;
+}
+
 // Stream-ordered scratch of one call: everything is allocated, used and freed on one stream, so a call
 // costs no device-wide synchronisation and no synchronous cudaMalloc/cudaFree.
 struct CallScratch {
@@ -141,6 +190,24 @@ cudaError_t mcd::launch_single_stars(const double *v_bg_sorted_dev, long long m,
     const long long grid = (n + per_block - 1) / per_block;
     single_stars_kernel<<<(unsigned)grid, kBgBlock, 0, stream>>>(v_bg_sorted_dev, m, v_dev, verr_dev, n, sigma_int, lanes,
                                                                  out_dev);
+    return cudaGetLastError();
+}
+
+// `scratch_dev` holds curve_lnlike_blocks(n, sm_count) doubles; `out_dev` one
+int mcd::curve_lnlike_blocks(long long n, int sm_count) {
+    const long long want = (n + kCurveBlock - 1) / kCurveBlock;
+    return (int)std::max<long long>(1, std::min<long long>(want, (long long)std::max(1, sm_count) * 8));
+}
+
+cudaError_t mcd::launch_curve_lnlike(const double *v_dev, const double *verr_dev, const double *pmember_dev,
+                                     const double *lbg_dev, const double *v_los_dev, const double *sigma_los_dev, long long n,
+                                     double *scratch_dev, double *out_dev, int sm_count, cudaStream_t stream) {
+    const int blocks = curve_lnlike_blocks(n, sm_count);
+    curve_lnlike_kernel<<<blocks, kCurveBlock, 0, stream>>>(v_dev, verr_dev, pmember_dev, lbg_dev, v_los_dev, sigma_los_dev,
+                                                            n, scratch_dev);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    curve_sum_kernel<<<1, kCurveBlock, 0, stream>>>(scratch_dev, blocks, out_dev);
     return cudaGetLastError();
 }
 

@@ -173,6 +173,11 @@ cudaError_t launch_per_star(const Variant &v, const LaunchParams &p, double *out
 size_t chain_shared_bytes(const Variant &v, long long stars_per_cta, int n_walkers, int n_theta);
 cudaError_t launch_chain(const Variant &v, const LaunchParams &p, const ChainParams &c, size_t smem, cudaStream_t stream);
 // SingleStars background column (mcd_background.cu): device pointers, v_bg sorted ascending
+// Runner._calculate_lnlike for caller-supplied model curves (csrc/mcd_background.cu)
+int curve_lnlike_blocks(long long n, int sm_count);
+cudaError_t launch_curve_lnlike(const double *v_dev, const double *verr_dev, const double *pmember_dev, const double *lbg_dev,
+                                const double *v_los_dev, const double *sigma_los_dev, long long n, double *scratch_dev,
+                                double *out_dev, int sm_count, cudaStream_t stream);
 cudaError_t launch_single_stars(const double *v_bg_sorted_dev, long long m, const double *v_dev, const double *verr_dev,
                                 long long n, double sigma_int, double *out_dev, int sm_count, cudaStream_t stream);
 // resident CTAs per SM of the lnlike kernel of this variant (occupancy API)

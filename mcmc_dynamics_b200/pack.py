@@ -252,6 +252,15 @@ class PackedModel(object):
                                                    _native.as_double_ptr(v_los), _native.as_double_ptr(sigma_los)))
         return v_los, sigma_los
 
+    def calculate_lnlike(self, v_los, sigma_los):
+        """``Runner._calculate_lnlike`` for curves computed by the caller, km/s per star (``mcd_calculate_lnlike``)."""
+        v_los = np.ascontiguousarray(np.broadcast_to(np.asarray(v_los, dtype=np.float64), (self.n_stars,)))
+        sigma_los = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma_los, dtype=np.float64), (self.n_stars,)))
+        out = ctypes.c_double(0.0)
+        _native.check(self._lib.mcd_calculate_lnlike(self.handle, _native.as_double_ptr(v_los),
+                                                     _native.as_double_ptr(sigma_los), ctypes.byref(out)))
+        return out.value
+
     # ---- device tensors (torch operator library; current CUDA stream) ----------------------
     def lnprob_tensor(self, theta):
         return _native.load_torch_ops().lnprob(self.handle.value, theta)
