@@ -59,8 +59,18 @@ def _worker(rank, world, port, out):
         want = make(columns).lnprob_many(theta)
         ok = bool(got[4] == -np.inf and np.all(np.isfinite(np.delete(got, 4)))
                   and np.allclose(np.delete(got, 4), np.delete(want, 4), rtol=1e-12, atol=0))
+        # the host stretch move over the sharded likelihood, as bench.py runs it at N > 1: every rank draws the
+        # same random numbers and sees the same all-reduced sums, so the replicas must stay in lock step
+        from mcmc_dynamics_b200 import sampler as samplers
+        start = synthetic.initial_ball(truth, names, 16, seed=2)
+        replica = samplers.HostEnsembleSampler(len(start), len(names), like.lnprob, seed=21)
+        replica.run_mcmc(start, 25)
+        whole = samplers.HostEnsembleSampler(len(start), len(names), make(columns).lnprob_many, seed=21)
+        whole.run_mcmc(start, 25)
+        ok = ok and bool(np.allclose(replica.lnprobability[:, 0], whole.lnprobability[:, 0], rtol=1e-12, atol=0))
+        digest = float(np.sum(replica.chain)) + float(np.sum(replica.lnprobability)) + float(replica.naccepted.sum())
         lo, hi = sharded.shard_range(1001, rank, world)
-        out.put((rank, ok, hi - lo))
+        out.put((rank, ok, hi - lo, digest))
     finally:
         dist.destroy_process_group()
 
@@ -91,6 +101,7 @@ def test_two_rank_gloo_allreduce_matches_whole_catalogue():
     assert sorted(r[0] for r in results) == [0, 1]
     assert all(r[1] for r in results)
     assert sorted(r[2] for r in results) == [500, 501]
+    assert results[0][3] == results[1][3]          # the two replicas of the host sampler took identical decisions
 
 
 @pytest.mark.gpu
