@@ -139,6 +139,56 @@ def test_fitted_parameters_and_batched_prior():
     assert np.array_equal(harness.oracle_for(model).lnprior_many(theta), lp)
 
 
+def test_batched_box_prior_matches_the_oracle_on_random_parameter_tables():
+    """Property test of the host prior (runner.py:206-217, parameter.py:691-692): random bounds, random
+    fixed / free splits -- fixed parameters are bounds-checked too -- and walkers placed inside, outside and
+    exactly on the bounds (inclusive)."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import harness
+    data, truth = synthetic.mock_cluster(12, seed=1)
+    names = ['v_sys', 'sigma_max', 'a', 'v_maxx', 'ra_center', 'dec_center', 'v_maxy', 'r_peak']
+
+    bound = st.one_of(st.just(None), st.floats(-50.0, 50.0, allow_nan=False).map(lambda x: round(x, 3)))
+    row = st.tuples(st.booleans(), bound, bound, st.sampled_from(['inside', 'below', 'above', 'at_min', 'at_max']))
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(row, min_size=len(names), max_size=len(names)), st.integers(0, 2 ** 31 - 1))
+    def check(rows, seed):
+        rng = np.random.default_rng(seed)
+        model = ModelFit(data)
+        placements = {}
+        for name, (fixed, lo, hi, where) in zip(names, rows):
+            lo, hi = (-np.inf if lo is None else lo), (np.inf if hi is None else hi)
+            if lo > hi:
+                lo, hi = hi, lo
+            if lo == hi:                                    # min == max raises, as in the reference (parameter.py:800-801)
+                hi = lo + 1.0
+            centre = 0.5 * (lo + hi) if np.isfinite(lo) and np.isfinite(hi) else (lo + 1.0 if np.isfinite(lo) else (
+                hi - 1.0 if np.isfinite(hi) else 0.0))
+            model.parameters[name].set(value=centre, min=lo, max=hi, fixed=fixed)
+            placements[name] = (lo, hi, centre, where)
+        if model.n_fitted_parameters == 0:
+            return
+        theta = np.empty((6, model.n_fitted_parameters))
+        for j, name in enumerate(model.fitted_parameters):
+            lo, hi, centre, where = placements[name]
+            theta[:, j] = centre
+            k = int(rng.integers(0, 6))                     # one walker per parameter leaves the middle
+            if where == 'below' and np.isfinite(lo):
+                theta[k, j] = lo - abs(lo) * 1e-12 - 1e-9
+            elif where == 'above' and np.isfinite(hi):
+                theta[k, j] = hi + abs(hi) * 1e-12 + 1e-9
+            elif where == 'at_min' and np.isfinite(lo):
+                theta[k, j] = lo
+            elif where == 'at_max' and np.isfinite(hi):
+                theta[k, j] = hi
+        got = model.lnprior(theta)
+        want = harness.oracle_for(model).lnprior_many(theta)
+        assert np.array_equal(got, want), (rows, theta, got, want)
+        assert model.lnprior(theta[0]) == want[0]
+    check()
+
+
 def test_descriptor_routing_and_units():
     data, truth = synthetic.mock_cluster(20, seed=1)
     model = ModelFitGB(synthetic.reader_from_columns(dict(
